@@ -1,0 +1,168 @@
+/*
+ * scmgan.h - C ABI of libscmgan.so: hand-written sm_100a kernels behind the scm-gan world-model training step.
+ *
+ * The reference (LilJing/scm-gan) is pure PyTorch and has no FFI of its own; each entry point below names the
+ * reference call site whose library kernels (cuDNN / cuBLAS / ATen) it replaces.  The host side that binds
+ * these (scm_gan_b200/_lib.py, ctypes) mirrors reference models.py / spectral_normalization.py one level up.
+ *
+ * Conventions
+ *  - every pointer is a CUDA device pointer unless the name ends in _host; buffers are owned by the caller
+ *    (torch's caching allocator); the library allocates nothing persistent and never synchronises;
+ *  - every call enqueues work on `stream` and is CUDA-graph-capture safe;
+ *  - return value: 0 = ok, SCMGAN_EINVAL (-1) bad argument, SCMGAN_EUNSUPPORTED (-2) shape not supported,
+ *    SCMGAN_ECUDA (-3) CUDA runtime/driver error; scmgan_last_error() returns a thread-local message;
+ *  - "plane": bf16 activation tensor [B][H+2][W+2][Cs] (NHWC + 1-pixel halo, Cs multiple of 8).  The halo
+ *    holds zeros (zero padding: Encoder/Decoder/RewardPredictor) or the wrapped border (the legacy circular
+ *    pad-1 of Transition, reference models.py:51-56 under torch<=1.4 semantics).
+ */
+#ifndef SCMGAN_H_
+#define SCMGAN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCMGAN_OK 0
+#define SCMGAN_EINVAL (-1)
+#define SCMGAN_EUNSUPPORTED (-2)
+#define SCMGAN_ECUDA (-3)
+
+#define SCMGAN_ACT_NONE 0
+#define SCMGAN_ACT_LRELU 1
+#define SCMGAN_ACT_SIGMOID 2
+
+typedef void* scmgan_stream_t; /* cudaStream_t */
+
+int scmgan_version(void);
+const char* scmgan_last_error(void);
+int scmgan_num_sms(void);
+
+/* fp32 NCHW tensor (batch stride src_bstride elements, channel stride H*W) -> plane channels
+ * [c_off, c_off+c_pad), zero-filling channels >= C; halo = wrap (1) or zeros (0).
+ * Replaces x.view / torch.cat / F.pad(mode='circular') copies: reference models.py:69-73, 143, 76-103. */
+int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
+                     int c_off, int c_pad, int wrap, scmgan_stream_t stream);
+
+/* Weight packing fp32 parameter -> bf16 [9][n_pad][k_pad] GEMM operand, optionally divided by *sigma
+ * (the `w / sigma` of reference spectral_normalization.py:35).
+ *   out[tap][n][k] = w[n*s_n + (k+k_src_off)*s_k + (flip ? 8-tap : tap)] / sigma */
+typedef struct {
+    const float* w;
+    void* out;
+    const float* sigma; /* device scalar or NULL */
+    int n_pad, k_pad, n_valid, k_valid;
+    long long s_n, s_k;
+    int k_src_off;
+    int flip;
+} scmgan_pack_job;
+int scmgan_pack_weights(int count, const scmgan_pack_job* jobs_host, scmgan_stream_t stream);
+
+/* 3x3 stride-1 same-size convolution over a plane as a tcgen05 implicit GEMM, with fused epilogue.
+ * Forward of nn.Conv2d / nn.ConvTranspose2d(stride 1, pad 1) (reference models.py:76-103, 145-154, 274-279)
+ * and, with flipped/transposed packed weights, their data gradient (cuDNN dgrad under main.py:285).
+ * Epilogue: y = acc*scale + bias[n] + sample_bias[b][n]; y += add; y = act(y); y *= lrelu'(gate);
+ *   -> bf16 plane `out` (interior + wrapped halo, or zero halo) and/or fp32 NCHW `out_f32`
+ *   -> optional Bernoulli head: sample_out = (uniforms < y) or (y > 0.5) when uniforms == NULL
+ *      (reference models.py:30-40, 107-112). */
+typedef struct {
+    int B, H, W;
+    const void* x; /* input plane */
+    int x_cs, x_c_off, cin; /* channel stride, first channel, channel count (multiple of 16) */
+    const void* w;          /* packed weights [9][n][cin] */
+    int n;                  /* GEMM N: multiple of 16, <= 256 */
+    float scale;
+    const float* bias;        /* [n] or NULL */
+    const float* sample_bias; /* [B][n] or NULL */
+    int act;
+    float slope;
+    void* out; /* bf16 plane or NULL */
+    int out_cs, out_c_off, wrap;
+    const void* add; /* bf16 plane or NULL */
+    int add_cs, add_c_off;
+    const void* gate; /* bf16 plane or NULL */
+    int gate_cs, gate_c_off;
+    float* out_f32; /* [B][n_valid][H][W] or NULL */
+    int n_valid;
+    float* sample_out;     /* [B][n_valid][H][W] or NULL */
+    const float* uniforms; /* [B][n_valid][H][W] or NULL */
+} scmgan_conv_desc;
+int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
+int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
+
+/* Weight gradient: g[co*g_s_co + ci*g_s_ci + tap'*g_s_tap] += scale * sum_interior dy[p][co] * x[p+tap][ci],
+ * tap' = flip ? 8-tap : tap.  g is fp32 and must be pre-initialised (atomically accumulated into).
+ * Replaces cuDNN wgrad under loss.backward() (reference main.py:285). */
+typedef struct {
+    int B, H, W;
+    const void* dy; /* gradient plane (only its interior is read) */
+    int dy_cs, dy_c_off, cout;
+    const void* x; /* input plane (halo included) */
+    int x_cs, x_c_off, cin;
+    float* g;
+    long long g_s_co, g_s_ci, g_s_tap;
+    int flip;
+    int co_valid, ci_valid;
+    float scale;
+} scmgan_wgrad_desc;
+int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* desc_host, scmgan_stream_t stream);
+
+/* S[b][c] += sum over the interior of plane channels [c_off, c_off+n); db[c] += the same summed over b.
+ * Bias gradients (cuDNN bias backward) and the folded action-channel gradient. */
+int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int H, int W, float* S, float* db,
+                        scmgan_stream_t stream);
+
+/* Spectral norm: one power iteration per wrapped conv (reference spectral_normalization.py:23-35);
+ * u, v updated in place, sigma written; u_save/v_save receive the post-update vectors for backward. */
+typedef struct {
+    const float* w;
+    float* u;
+    float* v;
+    float* sigma;
+    float* u_save;
+    float* v_save;
+    int rows, cols;
+} scmgan_sn_layer;
+int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers_host, scmgan_stream_t stream);
+
+/* dWbar = G/sigma - (<G,Wbar>/sigma^2) u v^T  (autograd of `w / sigma.expand_as(w)`, sigma = u.(W v)). */
+typedef struct {
+    const float* g;
+    const float* wbar;
+    const float* u;
+    const float* v;
+    const float* sigma;
+    float* dot; /* [1] scratch, zeroed by caller */
+    float* out;
+    int rows, cols;
+} scmgan_sn_bwd_layer;
+int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers_host, scmgan_stream_t stream);
+
+/* Folded action channels of Transition.conv1 (reference models.py:69-73). */
+int scmgan_action_bias(const float* wbar, const float* sigma, const float* bias, const float* act, int B, int Cout,
+                       int L, int A, float* out, scmgan_stream_t stream);
+int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L, int A, float* g,
+                        scmgan_stream_t stream);
+
+/* loss[0] += mean_b( mask[b] * mean_chw BCE(sigmoid(x), y) ); dx (optional) = d loss / d x.
+ * Fuses torch.sigmoid + F.binary_cross_entropy + means (reference main.py:188-197, 310-312). */
+int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
+                      float* loss, float* dx, scmgan_stream_t stream);
+
+/* clip_grad_value_ + Adam in one multi-tensor launch (reference main.py:287-296). */
+typedef struct {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int n;
+    float clip;
+} scmgan_adam_chunk;
+int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks_host, float lr, float beta1, float beta2, float eps,
+                     int step, const float* step_dev, float gscale, scmgan_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SCMGAN_H_ */

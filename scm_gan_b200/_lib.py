@@ -1,0 +1,113 @@
+"""ctypes binding of libscmgan.so (include/scmgan.h).
+
+This is the only place the shared library is touched.  There is deliberately no fallback: if the library is
+missing or a call fails, a RuntimeError is raised (the product path never routes through torch/CPU code).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libscmgan.so")
+
+ACT_NONE, ACT_LRELU, ACT_SIGMOID = 0, 1, 2
+
+c_f32p = C.c_void_p  # device pointers travel as integers
+
+
+class PackJob(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("sigma", C.c_void_p),
+                ("n_pad", C.c_int), ("k_pad", C.c_int), ("n_valid", C.c_int), ("k_valid", C.c_int),
+                ("s_n", C.c_longlong), ("s_k", C.c_longlong), ("k_src_off", C.c_int), ("flip", C.c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("x", C.c_void_p), ("x_cs", C.c_int), ("x_c_off", C.c_int), ("cin", C.c_int),
+                ("w", C.c_void_p), ("n", C.c_int),
+                ("scale", C.c_float), ("bias", C.c_void_p), ("sample_bias", C.c_void_p),
+                ("act", C.c_int), ("slope", C.c_float),
+                ("out", C.c_void_p), ("out_cs", C.c_int), ("out_c_off", C.c_int), ("wrap", C.c_int),
+                ("add", C.c_void_p), ("add_cs", C.c_int), ("add_c_off", C.c_int),
+                ("gate", C.c_void_p), ("gate_cs", C.c_int), ("gate_c_off", C.c_int),
+                ("out_f32", C.c_void_p), ("n_valid", C.c_int),
+                ("sample_out", C.c_void_p), ("uniforms", C.c_void_p)]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
+                ("dy", C.c_void_p), ("dy_cs", C.c_int), ("dy_c_off", C.c_int), ("cout", C.c_int),
+                ("x", C.c_void_p), ("x_cs", C.c_int), ("x_c_off", C.c_int), ("cin", C.c_int),
+                ("g", C.c_void_p), ("g_s_co", C.c_longlong), ("g_s_ci", C.c_longlong), ("g_s_tap", C.c_longlong),
+                ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float)]
+
+
+class SnLayer(C.Structure):
+    _fields_ = [("w", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("sigma", C.c_void_p),
+                ("u_save", C.c_void_p), ("v_save", C.c_void_p), ("rows", C.c_int), ("cols", C.c_int)]
+
+
+class SnBwdLayer(C.Structure):
+    _fields_ = [("g", C.c_void_p), ("wbar", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
+                ("sigma", C.c_void_p), ("dot", C.c_void_p), ("out", C.c_void_p),
+                ("rows", C.c_int), ("cols", C.c_int)]
+
+
+class AdamChunk(C.Structure):
+    _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
+                ("n", C.c_int), ("clip", C.c_float)]
+
+
+# name -> (restype, argtypes); must list every symbol include/scmgan.h declares (tests check this)
+SIGNATURES = {
+    "scmgan_version": (C.c_int, []),
+    "scmgan_last_error": (C.c_char_p, []),
+    "scmgan_num_sms": (C.c_int, []),
+    "scmgan_pack_nchw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scmgan_pack_weights": (C.c_int, [C.c_int, C.POINTER(PackJob), C.c_void_p]),
+    "scmgan_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "scmgan_conv3x3_dgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "scmgan_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "scmgan_plane_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_spectral_norm_fwd": (C.c_int, [C.c_int, C.POINTER(SnLayer), C.c_void_p]),
+    "scmgan_spectral_norm_bwd": (C.c_int, [C.c_int, C.POINTER(SnBwdLayer), C.c_void_p]),
+    "scmgan_action_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_void_p, C.c_void_p]),
+    "scmgan_action_wgrad": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                      C.c_void_p]),
+    "scmgan_bce_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_clip_adam": (C.c_int, [C.c_int, C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float,
+                                   C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libscmgan.so (once).  Raises RuntimeError when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(there is no non-CUDA fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = lib().scmgan_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (or None -> NULL)."""
+    return None if t is None else t.data_ptr()

@@ -1,0 +1,451 @@
+// C-ABI entry points of libscmgan.so (see include/scmgan.h).  Host-side only: argument validation,
+// TMA tensor-map encoding, launch-geometry selection, kernel launches.  No allocation, no synchronisation.
+#include "../../include/scmgan.h"
+#include "conv_igemm.cuh"
+#include "conv_wgrad.cuh"
+#include "elementwise.cuh"
+#include "host_util.cuh"
+
+#include <algorithm>
+#include <mutex>
+#include <string.h>
+
+namespace scm {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int cuda_fail(cudaError_t e, const char* what) {
+    set_error("CUDA error %d (%s) at %s", int(e), cudaGetErrorString(e), what);
+    return SCM_ECUDA;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available (no CUDA driver?)");
+        return SCM_ECUDA;
+    }
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[4];
+    cuuint32_t bx[5], es[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bx[i] = box[i];
+        es[i] = 1;
+    }
+    for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+    CUtensorMapSwizzle sw = CU_TENSOR_MAP_SWIZZLE_NONE;
+    if (swizzle_bytes == 32) sw = CU_TENSOR_MAP_SWIZZLE_32B;
+    else if (swizzle_bytes == 64) sw = CU_TENSOR_MAP_SWIZZLE_64B;
+    else if (swizzle_bytes == 128) sw = CU_TENSOR_MAP_SWIZZLE_128B;
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, cuuint32_t(rank), const_cast<void*>(base), gdim, gstr, bx,
+                    es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d (rank %d dims %llu,%llu box %u,%u swz %d)", int(r), rank,
+                  (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1], swizzle_bytes);
+        return SCM_ECUDA;
+    }
+    return SCM_OK;
+}
+
+int num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) sms = 148;
+    }
+    return sms;
+}
+
+constexpr int kSmemBudget = 200 * 1024;  // tiles; barriers/alignment slack on top (<= 227 KB per CTA)
+
+template <int CK>
+static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& P, cudaStream_t st) {
+    const int stage_bytes = IgemmCfg<CK>::kATileBytes + igemm_b_tile_bytes(P.n, CK);
+    int stages = std::min(kMaxStages, kSmemBudget / stage_bytes);
+    if (stages < 2) {
+        set_error("conv3x3: tile does not fit shared memory (n=%d ck=%d)", P.n, CK);
+        return SCM_EUNSUPPORTED;
+    }
+    const int smem = stages * stage_bytes + 1024 + 256;
+    static bool attr_set = false;  // per template instantiation
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      227 * 1024));
+        attr_set = true;
+    }
+    const int grid = std::min(P.num_tiles, num_sms());
+    conv3x3_igemm_kernel<CK><<<grid, kIgemmThreads, smem, st>>>(ta, tb, P, stages);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
+    SCM_REQUIRE(d != nullptr, "conv3x3: null descriptor");
+    SCM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "conv3x3: bad geometry B=%d H=%d W=%d", d->B, d->H, d->W);
+    SCM_REQUIRE(d->x && d->w, "conv3x3: null input/weight pointer");
+    SCM_REQUIRE(d->cin > 0 && d->cin % 16 == 0, "conv3x3: cin=%d must be a positive multiple of 16", d->cin);
+    SCM_REQUIRE(d->n >= 16 && d->n <= 256 && d->n % 16 == 0, "conv3x3: n=%d must be a multiple of 16 in [16,256]",
+                d->n);
+    SCM_REQUIRE(d->x_cs % 8 == 0 && d->x_c_off % 8 == 0 && d->x_c_off + d->cin <= d->x_cs,
+                "conv3x3: bad input channel window (cs=%d off=%d cin=%d)", d->x_cs, d->x_c_off, d->cin);
+    SCM_REQUIRE(d->out || d->out_f32, "conv3x3: no output requested");
+    if (d->out)
+        SCM_REQUIRE(d->out_cs % 8 == 0 && d->out_c_off % 8 == 0 && d->out_c_off + d->n <= d->out_cs,
+                    "conv3x3: bad output channel window (cs=%d off=%d n=%d)", d->out_cs, d->out_c_off, d->n);
+    if (d->add)
+        SCM_REQUIRE(d->add_cs % 8 == 0 && d->add_c_off % 8 == 0 && d->add_c_off + d->n <= d->add_cs,
+                    "conv3x3: bad add channel window");
+    if (d->gate)
+        SCM_REQUIRE(d->gate_cs % 8 == 0 && d->gate_c_off % 8 == 0 && d->gate_c_off + d->n <= d->gate_cs,
+                    "conv3x3: bad gate channel window");
+    if (d->out_f32) SCM_REQUIRE(d->n_valid > 0 && d->n_valid <= d->n, "conv3x3: bad n_valid=%d", d->n_valid);
+    SCM_REQUIRE(!d->sample_out || d->out_f32, "conv3x3: sample_out requires out_f32");
+
+    IgemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = d->B; P.H = d->H; P.W = d->W; P.Hp = d->H + 2; P.Wp = d->W + 2;
+    const long long rows = (long long)d->B * P.Hp * P.Wp;
+    SCM_REQUIRE(rows < (1LL << 31) - 256, "conv3x3: plane too large");
+    P.rows = int(rows);
+    P.num_tiles = int((rows + 127) / 128);
+    P.n = d->n;
+    const int CK = (d->cin % 64 == 0) ? 64 : 16;
+    P.cin_chunks = d->cin / CK;
+    P.a_c_off = d->x_c_off;
+    P.scale = d->scale; P.bias = d->bias; P.sample_bias = d->sample_bias; P.act = d->act; P.slope = d->slope;
+    P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
+    P.wrap = d->wrap;
+    P.add = reinterpret_cast<const __nv_bfloat16*>(d->add); P.add_cs = d->add_cs; P.add_c_off = d->add_c_off;
+    P.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate); P.gate_cs = d->gate_cs; P.gate_c_off = d->gate_c_off;
+    P.out_f32 = d->out_f32; P.n_valid = d->n_valid; P.sample_out = d->sample_out; P.uniforms = d->uniforms;
+
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};
+        uint64_t str[1] = {uint64_t(d->x_cs) * 2};
+        uint32_t box[2] = {uint32_t(CK), 128};
+        int rc = encode_tmap_bf16(&ta, d->x, 2, dims, str, box, CK * 2);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {uint64_t(d->cin), uint64_t(9 * d->n)};
+        uint64_t str[1] = {uint64_t(d->cin) * 2};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(d->n)};
+        int rc = encode_tmap_bf16(&tb, d->w, 2, dims, str, box, CK * 2);
+        if (rc) return rc;
+    }
+    return CK == 64 ? launch_igemm<64>(ta, tb, P, st) : launch_igemm<16>(ta, tb, P, st);
+}
+
+// one wgrad launch: P = 128 channels of `pp` (view per p_interior), Q = n channels of `qp`
+static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_off, bool p_interior, const void* qp,
+                        int q_cs, int q_c_off, int n, int q_sign, int flip, float scale, float* g, long long g_sm,
+                        long long g_sn, long long g_st, int m_valid, int n_valid, cudaStream_t st) {
+    const int Hp = H + 2, Wp = W + 2;
+    const int Wd = p_interior ? W : Wp, Hd = p_interior ? H : Hp;
+    // pixel box: BW covers a row of P's view, KP = BW*BH multiple of 16, ~64 pixels
+    int best_bw = 0, best_bh = 0;
+    double best_cost = 1e30;
+    for (int bh = 1; bh <= 16; bh *= 2) {
+        int bw = Wd;
+        while ((bw * bh) % 16) ++bw;
+        const int kp = bw * bh;
+        if (bw > 256 || kp > 128) continue;
+        const int nby = (Hd + bh - 1) / bh;
+        double cost = double(kp) * nby / (double(Wd) * Hd);  // padded work ratio
+        if (kp < 48) cost *= 1.0 + (48 - kp) / 48.0;         // tiny K blocks amortise barriers poorly
+        if (cost < best_cost) { best_cost = cost; best_bw = bw; best_bh = bh; }
+    }
+    if (!best_bw) {
+        set_error("wgrad: unsupported width %d", Wd);
+        return SCM_EUNSUPPORTED;
+    }
+    const int BW = best_bw, BH = best_bh, KP = BW * BH;
+    const int q_aw = (n % 64 == 0) ? 64 : (n % 32 == 0 ? 32 : 16);
+    const int q_atoms = n / q_aw;
+    const int q_atom_bytes = (KP * q_aw * 2 + 1023) & ~1023;
+    int tg = 9;
+    int stages = 0;
+    for (int cand : {9, 3, 1}) {
+        tg = cand;
+        if (tg * n > 512) continue;
+        const int stage_bytes = 2 * KP * 128 + tg * q_atoms * q_atom_bytes;
+        stages = std::min(4, kSmemBudget / stage_bytes);
+        if (stages >= 2) break;
+    }
+    if (stages < 2) {
+        set_error("wgrad: tile does not fit shared memory (n=%d KP=%d)", n, KP);
+        return SCM_EUNSUPPORTED;
+    }
+    const int stage_bytes = 2 * KP * 128 + tg * q_atoms * q_atom_bytes;
+    const int groups = (9 + tg - 1) / tg;
+
+    WgradParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = B; P.BW = BW; P.BH = BH;
+    P.nby = (Hd + BH - 1) / BH;
+    P.num_kblocks = B * P.nby;
+    int splits = std::max(1, std::min(P.num_kblocks / 8, std::max(1, num_sms() / groups)));
+    P.kb_per_cta = (P.num_kblocks + splits - 1) / splits;
+    splits = (P.num_kblocks + P.kb_per_cta - 1) / P.kb_per_cta;
+    P.tap0_stride = tg; P.n = n; P.q_aw = q_aw; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.q_sign = q_sign;
+    P.flip = flip; P.scale = scale; P.g = g; P.g_sm = g_sm; P.g_sn = g_sn; P.g_st = g_st;
+    P.m_valid = m_valid; P.n_valid = n_valid;
+
+    auto make_view = [&](CUtensorMap* t, const void* base, int cs, bool interior, int box_c, int swz) -> int {
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base);
+        if (interior) bp += (size_t(Wp) + 1) * cs;
+        uint64_t dims[4] = {uint64_t(cs), uint64_t(interior ? W : Wp), uint64_t(interior ? H : Hp), uint64_t(B)};
+        uint64_t str[3] = {uint64_t(cs) * 2, uint64_t(Wp) * cs * 2, uint64_t(Hp) * Wp * cs * 2};
+        uint32_t box[4] = {uint32_t(box_c), uint32_t(BW), uint32_t(BH), 1};
+        return encode_tmap_bf16(t, bp, 4, dims, str, box, swz);
+    };
+    CUtensorMap tp, tq;
+    int rc = make_view(&tp, pp, p_cs, p_interior, 64, 128);
+    if (rc) return rc;
+    rc = make_view(&tq, qp, q_cs, !p_interior, q_aw, q_aw * 2);
+    if (rc) return rc;
+
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        attr_set = true;
+    }
+    const int smem = stages * stage_bytes + 1024 + 256;
+    conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+}  // namespace scm
+
+using namespace scm;
+
+extern "C" {
+
+int scmgan_version(void) { return 100; }
+const char* scmgan_last_error(void) { return g_err; }
+int scmgan_num_sms(void) { return num_sms(); }
+
+int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
+                     int c_off, int c_pad, int wrap, scmgan_stream_t stream) {
+    SCM_REQUIRE(src && dst_plane, "pack_nchw: null pointer");
+    SCM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "pack_nchw: bad geometry");
+    SCM_REQUIRE(Cs % 8 == 0 && c_off % 8 == 0 && c_pad % 8 == 0 && c_pad >= C && c_off + c_pad <= Cs,
+                "pack_nchw: bad channel window (Cs=%d off=%d pad=%d C=%d)", Cs, c_off, c_pad, C);
+    const long long rows = (long long)B * (H + 2) * (W + 2);
+    const int threads = 128;
+    const long long blocks = (rows + threads - 1) / threads;
+    pack_nchw_to_plane_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t stream) {
+    SCM_REQUIRE(count >= 0 && (count == 0 || jobs), "pack_weights: bad arguments");
+    for (int base = 0; base < count; base += kMaxPackJobs) {
+        PackJobs J;
+        memset(&J, 0, sizeof(J));
+        J.count = std::min(kMaxPackJobs, count - base);
+        long long max_total = 0;
+        for (int i = 0; i < J.count; ++i) {
+            const scmgan_pack_job& s = jobs[base + i];
+            SCM_REQUIRE(s.w && s.out && s.n_pad > 0 && s.k_pad > 0 && s.n_valid <= s.n_pad && s.k_valid <= s.k_pad,
+                        "pack_weights: bad job %d", base + i);
+            PackJob& d = J.job[i];
+            d.w = s.w; d.out = reinterpret_cast<__nv_bfloat16*>(s.out); d.sigma = s.sigma;
+            d.n_pad = s.n_pad; d.k_pad = s.k_pad; d.n_valid = s.n_valid; d.k_valid = s.k_valid;
+            d.s_n = s.s_n; d.s_k = s.s_k; d.k_src_off = s.k_src_off; d.flip = s.flip;
+            max_total = std::max(max_total, 9LL * s.n_pad * s.k_pad);
+        }
+        const int threads = 256;
+        const int bx = int(std::min<long long>((max_total + threads - 1) / threads, 296));
+        pack_weights_kernel<<<dim3(bx, J.count), threads, 0, (cudaStream_t)stream>>>(J);
+        SCM_CUDA(cudaGetLastError());
+    }
+    return SCM_OK;
+}
+
+int scmgan_conv3x3_fwd(const scmgan_conv_desc* d, scmgan_stream_t stream) { return conv_impl(d, (cudaStream_t)stream); }
+int scmgan_conv3x3_dgrad(const scmgan_conv_desc* d, scmgan_stream_t stream) {
+    return conv_impl(d, (cudaStream_t)stream);
+}
+
+int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
+    SCM_REQUIRE(d != nullptr, "wgrad: null descriptor");
+    SCM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->dy && d->x && d->g, "wgrad: bad arguments");
+    SCM_REQUIRE(d->cout % 16 == 0 && d->cin % 16 == 0 && d->cout > 0 && d->cin > 0, "wgrad: channels must be x16");
+    SCM_REQUIRE(d->dy_cs % 8 == 0 && d->x_cs % 8 == 0 && d->dy_c_off % 8 == 0 && d->x_c_off % 8 == 0,
+                "wgrad: bad channel strides");
+    SCM_REQUIRE(d->dy_c_off + d->cout <= d->dy_cs && d->x_c_off + d->cin <= d->x_cs, "wgrad: channel window");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (d->cout % 128 == 0) {
+        for (int m0 = 0; m0 < d->cout; m0 += 128) {
+            if (m0 >= d->co_valid) break;
+            for (int c0 = 0; c0 < d->cin; c0 += 128) {
+                const int n = std::min(128, d->cin - c0);
+                const int nv = std::min(n, d->ci_valid - c0);
+                if (nv <= 0) break;
+                int rc = wgrad_launch(d->B, d->H, d->W, d->dy, d->dy_cs, d->dy_c_off + m0, true, d->x, d->x_cs,
+                                      d->x_c_off + c0, n, +1, d->flip, d->scale,
+                                      d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci, d->g_s_tap,
+                                      std::min(128, d->co_valid - m0), nv, st);
+                if (rc) return rc;
+            }
+        }
+        return SCM_OK;
+    }
+    if (d->cin % 128 == 0 && d->cout <= 256) {
+        for (int c0 = 0; c0 < d->cin; c0 += 128) {
+            const int mv = std::min(128, d->ci_valid - c0);
+            if (mv <= 0) break;
+            int rc = wgrad_launch(d->B, d->H, d->W, d->x, d->x_cs, d->x_c_off + c0, false, d->dy, d->dy_cs,
+                                  d->dy_c_off, d->cout, -1, d->flip, d->scale, d->g + c0 * d->g_s_ci, d->g_s_ci,
+                                  d->g_s_co, d->g_s_tap, mv, d->co_valid, st);
+            if (rc) return rc;
+        }
+        return SCM_OK;
+    }
+    set_error("wgrad: one of cout (%d) / cin (%d) must be a multiple of 128", d->cout, d->cin);
+    return SCM_EUNSUPPORTED;
+}
+
+int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int H, int W, float* S, float* db,
+                        scmgan_stream_t stream) {
+    SCM_REQUIRE(plane && (S || db), "colsum: null pointer");
+    SCM_REQUIRE(n % 8 == 0 && n > 0 && n <= 256 && Cs % 8 == 0 && c_off % 8 == 0 && c_off + n <= Cs,
+                "colsum: bad channel window");
+    const int threads = 256;
+    const int groups = n / 8;
+    const int lanes = threads / groups;
+    const int hw = H * W;
+    int chunks = std::max(1, std::min((hw + 255) / 256, std::max(1, 4 * num_sms() / B)));
+    const int rows_per_block = (hw + chunks - 1) / chunks;
+    chunks = (hw + rows_per_block - 1) / rows_per_block;
+    plane_colsum_kernel<<<dim3(chunks, B), threads, lanes * n * sizeof(float), (cudaStream_t)stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(plane), Cs, c_off, n, B, H, W, S, db, rows_per_block);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_stream_t stream) {
+    SCM_REQUIRE(count > 0 && count <= kMaxSnLayers && layers, "spectral_norm_fwd: bad layer count %d", count);
+    SnLayers L;
+    memset(&L, 0, sizeof(L));
+    L.count = count;
+    int max_smem = 0;
+    for (int i = 0; i < count; ++i) {
+        const scmgan_sn_layer& s = layers[i];
+        SCM_REQUIRE(s.w && s.u && s.v && s.sigma && s.rows > 0 && s.cols > 0, "spectral_norm_fwd: bad layer %d", i);
+        L.layer[i] = SnLayer{s.w, s.u, s.v, s.sigma, s.u_save, s.v_save, s.rows, s.cols};
+        max_smem = std::max(max_smem, int((s.rows + s.cols + 64) * sizeof(float)));
+    }
+    SCM_REQUIRE(max_smem <= 48 * 1024, "spectral_norm_fwd: layer too large");
+    sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(L);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmgan_stream_t stream) {
+    SCM_REQUIRE(count > 0 && count <= kMaxSnLayers && layers, "spectral_norm_bwd: bad layer count %d", count);
+    SnBwdLayers L;
+    memset(&L, 0, sizeof(L));
+    L.count = count;
+    for (int i = 0; i < count; ++i) {
+        const scmgan_sn_bwd_layer& s = layers[i];
+        SCM_REQUIRE(s.g && s.wbar && s.u && s.v && s.sigma && s.dot && s.out, "spectral_norm_bwd: bad layer %d", i);
+        L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols};
+    }
+    sn_bwd_dot_kernel<<<dim3(32, count), 256, 0, (cudaStream_t)stream>>>(L);
+    SCM_CUDA(cudaGetLastError());
+    sn_bwd_apply_kernel<<<dim3(64, count), 256, 0, (cudaStream_t)stream>>>(L);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_action_bias(const float* wbar, const float* sigma, const float* bias, const float* act, int B, int Cout,
+                       int L, int A, float* out, scmgan_stream_t stream) {
+    SCM_REQUIRE(wbar && act && out && B > 0 && Cout > 0 && A > 0, "action_bias: bad arguments");
+    const int total = B * Cout;
+    action_bias_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(wbar, sigma, bias, act, B, Cout, L, A,
+                                                                             out);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L, int A, float* g,
+                        scmgan_stream_t stream) {
+    SCM_REQUIRE(S && act && g && B > 0 && Cout > 0 && A > 0, "action_wgrad: bad arguments");
+    const int total = Cout * A;
+    action_wgrad_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, act, B, Cout, L, A, g);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
+                      float* loss, float* dx, scmgan_stream_t stream) {
+    SCM_REQUIRE(x && y && loss && B > 0 && per > 0, "bce_logits: bad arguments");
+    const int threads = 256;
+    int bx = int(std::min<long long>((per + threads * 4 - 1) / (threads * 4), std::max(1, 8 * num_sms() / B)));
+    bx = std::max(bx, 1);
+    bce_logits_kernel<<<dim3(bx, B), threads, 0, (cudaStream_t)stream>>>(x, y, y_bstride, mask, B, per, loss, dx);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float beta1, float beta2, float eps,
+                     int step, const float* step_dev, float gscale, scmgan_stream_t stream) {
+    SCM_REQUIRE(count >= 0 && (count == 0 || chunks), "clip_adam: bad arguments");
+    SCM_REQUIRE(step_dev || step >= 1, "clip_adam: step must be >= 1");
+    for (int base = 0; base < count; base += kAdamChunksPerLaunch) {
+        AdamArgs A;
+        memset(&A, 0, sizeof(A));
+        A.count = std::min(kAdamChunksPerLaunch, count - base);
+        int max_n = 0;
+        for (int i = 0; i < A.count; ++i) {
+            const scmgan_adam_chunk& c = chunks[base + i];
+            SCM_REQUIRE(c.p && c.g && c.m && c.v && c.n > 0, "clip_adam: bad chunk %d", base + i);
+            A.chunk[i] = AdamChunk{c.p, c.g, c.m, c.v, c.n, c.clip};
+            max_n = std::max(max_n, c.n);
+        }
+        A.lr = lr; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.step_ptr = step_dev; A.gscale = gscale;
+        if (!step_dev) {
+            A.bc1 = 1.f - powf(beta1, float(step));
+            A.bc2_sqrt = sqrtf(1.f - powf(beta2, float(step)));
+        }
+        const int bx = std::max(1, std::min((max_n + 1023) / 1024, 64));
+        clip_adam_kernel<<<dim3(bx, A.count), 256, 0, (cudaStream_t)stream>>>(A);
+        SCM_CUDA(cudaGetLastError());
+    }
+    return SCM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,175 @@
+// Weight gradient of the 3x3 convolutions as tcgen05 GEMMs reduced over pixels (sm_100a).
+//
+// Replaces cuDNN's convolution_backward (wgrad half) invoked by loss.backward() (reference main.py:285)
+// for every conv of models.py:51-56, 129-133, 260-266.
+//
+//   dW[tap][m][n] = sum_{interior pixels p} P[p (+shift)][m] * Q[p (+shift)][n]
+//
+// One operand is the output gradient dY (an *interior view* tensor map: everything outside the H x W
+// interior is out-of-bounds and zero-filled by TMA, so halo rows never contribute), the other is the layer
+// input X (full padded-plane view, box shifted by the filter tap).  Which of the two plays the M role
+// (exactly 128 channels) is chosen by the host so that M = 128.  Both operands are MN-major in shared
+// memory (channels contiguous, pixels along K), which is exactly what a TMA box {channels, w, h, 1}
+// produces, so no transposition is ever materialised.
+//
+// Work split: a CTA owns a group of `tg` consecutive taps (tg*n <= 512 TMEM columns) and a contiguous
+// range of pixel blocks (split-K).  The fp32 partial results are reduced with red.global.add.f32 directly
+// into a gradient tensor with arbitrary (m, n, tap) strides, i.e. straight into PyTorch's
+// [Cout][Cin][3][3] (or ConvTranspose [Cin][Cout][3][3]) layout.
+#pragma once
+#include "ptx.cuh"
+
+namespace scm {
+
+struct WgradParams {
+    int B;
+    int BW, BH;        // pixel box; KP = BW*BH pixels per K block (multiple of 16).  BW covers a full row
+    int nby;           // ceil(Hd / BH), Hd = rows of P's view (H for an interior view, H+2 for a padded view)
+    int num_kblocks;   // B * nby
+    int kb_per_cta;    // K blocks per split
+    int tap0_stride;   // taps per group (tg)
+    int n;             // N (channels of Q handled by this launch), multiple of 16, <= 256, tg*n <= 512
+    int q_aw;          // Q atom width in channels: 64, 32 or 16 (divides n)
+    int p_c_off, q_c_off;
+    int q_sign;        // Q box origin = (q_sign*kx, h0 + q_sign*ky): +1 when Q is the padded input plane and
+                       // P the interior-view gradient; -1 when P is the padded input and Q the gradient
+    int flip;          // 1: gradient tap index = 8 - tap (ConvTranspose / flipped packing)
+    float scale;
+    float* g;          // gradient tensor (fp32, accumulated atomically)
+    long long g_sm, g_sn, g_st;  // element strides for m, n, tap
+    int m_valid, n_valid;
+};
+
+constexpr int kWgradThreads = 192;
+
+__global__ void __launch_bounds__(kWgradThreads, 1)
+conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q,
+                     const __grid_constant__ WgradParams P, int num_stages) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int KP = P.BW * P.BH;
+    const int tg = P.tap0_stride;
+    const int p_atom_bytes = KP * 128;                          // one 64-channel atom of P
+    const int p_bytes = 2 * p_atom_bytes;                       // M = 128
+    const int q_atoms = P.n / P.q_aw;
+    const int q_atom_bytes = (KP * P.q_aw * 2 + 1023) & ~1023;  // keep every atom 1024B aligned
+    const int q_tap_bytes = q_atoms * q_atom_bytes;
+    const int stage_bytes = p_bytes + tg * q_tap_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + size_t(num_stages) * stage_bytes);
+    uint64_t* full_bar = bars;
+    uint64_t* empty_bar = bars + 8;
+    uint64_t* acc_full = bars + 16;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int group = blockIdx.y;          // tap group
+    const int tap_begin = group * tg;
+    const int ntaps = min(tg, 9 - tap_begin);
+    const int kb_begin = blockIdx.x * P.kb_per_cta;
+    const int kb_end = min(P.num_kblocks, kb_begin + P.kb_per_cta);
+    const int nkb = max(0, kb_end - kb_begin);
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_p);
+        prefetch_tmap(&tmap_q);
+        for (int s = 0; s < num_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (nkb > 0) {
+        if (warp == 0) {
+            if (lane == 0) {
+                const uint32_t tx = uint32_t(2 * KP * 128 + ntaps * q_atoms * KP * P.q_aw * 2);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    const int b = kb / P.nby;
+                    const int h0 = (kb - b * P.nby) * P.BH;
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sp = smem + size_t(stage) * stage_bytes;
+                    mbar_arrive_expect_tx(&full_bar[stage], tx);
+                    tma_load_4d(sp, &tmap_p, &full_bar[stage], P.p_c_off, 0, h0, b);
+                    tma_load_4d(sp + p_atom_bytes, &tmap_p, &full_bar[stage], P.p_c_off + 64, 0, h0, b);
+                    for (int t = 0; t < ntaps; ++t) {
+                        const int tap = tap_begin + t;
+                        const int dy = P.q_sign * (tap / 3), dx = P.q_sign * (tap % 3);
+                        uint8_t* sq = sp + p_bytes + t * q_tap_bytes;
+                        for (int j = 0; j < q_atoms; ++j)
+                            tma_load_4d(sq + j * q_atom_bytes, &tmap_q, &full_bar[stage], P.q_c_off + j * P.q_aw, dx,
+                                        h0 + dy, b);
+                    }
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                const uint32_t idesc = make_idesc_f16(128, P.n, 1, 1, 1);
+                const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
+                const uint32_t q_sbo = 8u * P.q_aw * 2u;
+                const uint32_t q_kstep = 16u * P.q_aw * 2u;
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t sp = smem_u32(smem + size_t(stage) * stage_bytes);
+                    for (int t = 0; t < ntaps; ++t) {
+                        const uint32_t sq = sp + p_bytes + t * q_tap_bytes;
+                        const uint32_t tmem_d = tmem_base + uint32_t(t * P.n);
+                        for (int k = 0; k < KP / 16; ++k) {
+                            const uint64_t adesc = make_smem_desc(sp + k * 2048, p_atom_bytes, 1024, kLayoutSw128);
+                            const uint64_t bdesc = make_smem_desc(sq + k * q_kstep, q_atom_bytes, q_sbo, q_layout);
+                            umma_f16(tmem_d, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+                umma_commit(acc_full);
+            }
+        } else {
+            const int q = warp & 3;
+            const int m = q * 32 + lane;
+            mbar_wait(acc_full, 0);
+            tc_fence_after();
+            for (int t = 0; t < ntaps; ++t) {
+                const int tap = tap_begin + t;
+                const int gtap = P.flip ? 8 - tap : tap;
+                for (int n0 = 0; n0 < P.n; n0 += 16) {
+                    float v[16];
+                    tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(t * P.n + n0), v);
+                    tmem_ld_wait();
+                    if (m < P.m_valid) {
+                        float* gp = P.g + (long long)m * P.g_sm + (long long)gtap * P.g_st;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            if (n0 + i < P.n_valid) atomicAdd(gp + (long long)(n0 + i) * P.g_sn, v[i] * P.scale);
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace scm

@@ -1,0 +1,362 @@
+// HBM-bound helper kernels around the tcgen05 GEMMs: layout packing, weight packing, spectral-norm power
+// iteration and its backward, bias/colsum reductions, fused losses and the fused clip+Adam optimiser.
+#pragma once
+#include "ptx.cuh"
+
+namespace scm {
+
+// ----------------------------------------------------------------------------------------------
+// fp32 NCHW (caller tensors) -> bf16 plane [B][H+2][W+2][Cs] at channel offset c_off, halo = wrap or zero.
+// One thread per plane pixel; channels [c_off, c_off + c_pad) are written (zeros beyond C).
+// ----------------------------------------------------------------------------------------------
+__global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long long src_bstride, int C, int B, int H,
+                                          int W, __nv_bfloat16* __restrict__ dst, int Cs, int c_off, int c_pad,
+                                          int wrap) {
+    const int Hp = H + 2, Wp = W + 2;
+    const long long rows = (long long)B * Hp * Wp;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rows) return;
+    const int b = int(p / (Hp * Wp));
+    const int rem = int(p - (long long)b * Hp * Wp);
+    int hp = rem / Wp, wp = rem - hp * Wp;
+    int h = hp - 1, w = wp - 1;
+    bool zero = false;
+    if (wrap) {
+        h = (h + H) % H;
+        w = (w + W) % W;
+    } else {
+        zero = (h < 0 || h >= H || w < 0 || w >= W);
+    }
+    const float* s = src + (long long)b * src_bstride + (long long)h * W + w;
+    __nv_bfloat16* d = dst + p * Cs + c_off;
+    for (int c0 = 0; c0 < c_pad; c0 += 8) {
+        uint4 o;
+        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int c = c0 + i;
+            float x = 0.f;
+            if (!zero && c < C) x = __ldg(s + (long long)c * H * W);
+            oh[i] = __float2bfloat16_rn(x);
+        }
+        *reinterpret_cast<uint4*>(d + c0) = o;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Weight packing: fp32 parameter tensor -> bf16 [9][n_pad][k_pad] (K-major B operand of the implicit GEMM).
+//   out[tap][n][k] = W[n*s_n + k*s_k + (flip ? 8-tap : tap)] / sigma      (zero outside n_valid x k_valid)
+// Covers Conv2d forward (n=co,k=ci), Conv2d dgrad (n=ci,k=co,flip), ConvTranspose2d forward/dgrad.
+// ----------------------------------------------------------------------------------------------
+struct PackJob {
+    const float* w;
+    __nv_bfloat16* out;
+    const float* sigma;  // nullptr => 1
+    int n_pad, k_pad, n_valid, k_valid;
+    long long s_n, s_k;
+    int k_src_off;  // first source k (e.g. skip nothing: 0)
+    int flip;
+};
+constexpr int kMaxPackJobs = 16;
+struct PackJobs {
+    PackJob job[kMaxPackJobs];
+    int count;
+};
+
+__global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
+    const PackJob& J = jobs.job[blockIdx.y];
+    const long long total = 9LL * J.n_pad * J.k_pad;
+    const float inv = J.sigma ? 1.f / __ldg(J.sigma) : 1.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = int(i % J.k_pad);
+        const long long r = i / J.k_pad;
+        const int n = int(r % J.n_pad);
+        const int tap = int(r / J.n_pad);
+        float x = 0.f;
+        if (n < J.n_valid && k < J.k_valid)
+            x = __ldg(J.w + n * J.s_n + (long long)(k + J.k_src_off) * J.s_k + (J.flip ? 8 - tap : tap)) * inv;
+        J.out[i] = __float2bfloat16_rn(x);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Spectral norm power iteration (reference spectral_normalization.py:23-35), one CTA per wrapped conv:
+//   v <- normalize(W^T u);  u <- normalize(W v);  sigma = u . (W v)        (eps = 1e-12, as l2normalize)
+// W is [rows][cols] fp32 (rows = Cout, cols = Cin*9).  u, v are updated in place; u, v, sigma are also
+// copied to the per-call save slots needed by the backward pass.
+// ----------------------------------------------------------------------------------------------
+struct SnLayer {
+    const float* w;
+    float* u;
+    float* v;
+    float* sigma;   // [1]
+    float* u_save;  // [rows] or nullptr
+    float* v_save;  // [cols] or nullptr
+    int rows, cols;
+};
+constexpr int kMaxSnLayers = 8;
+struct SnLayers {
+    SnLayer layer[kMaxSnLayers];
+    int count;
+};
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+
+// block-wide sum for 1024 threads; result broadcast to all threads
+__device__ __forceinline__ float block_sum(float x, float* red /*[33]*/) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    x = warp_sum(x);
+    __syncthreads();
+    if (lane == 0) red[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        float y = (lane < (blockDim.x >> 5)) ? red[lane] : 0.f;
+        y = warp_sum(y);
+        if (lane == 0) red[32] = y;
+    }
+    __syncthreads();
+    return red[32];
+}
+
+__global__ void __launch_bounds__(1024, 1) sn_power_iter_kernel(const __grid_constant__ SnLayers L) {
+    extern __shared__ float sn_smem[];  // [cols] t/v  + [rows] s/u + 33
+    const SnLayer& Y = L.layer[blockIdx.x];
+    const int R = Y.rows, C = Y.cols;
+    float* sv = sn_smem;
+    float* su = sn_smem + C;
+    float* red = su + R;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int n = tid; n < R; n += nt) su[n] = Y.u[n];
+    __syncthreads();
+    // t = W^T u  (thread per column: coalesced along k)
+    float ss = 0.f;
+    for (int k = tid; k < C; k += nt) {
+        float acc = 0.f;
+        for (int n = 0; n < R; ++n) acc = fmaf(__ldg(Y.w + (long long)n * C + k), su[n], acc);
+        sv[k] = acc;
+        ss += acc * acc;
+    }
+    float nrm = sqrtf(block_sum(ss, red));
+    const float inv_v = 1.f / (nrm + 1e-12f);
+    for (int k = tid; k < C; k += nt) sv[k] *= inv_v;
+    __syncthreads();
+    // s = W v  (warp per row: coalesced along k)
+    const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    for (int n = warp; n < R; n += nw) {
+        float acc = 0.f;
+        for (int k = lane; k < C; k += 32) acc = fmaf(__ldg(Y.w + (long long)n * C + k), sv[k], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) su[n] = acc;
+    }
+    __syncthreads();
+    float s2 = 0.f;
+    for (int n = tid; n < R; n += nt) s2 += su[n] * su[n];
+    s2 = block_sum(s2, red);
+    const float inv_u = 1.f / (sqrtf(s2) + 1e-12f);
+    // sigma = u_new . (W v) = sum s^2 * inv_u
+    if (tid == 0) *Y.sigma = s2 * inv_u;
+    for (int n = tid; n < R; n += nt) {
+        const float un = su[n] * inv_u;
+        Y.u[n] = un;
+        if (Y.u_save) Y.u_save[n] = un;
+    }
+    for (int k = tid; k < C; k += nt) {
+        Y.v[k] = sv[k];
+        if (Y.v_save) Y.v_save[k] = sv[k];
+    }
+}
+
+// Spectral-norm backward: dWbar = G/sigma - (<G, Wbar>/sigma^2) * u v^T   (u, v, sigma of that forward call)
+struct SnBwdLayer {
+    const float* g;     // gradient wrt the normalised weight [rows][cols]
+    const float* wbar;  // [rows][cols]
+    const float* u;
+    const float* v;
+    const float* sigma;
+    float* dot;   // [1] scratch, zeroed by the caller
+    float* out;   // [rows][cols]
+    int rows, cols;
+};
+struct SnBwdLayers {
+    SnBwdLayer layer[kMaxSnLayers];
+    int count;
+};
+
+__global__ void sn_bwd_dot_kernel(const __grid_constant__ SnBwdLayers L) {
+    __shared__ float red[33];
+    const SnBwdLayer& Y = L.layer[blockIdx.y];
+    const long long total = (long long)Y.rows * Y.cols;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x)
+        acc = fmaf(__ldg(Y.g + i), __ldg(Y.wbar + i), acc);
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(Y.dot, acc);
+}
+
+__global__ void sn_bwd_apply_kernel(const __grid_constant__ SnBwdLayers L) {
+    const SnBwdLayer& Y = L.layer[blockIdx.y];
+    const long long total = (long long)Y.rows * Y.cols;
+    const float sig = __ldg(Y.sigma);
+    const float inv = 1.f / sig;
+    const float coef = __ldg(Y.dot) * inv * inv;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int n = int(i / Y.cols), k = int(i - (long long)n * Y.cols);
+        Y.out[i] = __ldg(Y.g + i) * inv - coef * __ldg(Y.u + n) * __ldg(Y.v + k);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Per-sample channel sums over the interior of a bf16 plane (bias gradients / folded-action gradients):
+//   S[b][c] += sum_{interior p} plane[b][p][c_off + c];   db[c] += same summed over b (optional)
+// grid = (row chunks, B); block = 256 threads = (n/8 channel groups) x (row lanes)
+// ----------------------------------------------------------------------------------------------
+__global__ void plane_colsum_kernel(const __nv_bfloat16* __restrict__ plane, int Cs, int c_off, int n, int B, int H,
+                                    int W, float* __restrict__ S, float* __restrict__ db, int rows_per_block) {
+    extern __shared__ float cs_smem[];  // [row lanes][n]
+    const int Hp = H + 2, Wp = W + 2;
+    const int groups = n >> 3;
+    const int lanes = blockDim.x / groups;
+    const int g = threadIdx.x % groups, rl = threadIdx.x / groups;
+    const int b = blockIdx.y;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (rl < lanes) {
+        const int r0 = blockIdx.x * rows_per_block;
+        const int r1 = min(H * W, r0 + rows_per_block);
+        for (int r = r0 + rl; r < r1; r += lanes) {
+            const int h = r / W, w = r - h * W;
+            const long long p = ((long long)b * Hp + (h + 1)) * Wp + (w + 1);
+            const uint4 q = __ldg(reinterpret_cast<const uint4*>(plane + p * Cs + c_off + g * 8));
+            const __nv_bfloat16* hq = reinterpret_cast<const __nv_bfloat16*>(&q);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc[i] += __bfloat162float(hq[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) cs_smem[rl * n + g * 8 + i] = acc[i];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        float s = 0.f;
+        for (int l = 0; l < lanes; ++l) s += cs_smem[l * n + c];
+        if (S) atomicAdd(S + (long long)b * n + c, s);
+        if (db) atomicAdd(db + c, s);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Folded action channels of Transition.conv1 (reference models.py:69-73): under circular padding a
+// spatially constant input channel contributes a per-sample constant, so
+//   sample_bias[b][n] = bias[n] + (1/sigma) * sum_a act[b][a] * sum_tap Wbar[n][L + a][tap]
+// and in backward   dW[n][L + a][tap] = sum_b S[b][n] * act[b][a]   for every tap.
+// ----------------------------------------------------------------------------------------------
+__global__ void action_bias_kernel(const float* __restrict__ wbar, const float* __restrict__ sigma,
+                                   const float* __restrict__ bias, const float* __restrict__ act, int B, int Cout,
+                                   int L, int A, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * Cout) return;
+    const int b = i / Cout, n = i - b * Cout;
+    const float inv = sigma ? 1.f / __ldg(sigma) : 1.f;
+    float acc = 0.f;
+    for (int a = 0; a < A; ++a) {
+        const float av = __ldg(act + b * A + a);
+        if (av != 0.f) {
+            const float* wp = wbar + ((long long)n * (L + A) + (L + a)) * 9;
+            float s = 0.f;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) s += __ldg(wp + t);
+            acc = fmaf(av, s, acc);
+        }
+    }
+    out[i] = (bias ? __ldg(bias + n) : 0.f) + acc * inv;
+}
+
+__global__ void action_wgrad_kernel(const float* __restrict__ S, const float* __restrict__ act, int B, int Cout,
+                                    int L, int A, float* __restrict__ g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Cout * A) return;
+    const int n = i / A, a = i - n * A;
+    float acc = 0.f;
+    for (int b = 0; b < B; ++b) acc = fmaf(__ldg(S + b * Cout + n), __ldg(act + b * A + a), acc);
+    float* gp = g + ((long long)n * (L + A) + (L + a)) * 9;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) gp[t] = acc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fused sigmoid + binary cross entropy + masked per-sample mean (reference main.py:188-197, 310-312):
+//   loss += (1/B) * sum_b mask[b] * mean_{c,h,w} BCE(sigmoid(x), y)       (log clamped at -100 as torch)
+//   dx = (sigmoid(x) - y) * mask[b] / (B*C*H*W)
+// The gradient is produced in the same pass (forward+backward fusion); autograd scales it by grad_output.
+// ----------------------------------------------------------------------------------------------
+__global__ void bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ y, long long y_bstride,
+                                  const float* __restrict__ mask, int B, long long per, float* __restrict__ loss,
+                                  float* __restrict__ dx) {
+    __shared__ float red[33];
+    const int b = blockIdx.y;
+    const float m = mask ? __ldg(mask + b) : 1.f;
+    const float inv = 1.f / (float(B) * float(per));
+    const float* xb = x + (long long)b * per;
+    const float* yb = y + (long long)b * y_bstride;
+    float acc = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float xv = __ldg(xb + i), yv = __ldg(yb + i);
+        const float p = 1.f / (1.f + __expf(-xv));
+        const float lp = fmaxf(__logf(p), -100.f), lq = fmaxf(__logf(1.f - p), -100.f);
+        acc -= yv * lp + (1.f - yv) * lq;
+        if (dx) dx[(long long)b * per + i] = (p - yv) * m * inv;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) atomicAdd(loss, acc * m * inv);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Fused clip_grad_value_ + Adam (reference main.py:287-296; torch.optim.Adam defaults, no weight decay).
+// Multi-tensor: one launch updates every parameter of every network.
+// ----------------------------------------------------------------------------------------------
+struct AdamChunk {
+    float* p;
+    const float* g;
+    float* m;
+    float* v;
+    int n;
+    float clip;  // <= 0: no clipping
+};
+constexpr int kAdamChunksPerLaunch = 48;
+struct AdamArgs {
+    AdamChunk chunk[kAdamChunksPerLaunch];
+    int count;
+    float lr, beta1, beta2, eps;
+    float bc1, bc2_sqrt;  // 1 - beta1^t, sqrt(1 - beta2^t) (ignored when step_ptr != nullptr)
+    const float* step_ptr;  // device step counter (float) for graph replay, or nullptr
+    float gscale;           // multiplies the gradient before clipping (1/world_size for DP)
+};
+
+__global__ void clip_adam_kernel(const __grid_constant__ AdamArgs A) {
+    const AdamChunk& C = A.chunk[blockIdx.y];
+    float bc1 = A.bc1, bc2s = A.bc2_sqrt;
+    if (A.step_ptr) {
+        const float t = __ldg(A.step_ptr);
+        bc1 = 1.f - powf(A.beta1, t);
+        bc2s = sqrtf(1.f - powf(A.beta2, t));
+    }
+    const float step_size = A.lr / bc1;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < C.n; i += gridDim.x * blockDim.x) {
+        float g = C.g[i] * A.gscale;
+        if (C.clip > 0.f) g = fminf(fmaxf(g, -C.clip), C.clip);
+        const float m = A.beta1 * C.m[i] + (1.f - A.beta1) * g;
+        const float v = A.beta2 * C.v[i] + (1.f - A.beta2) * g * g;
+        C.m[i] = m;
+        C.v[i] = v;
+        const float denom = sqrtf(v) / bc2s + A.eps;
+        C.p[i] -= step_size * (m / denom);
+    }
+}
+
+}  // namespace scm

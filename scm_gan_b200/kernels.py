@@ -1,0 +1,144 @@
+"""Thin tensor-level wrappers over the C ABI: they take torch CUDA tensors (memory + stream plumbing only)
+and enqueue the hand-written kernels on torch's current stream.  No arithmetic happens in Python/torch here.
+
+A "plane" is a bf16 tensor [B, H+2, W+2, Cs] (NHWC with a one-pixel halo), see include/scmgan.h.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+from ._lib import ACT_LRELU, ACT_NONE, ACT_SIGMOID  # noqa: F401
+
+LRELU_SLOPE = 0.01  # F.leaky_relu default used by reference models.py:77-99
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def new_plane(B, H, W, Cs, device):
+    # every element (halo included) is written by the producing kernel, so empty() is enough
+    return torch.empty((B, H + 2, W + 2, Cs), dtype=torch.bfloat16, device=device)
+
+
+def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False):
+    """fp32 [B,C,H,W] (arbitrary batch stride, dense CHW) -> plane channels [c_off, c_off+c_pad)."""
+    B, Cc, H, W = src.shape
+    assert src.dtype == torch.float32 and src.is_cuda
+    assert src.stride(3) == 1 and src.stride(2) == W and src.stride(1) == H * W, "dense CHW required"
+    Cs = dst_plane.shape[3]
+    if c_pad is None:
+        c_pad = (Cc + 15) // 16 * 16
+    L.check(L.lib().scmgan_pack_nchw(src.data_ptr(), src.stride(0), Cc, B, H, W, dst_plane.data_ptr(), Cs, c_off,
+                                     c_pad, int(wrap), _stream()), "scmgan_pack_nchw")
+
+
+def pack_weights(jobs):
+    """jobs: list of dicts(w, out, sigma, n_pad, k_pad, n_valid, k_valid, s_n, s_k, k_src_off, flip)."""
+    arr = (L.PackJob * len(jobs))()
+    for i, j in enumerate(jobs):
+        arr[i] = L.PackJob(j["w"].data_ptr(), j["out"].data_ptr(), L.ptr(j.get("sigma")), j["n_pad"], j["k_pad"],
+                           j["n_valid"], j["k_valid"], j["s_n"], j["s_k"], j.get("k_src_off", 0), j.get("flip", 0))
+    L.check(L.lib().scmgan_pack_weights(len(jobs), arr, _stream()), "scmgan_pack_weights")
+
+
+def packed_weight(n_pad, k_pad, device):
+    return torch.empty((9, n_pad, k_pad), dtype=torch.bfloat16, device=device)
+
+
+def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, act=ACT_NONE,
+            out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
+            n_valid=0, sample_out=None, uniforms=None, dgrad=False):
+    n = w_packed.shape[1]
+    assert w_packed.shape[2] == cin and w_packed.dtype == torch.bfloat16
+    d = L.ConvDesc()
+    d.B, d.H, d.W = B, H, W
+    d.x, d.x_cs, d.x_c_off, d.cin = x_plane.data_ptr(), x_plane.shape[3], x_c_off, cin
+    d.w, d.n = w_packed.data_ptr(), n
+    d.scale, d.bias, d.sample_bias = scale, L.ptr(bias), L.ptr(sample_bias)
+    d.act, d.slope = act, LRELU_SLOPE
+    d.out = L.ptr(out)
+    d.out_cs = out.shape[3] if out is not None else 0
+    d.out_c_off, d.wrap = out_c_off, int(wrap)
+    d.add = L.ptr(add)
+    d.add_cs = add.shape[3] if add is not None else 0
+    d.add_c_off = add_c_off
+    d.gate = L.ptr(gate)
+    d.gate_cs = gate.shape[3] if gate is not None else 0
+    d.gate_c_off = gate_c_off
+    d.out_f32, d.n_valid = L.ptr(out_f32), n_valid
+    d.sample_out, d.uniforms = L.ptr(sample_out), L.ptr(uniforms)
+    fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
+    L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
+
+
+def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
+          co_valid=None, ci_valid=None, scale=1.0):
+    d = L.WgradDesc()
+    d.B, d.H, d.W = B, H, W
+    d.dy, d.dy_cs, d.dy_c_off, d.cout = dy_plane.data_ptr(), dy_plane.shape[3], dy_c_off, cout
+    d.x, d.x_cs, d.x_c_off, d.cin = x_plane.data_ptr(), x_plane.shape[3], x_c_off, cin
+    d.g, d.g_s_co, d.g_s_ci, d.g_s_tap = g.data_ptr(), g_s_co, g_s_ci, g_s_tap
+    d.flip = int(flip)
+    d.co_valid = cout if co_valid is None else co_valid
+    d.ci_valid = cin if ci_valid is None else ci_valid
+    d.scale = scale
+    L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
+
+
+def plane_colsum(plane, c_off, n, B, H, W, S=None, db=None):
+    L.check(L.lib().scmgan_plane_colsum(plane.data_ptr(), plane.shape[3], c_off, n, B, H, W, L.ptr(S), L.ptr(db),
+                                        _stream()), "scmgan_plane_colsum")
+
+
+def spectral_norm_fwd(layers):
+    """layers: list of (wbar, u, v, sigma, u_save, v_save); wbar is [rows, ...]."""
+    arr = (L.SnLayer * len(layers))()
+    for i, (w, u, v, s, us, vs) in enumerate(layers):
+        rows = w.shape[0]
+        arr[i] = L.SnLayer(w.data_ptr(), u.data_ptr(), v.data_ptr(), s.data_ptr(), L.ptr(us), L.ptr(vs), rows,
+                           w.numel() // rows)
+    L.check(L.lib().scmgan_spectral_norm_fwd(len(layers), arr, _stream()), "scmgan_spectral_norm_fwd")
+
+
+def spectral_norm_bwd(layers):
+    """layers: list of (g, wbar, u, v, sigma, dot, out)."""
+    arr = (L.SnBwdLayer * len(layers))()
+    for i, (g, w, u, v, s, dot, out) in enumerate(layers):
+        rows = w.shape[0]
+        arr[i] = L.SnBwdLayer(g.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), s.data_ptr(), dot.data_ptr(),
+                              out.data_ptr(), rows, w.numel() // rows)
+    L.check(L.lib().scmgan_spectral_norm_bwd(len(layers), arr, _stream()), "scmgan_spectral_norm_bwd")
+
+
+def action_bias(wbar, sigma, bias, act, latent, out):
+    B, A = act.shape
+    cout = wbar.shape[0]
+    L.check(L.lib().scmgan_action_bias(wbar.data_ptr(), L.ptr(sigma), L.ptr(bias), act.data_ptr(), B, cout, latent, A,
+                                       out.data_ptr(), _stream()), "scmgan_action_bias")
+
+
+def action_wgrad(S, act, latent, g):
+    B, A = act.shape
+    cout = g.shape[0]
+    L.check(L.lib().scmgan_action_wgrad(S.data_ptr(), act.data_ptr(), B, cout, latent, A, g.data_ptr(), _stream()),
+            "scmgan_action_wgrad")
+
+
+def bce_logits(x, y, mask, loss, dx=None):
+    """x: [B,...] dense fp32 logits; y: same shape, dense per sample (batch stride free)."""
+    B = x.shape[0]
+    per = x.numel() // B
+    assert x.is_contiguous() and y.stride(-1) == 1
+    L.check(L.lib().scmgan_bce_logits(x.data_ptr(), y.data_ptr(), y.stride(0), L.ptr(mask), B, per, loss.data_ptr(),
+                                      L.ptr(dx), _stream()), "scmgan_bce_logits")
+
+
+def clip_adam(chunks, lr, beta1, beta2, eps, step, step_dev=None, gscale=1.0):
+    """chunks: list of (p, g, m, v, clip)."""
+    arr = (L.AdamChunk * len(chunks))()
+    for i, (p, g, m, v, clip) in enumerate(chunks):
+        arr[i] = L.AdamChunk(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), clip)
+    L.check(L.lib().scmgan_clip_adam(len(chunks), arr, lr, beta1, beta2, eps, step, L.ptr(step_dev), gscale,
+                                     _stream()), "scmgan_clip_adam")

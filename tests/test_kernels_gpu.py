@@ -1,0 +1,347 @@
+"""Kernel-level parity (-m gpu): every C-ABI kernel against a plain fp32 torch statement of the same op.
+
+The tensor-core kernels take bf16 operands; the references below are fed the *same bf16-rounded operands* in fp32
+(TF32 off), so the only differences are fp32 summation order and the bf16 rounding of stored outputs.
+Tolerances are written next to each check.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+def _setup():
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+
+
+def bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def plane_interior(plane, c_off, C):
+    """[B,Hp,Wp,Cs] bf16 -> [B,C,H,W] fp32"""
+    return plane[:, 1:-1, 1:-1, c_off:c_off + C].permute(0, 3, 1, 2).float().contiguous()
+
+
+def ref_plane(x_nchw, wrap):
+    """[B,C,H,W] -> padded [B,C,H+2,W+2]"""
+    return F.pad(x_nchw, (1, 1, 1, 1), mode="circular" if wrap else "constant")
+
+
+def ref_conv(x_nchw, w, wrap):
+    return F.conv2d(ref_plane(x_nchw, wrap), w)
+
+
+def make_plane(x_nchw, Cs, c_off, wrap):
+    from scm_gan_b200 import kernels as K
+    B, C, H, W = x_nchw.shape
+    plane = torch.full((B, H + 2, W + 2, Cs), float("nan"), dtype=torch.bfloat16, device=DEV)
+    K.pack_nchw(x_nchw, plane, c_off=c_off, c_pad=(C + 15) // 16 * 16, wrap=wrap)
+    return plane
+
+
+def pack_conv_weight(w, n_pad, k_pad, sigma=None, dgrad=False, k_src_off=0, k_valid=None):
+    """w: Conv2d weight [Co,Ci,3,3] -> packed [9][n_pad][k_pad]"""
+    from scm_gan_b200 import kernels as K
+    Co, Ci = w.shape[:2]
+    out = K.packed_weight(n_pad, k_pad, w.device)
+    if not dgrad:
+        job = dict(w=w, out=out, sigma=sigma, n_pad=n_pad, k_pad=k_pad, n_valid=Co,
+                   k_valid=Ci if k_valid is None else k_valid, s_n=Ci * 9, s_k=9, k_src_off=k_src_off, flip=0)
+    else:
+        job = dict(w=w, out=out, sigma=sigma, n_pad=n_pad, k_pad=k_pad, n_valid=Ci, k_valid=Co, s_n=9, s_k=Ci * 9,
+                   flip=1)
+    K.pack_weights([job])
+    return out
+
+
+def relerr(a, b):
+    return ((a - b).norm() / (b.norm() + 1e-30)).item()
+
+
+def report(name, got, ref, tol):
+    err = (got - ref).abs().max().item()
+    rel = relerr(got, ref)
+    ok = rel <= tol and bool(torch.isfinite(got).all())
+    print(f"[{name}] max_abs={err:.3e} rel_l2={rel:.3e} tol={tol:.1e} ref_norm={ref.norm().item():.3e} "
+          f"{'OK' if ok else 'FAIL'}", flush=True)
+    if not ok:
+        d = (got - ref).abs().flatten()
+        idx = d.argsort(descending=True)[:5]
+        for i in idx.tolist():
+            print("    worst idx", i, "got", got.flatten()[i].item(), "ref", ref.flatten()[i].item())
+    return ok
+
+
+# ------------------------------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("wrap", [False, True])
+def test_pack_nchw(wrap):
+    _setup()
+    torch.manual_seed(1)
+    B, C, H, W = 3, 9, 5, 7
+    x = torch.randn(B, C, H, W, device=DEV)
+    plane = make_plane(x, 32, 16, wrap)
+    got = plane[:, :, :, 16:32].permute(0, 3, 1, 2).float()
+    ref = torch.zeros(B, 16, H + 2, W + 2, device=DEV)
+    ref[:, :C] = bf(ref_plane(x, wrap))
+    assert torch.equal(got, ref)
+
+
+CONV_CASES = [
+    # (B, H, W, Cin, Cout, wrap, act)
+    (3, 15, 19, 128, 128, False, 1),
+    (2, 15, 19, 128, 128, True, 1),
+    (2, 8, 8, 16, 128, True, 1),
+    (2, 6, 10, 64, 64, False, 0),
+    (1, 64, 64, 256, 128, True, 1),
+    (5, 9, 7, 256, 16, True, 0),
+    (2, 16, 16, 128, 48, False, 0),
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES)
+def test_conv_fwd_plane(case):
+    """bias + activation epilogue, bf16 plane output incl. halo handling."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    B, H, W, Ci, Co, wrap, act = case
+    torch.manual_seed(2)
+    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    bias = torch.randn(Co, device=DEV)
+    xp = make_plane(x, Ci, 0, wrap)
+    wp = pack_conv_weight(w, Co, Ci)
+    out = torch.full((B, H + 2, W + 2, Co + 16), float("nan"), dtype=torch.bfloat16, device=DEV)
+    K.conv3x3(xp, wp, B, H, W, cin=Ci, bias=bias, act=act, out=out, out_c_off=16, wrap=wrap)
+    torch.cuda.synchronize()
+    ref = ref_conv(x, w, wrap) + bias.view(1, -1, 1, 1)
+    if act == 1:
+        ref = F.leaky_relu(ref)
+    got = plane_interior(out, 16, Co)
+    # bf16 output rounding: 2^-9 relative per element
+    assert report(f"conv_fwd {case}", got, ref, 4e-3)
+    # halo of the produced plane: wrapped copy or zeros
+    full = out[:, :, :, 16:16 + Co].permute(0, 3, 1, 2).float()
+    assert torch.equal(full, ref_plane(got, wrap)), "halo mismatch"
+    # channels outside the written window stay untouched (NaN sentinel)
+    assert torch.isnan(out[:, :, :, :16].float()).all()
+
+
+def test_conv_sample_bias_and_f32_head():
+    """Transition conv1-style per-sample bias; conv6-style sigmoid + Bernoulli head with fp32 NCHW outputs."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(3)
+    B, H, W, Ci, Co = 4, 15, 19, 256, 16
+    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    bias = torch.randn(Co, device=DEV)
+    sb = torch.randn(B, Co, device=DEV)
+    u = torch.rand(B, Co, H, W, device=DEV)
+    xp = make_plane(x, Ci, 0, True)
+    wp = pack_conv_weight(w, Co, Ci)
+    p = torch.empty(B, Co, H, W, device=DEV)
+    z = torch.empty(B, Co, H, W, device=DEV)
+    K.conv3x3(xp, wp, B, H, W, cin=Ci, bias=bias, sample_bias=sb, act=2, out_f32=p, n_valid=Co, sample_out=z,
+              uniforms=u)
+    ref = torch.sigmoid(ref_conv(x, w, True) + bias.view(1, -1, 1, 1) + sb.view(B, Co, 1, 1))
+    assert report("conv f32 head p", p, ref, 1e-4)
+    zr = (u < p).float()
+    assert torch.equal(z, zr)
+    # eval mode: threshold
+    K.conv3x3(xp, wp, B, H, W, cin=Ci, bias=bias, sample_bias=sb, act=2, out_f32=p, n_valid=Co, sample_out=z)
+    assert torch.equal(z, (p > 0.5).float())
+
+
+def test_conv_dgrad_epilogue():
+    """dgrad = conv with flipped/transposed weights; epilogue adds a residual plane and gates with lrelu'."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(4)
+    B, H, W, Ci, Co = 2, 15, 19, 128, 128
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    dy = bf(torch.randn(B, Co, H, W, device=DEV))
+    resid = bf(torch.randn(B, Ci, H, W, device=DEV))
+    actv = bf(torch.randn(B, Ci, H, W, device=DEV))
+    for wrap in (True, False):
+        dyp = make_plane(dy, Co, 0, wrap)
+        rp = make_plane(resid, Ci, 0, wrap)
+        ap = make_plane(actv, Ci, 0, wrap)
+        wd = pack_conv_weight(w, Ci, Co, dgrad=True)
+        out = K.new_plane(B, H, W, Ci, DEV)
+        K.conv3x3(dyp, wd, B, H, W, cin=Co, out=out, wrap=wrap, add=rp, gate=ap, dgrad=True)
+        # reference: autograd of the forward conv
+        xin = torch.zeros(B, Ci, H, W, device=DEV, requires_grad=True)
+        y = ref_conv(xin, w, wrap)
+        (gx,) = torch.autograd.grad(y, xin, dy)
+        ref = (gx + resid) * torch.where(actv > 0, 1.0, 0.01)
+        got = plane_interior(out, 0, Ci)
+        assert report(f"dgrad wrap={wrap}", got, ref, 4e-3)
+
+
+WGRAD_CASES = [
+    # (B, H, W, Cin, Cout, wrap)
+    (3, 15, 19, 128, 128, True),
+    (2, 64, 64, 128, 128, True),
+    (2, 15, 19, 256, 128, True),
+    (3, 15, 19, 16, 128, False),
+    (3, 15, 19, 256, 16, True),
+    (2, 16, 16, 128, 16, False),
+    (2, 15, 19, 128, 48, False),
+]
+
+
+@pytest.mark.parametrize("case", WGRAD_CASES)
+def test_wgrad(case):
+    _setup()
+    from scm_gan_b200 import kernels as K
+    B, H, W, Ci, Co, wrap = case
+    torch.manual_seed(5)
+    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    dy = bf(torch.randn(B, Co, H, W, device=DEV))
+    xp = make_plane(x, Ci, 0, wrap)
+    dyp = make_plane(dy, Co, 0, wrap)  # halo deliberately non-zero in wrap mode: must be ignored
+    g = torch.zeros(Co, Ci, 3, 3, device=DEV)
+    K.wgrad(dyp, xp, g, B, H, W, cout=Co, cin=Ci, g_s_co=Ci * 9, g_s_ci=9)
+    w = torch.zeros(Co, Ci, 3, 3, device=DEV, requires_grad=True)
+    y = ref_conv(x, w, wrap)
+    (gw,) = torch.autograd.grad(y, w, dy)
+    assert report(f"wgrad {case}", g, gw, 1e-4)
+
+
+def test_spectral_norm_fwd_bwd():
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(6)
+    shapes = [(128, 21, 3, 3), (128, 128, 3, 3), (128, 256, 3, 3)]
+    ws = [torch.randn(s, device=DEV) * 0.05 for s in shapes]
+    us = [F.normalize(torch.randn(s[0], device=DEV), dim=0) for s in shapes]
+    vs = [F.normalize(torch.randn(s[1] * 9, device=DEV), dim=0) for s in shapes]
+    sig = torch.zeros(len(shapes), device=DEV)
+    u2 = [u.clone() for u in us]
+    v2 = [v.clone() for v in vs]
+    usave = [torch.empty_like(u) for u in us]
+    vsave = [torch.empty_like(v) for v in vs]
+    K.spectral_norm_fwd([(w, u2[i], v2[i], sig[i:i + 1], usave[i], vsave[i]) for i, w in enumerate(ws)])
+    for i, w in enumerate(ws):
+        wm = w.view(w.shape[0], -1)
+        v = wm.t().mv(us[i]); v = v / (v.norm() + 1e-12)
+        u = wm.mv(v); u = u / (u.norm() + 1e-12)
+        s = u.dot(wm.mv(v))
+        assert report(f"sn v {i}", v2[i], v, 1e-5)
+        assert report(f"sn u {i}", u2[i], u, 1e-5)
+        assert abs(sig[i].item() - s.item()) <= 1e-5 * abs(s.item())
+        assert torch.equal(usave[i], u2[i]) and torch.equal(vsave[i], v2[i])
+        # backward
+        g = torch.randn_like(w)
+        wb = w.clone().requires_grad_(True)
+        sigma = u.dot(wb.view(wb.shape[0], -1).mv(v))
+        (ref,) = torch.autograd.grad(wb / sigma.expand_as(wb), wb, g)
+        dot = torch.zeros(1, device=DEV)
+        out = torch.empty_like(w)
+        K.spectral_norm_bwd([(g, w, usave[i], vsave[i], sig[i:i + 1], dot, out)])
+        assert report(f"sn bwd {i}", out, ref, 1e-4)
+
+
+def test_colsum_action_bce_adam():
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(7)
+    B, H, W, Cc = 3, 15, 19, 128
+    x = bf(torch.randn(B, Cc, H, W, device=DEV))
+    xp = make_plane(x, Cc + 16, 16, True)
+    S = torch.zeros(B, Cc, device=DEV)
+    db = torch.zeros(Cc, device=DEV)
+    K.plane_colsum(xp, 16, Cc, B, H, W, S=S, db=db)
+    assert report("colsum S", S, x.sum((2, 3)), 1e-5)
+    assert report("colsum db", db, x.sum((0, 2, 3)), 1e-5)
+
+    # folded action channels
+    Lz, A = 16, 5
+    wbar = torch.randn(128, Lz + A, 3, 3, device=DEV)
+    sigma = torch.tensor([1.7], device=DEV)
+    bias = torch.randn(128, device=DEV)
+    act = torch.eye(A, device=DEV)[torch.randint(A, (B,), device=DEV)]
+    sb = torch.empty(B, 128, device=DEV)
+    K.action_bias(wbar, sigma, bias, act, Lz, sb)
+    ref = bias + act @ (wbar[:, Lz:].sum((2, 3)) / sigma).t()
+    assert report("action_bias", sb, ref, 1e-5)
+    g = torch.zeros_like(wbar)
+    K.action_wgrad(S, act, Lz, g)
+    refg = (S.t() @ act).view(128, A, 1, 1).expand(128, A, 3, 3)
+    assert report("action_wgrad", g[:, Lz:], refg, 1e-5)
+    assert g[:, :Lz].abs().max().item() == 0
+
+    # fused sigmoid + BCE + masked mean, forward value and gradient
+    logits = torch.randn(B, 3, H, W, device=DEV) * 3
+    states = (torch.rand(B, 4, 3, H, W, device=DEV) < 0.15).float()
+    tgt = states[:, 2]
+    mask = torch.tensor([1.0, 0.0, 1.0], device=DEV)
+    loss = torch.zeros(1, device=DEV)
+    dx = torch.empty_like(logits)
+    K.bce_logits(logits, tgt, mask, loss, dx)
+    lg = logits.clone().requires_grad_(True)
+    rl = (F.binary_cross_entropy(torch.sigmoid(lg), tgt, reduction="none").mean(-1).mean(-1).mean(-1) * mask).mean()
+    rl.backward()
+    assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
+    assert report("bce dx", dx, lg.grad, 1e-5)
+
+    # fused clip + Adam vs torch.optim.Adam after clip_grad_value_
+    ps = [torch.randn(1000, device=DEV), torch.randn(77, 3, device=DEV)]
+    gs = [torch.randn_like(p) * 0.3 for p in ps]
+    ref_ps = [p.clone().requires_grad_(True) for p in ps]
+    opt = torch.optim.Adam(ref_ps, lr=1e-4)
+    ms = [torch.zeros_like(p) for p in ps]
+    vv = [torch.zeros_like(p) for p in ps]
+    for step in range(1, 4):
+        for rp, g in zip(ref_ps, gs):
+            rp.grad = g.clone()
+        torch.nn.utils.clip_grad_value_(ref_ps, 0.1)
+        opt.step()
+        K.clip_adam([(p, g, m, v, 0.1) for p, g, m, v in zip(ps, gs, ms, vv)], 1e-4, 0.9, 0.999, 1e-8, step)
+    for p, rp in zip(ps, ref_ps):
+        assert report("adam", p, rp.detach(), 1e-6)
+
+
+if __name__ == "__main__":
+    import sys
+    import traceback
+    fails = 0
+
+    def run(fn, *a):
+        global fails
+        try:
+            fn(*a)
+            torch.cuda.synchronize()
+        except Exception:
+            fails += 1
+            traceback.print_exc()
+            print(f"FAILED {fn.__name__} {a}", flush=True)
+            try:
+                torch.cuda.synchronize()
+            except Exception as e:  # sticky CUDA error: stop
+                print("sticky CUDA error, aborting:", e)
+                sys.exit(2)
+
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only in ("", "pack"):
+        run(test_pack_nchw, False)
+        run(test_pack_nchw, True)
+    if only in ("", "conv"):
+        for c in CONV_CASES:
+            run(test_conv_fwd_plane, c)
+        run(test_conv_sample_bias_and_f32_head)
+        run(test_conv_dgrad_epilogue)
+    if only in ("", "wgrad"):
+        for c in WGRAD_CASES:
+            run(test_wgrad, c)
+    if only in ("", "misc"):
+        run(test_spectral_norm_fwd_bwd)
+        run(test_colsum_action_bce_adam)
+    print("failures:", fails)
+    sys.exit(1 if fails else 0)
