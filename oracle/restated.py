@@ -33,17 +33,17 @@ def l2normalize(v, eps=1e-12):
 def spectral_norm_weight(sd, prefix):
     """reference spectral_normalization.py:23-35 (`_update_u_v`, power_iterations=1).
 
-    Mutates sd[prefix+'weight_u'/'weight_v'] exactly like the `.data` assignments and returns the normalised weight
-    (differentiable w.r.t. weight_bar through both the division and sigma)."""
+    u and v are advanced through `.data` assignments exactly like the reference.  Consequence (verified against
+    the live reference, see DESIGN.md "SpectralNorm backward"): autograd saves the u/v *Parameters*, not their
+    values, so when a wrapped conv is called several times before backward() (every rollout step), the gradient
+    of every call's sigma is taken with the u, v of the LAST call:
+        dWbar = sum_t [ G_t/sigma_t - (<G_t, Wbar>/sigma_t^2) * u_last v_last^T ].
+    Returns the normalised weight (differentiable w.r.t. weight_bar through the division and sigma)."""
     u, v, w = sd[prefix + "weight_u"], sd[prefix + "weight_v"], sd[prefix + "weight_bar"]
     height = w.shape[0]
-    wm = w.detach().view(height, -1)
-    v_new = l2normalize(torch.mv(wm.t(), u.detach()))
-    u_new = l2normalize(torch.mv(wm, v_new))
-    with torch.no_grad():
-        v.copy_(v_new)
-        u.copy_(u_new)
-    sigma = u_new.dot(w.view(height, -1).mv(v_new))
+    v.data = l2normalize(torch.mv(torch.t(w.view(height, -1).data), u.data))
+    u.data = l2normalize(torch.mv(w.view(height, -1).data, v.data))
+    sigma = u.dot(w.view(height, -1).mv(v))
     return w / sigma.expand_as(w)
 
 
