@@ -38,12 +38,16 @@ typedef void* scmgan_stream_t; /* cudaStream_t */
 int scmgan_version(void);
 const char* scmgan_last_error(void);
 int scmgan_num_sms(void);
+/* number of kernels this library has launched so far in this process (diagnostics: bench.py "gpu_launches") */
+long long scmgan_launch_count(void);
 
 /* fp32 NCHW tensor (batch stride src_bstride elements, channel stride H*W) -> plane channels
  * [c_off, c_off+c_pad), zero-filling channels >= C; halo = wrap (1) or zeros (0).
+ * sig (optional, dense fp32 [B][C][H][W]): multiply by sig*(1-sig) - the backward of the output sigmoid
+ * (reference models.py:103,154) fused into the packing of the incoming gradient.
  * Replaces x.view / torch.cat / F.pad(mode='circular') copies: reference models.py:69-73, 143, 76-103. */
 int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
-                     int c_off, int c_pad, int wrap, scmgan_stream_t stream);
+                     int c_off, int c_pad, int wrap, const float* sig, scmgan_stream_t stream);
 
 /* Weight packing fp32 parameter -> bf16 [9][n_pad][k_pad] GEMM operand, optionally divided by *sigma
  * (the `w / sigma` of reference spectral_normalization.py:35).
@@ -150,6 +154,14 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
 int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
                       float* loss, float* dx, scmgan_stream_t stream);
 
+/* Reward head of RewardPredictor (reference models.py:240-250): softmax over the 3 classes of each reward,
+ * p(+1) - p(-1), summed over the stride-2 valid lattice of the second conv.  y2 is that conv evaluated as a
+ * stride-1 same-size conv, fp32 [B][3R][H][W]; r [B][R]; map (optional) [B][R][h2][w2].
+ * The backward writes the gradient w.r.t. y2 as a bf16 plane [B][H+2][W+2][16] (zero off the lattice). */
+int scmgan_reward_head_fwd(const float* y2, int B, int R, int H, int W, float* r, float* map, scmgan_stream_t stream);
+int scmgan_reward_head_bwd(const float* y2, const float* dr, int B, int R, int H, int W, void* d2_plane,
+                           scmgan_stream_t stream);
+
 /* clip_grad_value_ + Adam in one multi-tensor launch (reference main.py:287-296). */
 typedef struct {
     float* p;
@@ -157,7 +169,8 @@ typedef struct {
     float* m;
     float* v;
     int n;
-    float clip;
+    float clip;        /* <= 0: no clipping */
+    const float* step; /* optional per-chunk device step counter (float); overrides step/step_dev */
 } scmgan_adam_chunk;
 int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks_host, float lr, float beta1, float beta2, float eps,
                      int step, const float* step_dev, float gscale, scmgan_stream_t stream);

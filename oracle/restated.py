@@ -47,14 +47,64 @@ def spectral_norm_weight(sd, prefix):
     return w / sigma.expand_as(w)
 
 
-def _sn_conv(sd, name, x, circular):
+# --------------------------------------------------------------------------------------------------------------
+# Optional operand rounding ("bf16-operand restatement").  With OPERAND_DTYPE = None (default) everything below is
+# the plain fp32 algorithm.  With OPERAND_DTYPE = torch.bfloat16 the *same* algorithm is evaluated with conv inputs,
+# normalised weights and the gradients entering each conv's backward rounded to that dtype (fp32 accumulation), i.e.
+# the arithmetic contract BASELINE.json's north_star prescribes for the tensor-core path.  Tests use it to separate
+# "kernel bug" from "operand precision": LeakyReLU kinks turn a 2^-9 operand rounding into percent-level L2
+# differences of fp32 gradients (sign flips of near-zero pre-activations), see DESIGN.md "Parity".
+# --------------------------------------------------------------------------------------------------------------
+OPERAND_DTYPE = None
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        return x.to(dtype).to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, None
+
+
+class _RoundGrad(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, dtype):
+        ctx.dtype = dtype
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.to(ctx.dtype).to(g.dtype), None
+
+
+def _q(x):
+    """operand rounding (forward), straight-through gradient"""
+    return x if OPERAND_DTYPE is None else _RoundSTE.apply(x, OPERAND_DTYPE)
+
+
+def _qg(x):
+    """identity forward; the gradient flowing back through this point is rounded (gradient planes are bf16)"""
+    return x if OPERAND_DTYPE is None else _RoundGrad.apply(x, OPERAND_DTYPE)
+
+
+def _sn_conv(sd, name, x, circular, exact_tail=0):
     """SpectralNorm(nn.Conv2d(..., 3x3, stride 1)) forward: reference spectral_normalization.py:66-68 +
-    models.py:51-55 / 129-133.  circular => legacy wrap-by-one padding, else zero padding 1."""
+    models.py:51-55 / 129-133.  circular => legacy wrap-by-one padding, else zero padding 1.
+    exact_tail: number of trailing input channels kept in fp32 under operand rounding (the spatially constant
+    action channels of Transition.conv1, which the product folds into an fp32 per-sample bias)."""
     w = spectral_norm_weight(sd, name + ".module.")
     b = sd[name + ".module.bias"]
+    if OPERAND_DTYPE is not None and exact_tail:
+        n = x.shape[1] - exact_tail
+        xq = torch.cat([_q(x[:, :n]), x[:, n:]], dim=1)
+        wq = torch.cat([_q(w[:, :n]), w[:, n:]], dim=1)
+    else:
+        xq, wq = _q(x), _q(w)
     if circular:
-        return F.conv2d(F.pad(x, (1, 1, 1, 1), mode="circular"), w, b)
-    return F.conv2d(x, w, b, padding=1)
+        return _qg(F.conv2d(F.pad(xq, (1, 1, 1, 1), mode="circular"), wq, b))
+    return _qg(F.conv2d(xq, wq, b, padding=1))
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -68,7 +118,7 @@ def encoder_forward(sd, x):
     x = F.leaky_relu(_sn_conv(sd, "conv1", x, False))
     x = F.leaky_relu(_sn_conv(sd, "conv2", x, False))
     x = F.leaky_relu(_sn_conv(sd, "conv3", x, False))
-    x = F.conv2d(x, sd["conv4.weight"], sd["conv4.bias"], padding=1)
+    x = _qg(F.conv2d(_q(x), _q(sd["conv4.weight"]), sd["conv4.bias"], padding=1))
     return torch.sigmoid(x)
 
 
@@ -90,7 +140,7 @@ def transition_forward(sd, z, a, training=True, uniforms=None, return_all=False,
     assert a.shape[0] == b  # models.py:66
     actions = a.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, h, w)
     x = torch.cat([z, actions], dim=1)
-    x = F.leaky_relu(_sn_conv(sd, "conv1", x, True))
+    x = F.leaky_relu(_sn_conv(sd, "conv1", x, True, exact_tail=a.shape[1]))
     skip1 = x
     x = F.leaky_relu(_sn_conv(sd, "conv2", x, True))
     skip2 = x
@@ -102,9 +152,11 @@ def transition_forward(sd, z, a, training=True, uniforms=None, return_all=False,
     x = F.leaky_relu(_sn_conv(sd, "conv5", x, True))
     out5 = x
     x = torch.cat([x, skip1], dim=1)
-    x = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="circular"), sd["conv6.weight"], sd["conv6.bias"])
+    x = _qg(F.conv2d(F.pad(_q(x), (1, 1, 1, 1), mode="circular"), _q(sd["conv6.weight"]), sd["conv6.bias"]))
     p = torch.sigmoid(x)
     if training:
+        if callable(uniforms):  # hook(p) -> uniforms, lets a test keep its draws away from p (margin-safe sampling)
+            uniforms = uniforms(p.detach())
         if uniforms is None:
             uniforms = torch.rand_like(p)
         x = _StraightThroughBernoulli.apply(p, uniforms)
@@ -120,10 +172,16 @@ def transition_forward(sd, z, a, training=True, uniforms=None, return_all=False,
 def decoder_forward(sd, z, visualize=False):
     """reference models.py:270-291.  Returns logits [B, C, H, W] (caller applies sigmoid, main.py:189)."""
     b, latent, h, w = z.shape
-    x = F.conv_transpose2d(z, sd["conv1.weight"], sd["conv1.bias"], stride=1, padding=1)
+    x = _qg(F.conv_transpose2d(_q(z), _q(sd["conv1.weight"]), sd["conv1.bias"], stride=1, padding=1))
     x = F.leaky_relu(x)
-    x = F.conv_transpose2d(x, sd["conv2.weight"], sd["conv2.bias"], stride=1, padding=1)
-    color = x.shape[1] // latent
+    w2, b2 = sd["conv2.weight"], sd["conv2.bias"]
+    color = w2.shape[1] // latent
+    if OPERAND_DTYPE is not None and not visualize:
+        # the product sums the latent groups of the (linear) last layer in fp32 *before* rounding the weights
+        w2f = w2.view(w2.shape[0], latent, color, 3, 3).sum(1)
+        b2f = b2.view(latent, color).sum(0)
+        return _qg(F.conv_transpose2d(_q(x), _q(w2f), b2f, stride=1, padding=1))
+    x = _qg(F.conv_transpose2d(_q(x), _q(w2), b2, stride=1, padding=1))
     x = x.view(b, latent, color, h, w)
     vis = x[0]
     x = torch.sum(x, dim=1)
@@ -134,8 +192,8 @@ def decoder_forward(sd, z, visualize=False):
 
 def reward_forward(sd, z, visualize=False):
     """reference models.py:235-250.  [B, L, H, W] -> [B, R]"""
-    x = F.leaky_relu(F.conv2d(z, sd["conv1.weight"], sd["conv1.bias"]))
-    x = F.conv2d(x, sd["conv2.weight"], sd["conv2.bias"], stride=2)
+    x = F.leaky_relu(_qg(F.conv2d(_q(z), _q(sd["conv1.weight"]), sd["conv1.bias"])))
+    x = _qg(F.conv2d(_q(x), _q(sd["conv2.weight"]), sd["conv2.bias"], stride=2))
     b, ch, h, w = x.shape
     x = torch.softmax(x.view(b, 3, ch // 3, h, w), dim=1)
     x = x[:, 0] - x[:, 2]
@@ -230,10 +288,10 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
     bsz = states.shape[0]
     hn = states.shape[1]
     eye = torch.eye(num_actions, dtype=states.dtype, device=states.device)
-    it = iter(uniforms) if uniforms is not None else None
+    it = iter(uniforms) if (uniforms is not None and not callable(uniforms)) else None
 
     def trans(zz, aa):
-        u = next(it) if it is not None else None
+        u = next(it) if it is not None else uniforms
         return transition_forward(nets["transition"], zz, aa, training=True, uniforms=u)
 
     z = encoder_forward(nets["encoder"], states[:, 0:3])  # main.py:162

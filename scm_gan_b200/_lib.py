@@ -54,7 +54,7 @@ class SnBwdLayer(C.Structure):
 
 class AdamChunk(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
-                ("n", C.c_int), ("clip", C.c_float)]
+                ("n", C.c_int), ("clip", C.c_float), ("step", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol include/scmgan.h declares (tests check this)
@@ -62,8 +62,9 @@ SIGNATURES = {
     "scmgan_version": (C.c_int, []),
     "scmgan_last_error": (C.c_char_p, []),
     "scmgan_num_sms": (C.c_int, []),
+    "scmgan_launch_count": (C.c_longlong, []),
     "scmgan_pack_nchw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "scmgan_pack_weights": (C.c_int, [C.c_int, C.POINTER(PackJob), C.c_void_p]),
     "scmgan_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "scmgan_conv3x3_dgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
@@ -78,6 +79,10 @@ SIGNATURES = {
                                       C.c_void_p]),
     "scmgan_bce_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_reward_head_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "scmgan_reward_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                         C.c_void_p]),
     "scmgan_clip_adam": (C.c_int, [C.c_int, C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
 }

@@ -7,12 +7,14 @@
 #include "host_util.cuh"
 
 #include <algorithm>
+#include <atomic>
 #include <mutex>
 #include <string.h>
 
 namespace scm {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};  // kernels launched through this library (reported by bench.py)
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -103,6 +105,7 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Igem
     const int grid = std::min(P.num_tiles, num_sms());
     conv3x3_igemm_kernel<CK><<<grid, kIgemmThreads, smem, st>>>(ta, tb, P, stages);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -241,6 +244,7 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     const int smem = stages * stage_bytes + 1024 + 256;
     conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -253,9 +257,10 @@ extern "C" {
 int scmgan_version(void) { return 100; }
 const char* scmgan_last_error(void) { return g_err; }
 int scmgan_num_sms(void) { return num_sms(); }
+long long scmgan_launch_count(void) { return g_launches.load(); }
 
 int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
-                     int c_off, int c_pad, int wrap, scmgan_stream_t stream) {
+                     int c_off, int c_pad, int wrap, const float* sig, scmgan_stream_t stream) {
     SCM_REQUIRE(src && dst_plane, "pack_nchw: null pointer");
     SCM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "pack_nchw: bad geometry");
     SCM_REQUIRE(Cs % 8 == 0 && c_off % 8 == 0 && c_pad % 8 == 0 && c_pad >= C && c_off + c_pad <= Cs,
@@ -264,8 +269,9 @@ int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int 
     const int threads = 128;
     const long long blocks = (rows + threads - 1) / threads;
     pack_nchw_to_plane_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap);
+        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap, sig);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -290,6 +296,7 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t 
         const int bx = int(std::min<long long>((max_total + threads - 1) / threads, 296));
         pack_weights_kernel<<<dim3(bx, J.count), threads, 0, (cudaStream_t)stream>>>(J);
         SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     }
     return SCM_OK;
 }
@@ -353,6 +360,7 @@ int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int 
     plane_colsum_kernel<<<dim3(chunks, B), threads, lanes * n * sizeof(float), (cudaStream_t)stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(plane), Cs, c_off, n, B, H, W, S, db, rows_per_block);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -371,6 +379,7 @@ int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_st
     SCM_REQUIRE(max_smem <= 48 * 1024, "spectral_norm_fwd: layer too large");
     sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -386,8 +395,10 @@ int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmga
     }
     sn_bwd_dot_kernel<<<dim3(32, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     sn_bwd_apply_kernel<<<dim3(64, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -398,6 +409,7 @@ int scmgan_action_bias(const float* wbar, const float* sigma, const float* bias,
     action_bias_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(wbar, sigma, bias, act, B, Cout, L, A,
                                                                              out);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -407,6 +419,7 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
     const int total = Cout * A;
     action_wgrad_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, act, B, Cout, L, A, g);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -418,6 +431,30 @@ int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const
     bx = std::max(bx, 1);
     bce_logits_kernel<<<dim3(bx, B), threads, 0, (cudaStream_t)stream>>>(x, y, y_bstride, mask, B, per, loss, dx);
     SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_reward_head_fwd(const float* y2, int B, int R, int H, int W, float* r, float* map,
+                           scmgan_stream_t stream) {
+    SCM_REQUIRE(y2 && r && B > 0 && R > 0 && 3 * R <= 16 && H >= 5 && W >= 5, "reward_head_fwd: bad arguments");
+    const int h2 = (H - 5) / 2 + 1, w2 = (W - 5) / 2 + 1;
+    reward_head_fwd_kernel<<<dim3(B, R), 128, 0, (cudaStream_t)stream>>>(y2, B, R, H, W, h2, w2, r, map);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_reward_head_bwd(const float* y2, const float* dr, int B, int R, int H, int W, void* d2_plane,
+                           scmgan_stream_t stream) {
+    SCM_REQUIRE(y2 && dr && d2_plane && B > 0 && R > 0 && 3 * R <= 16 && H >= 5 && W >= 5,
+                "reward_head_bwd: bad arguments");
+    const int h2 = (H - 5) / 2 + 1, w2 = (W - 5) / 2 + 1;
+    const long long rows = (long long)B * (H + 2) * (W + 2);
+    reward_head_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        y2, dr, B, R, H, W, h2, w2, reinterpret_cast<__nv_bfloat16*>(d2_plane));
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     return SCM_OK;
 }
 
@@ -433,7 +470,7 @@ int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float
         for (int i = 0; i < A.count; ++i) {
             const scmgan_adam_chunk& c = chunks[base + i];
             SCM_REQUIRE(c.p && c.g && c.m && c.v && c.n > 0, "clip_adam: bad chunk %d", base + i);
-            A.chunk[i] = AdamChunk{c.p, c.g, c.m, c.v, c.n, c.clip};
+            A.chunk[i] = AdamChunk{c.p, c.g, c.m, c.v, c.n, c.clip, c.step};
             max_n = std::max(max_n, c.n);
         }
         A.lr = lr; A.beta1 = beta1; A.beta2 = beta2; A.eps = eps; A.step_ptr = step_dev; A.gscale = gscale;
@@ -444,6 +481,7 @@ int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float
         const int bx = std::max(1, std::min((max_n + 1023) / 1024, 64));
         clip_adam_kernel<<<dim3(bx, A.count), 256, 0, (cudaStream_t)stream>>>(A);
         SCM_CUDA(cudaGetLastError());
+    ++g_launches;
     }
     return SCM_OK;
 }

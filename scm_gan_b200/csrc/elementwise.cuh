@@ -9,9 +9,11 @@ namespace scm {
 // fp32 NCHW (caller tensors) -> bf16 plane [B][H+2][W+2][Cs] at channel offset c_off, halo = wrap or zero.
 // One thread per plane pixel; channels [c_off, c_off + c_pad) are written (zeros beyond C).
 // ----------------------------------------------------------------------------------------------
+// Optional `sig` (fp32 NCHW, dense): multiply by sig*(1-sig), i.e. the sigmoid derivative of a saved
+// probability map (backward of the Encoder / Transition output sigmoid, reference models.py:103,154).
 __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long long src_bstride, int C, int B, int H,
                                           int W, __nv_bfloat16* __restrict__ dst, int Cs, int c_off, int c_pad,
-                                          int wrap) {
+                                          int wrap, const float* __restrict__ sig) {
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -28,6 +30,7 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
         zero = (h < 0 || h >= H || w < 0 || w >= W);
     }
     const float* s = src + (long long)b * src_bstride + (long long)h * W + w;
+    const float* sg = sig ? sig + ((long long)b * C * H + h) * W + w : nullptr;
     __nv_bfloat16* d = dst + p * Cs + c_off;
     for (int c0 = 0; c0 < c_pad; c0 += 8) {
         uint4 o;
@@ -36,7 +39,13 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
         for (int i = 0; i < 8; ++i) {
             const int c = c0 + i;
             float x = 0.f;
-            if (!zero && c < C) x = __ldg(s + (long long)c * H * W);
+            if (!zero && c < C) {
+                x = __ldg(s + (long long)c * H * W);
+                if (sg) {
+                    const float q = __ldg(sg + (long long)c * H * W);
+                    x *= q * (1.f - q);
+                }
+            }
             oh[i] = __float2bfloat16_rn(x);
         }
         *reinterpret_cast<uint4*>(d + c0) = o;
@@ -327,6 +336,7 @@ struct AdamChunk {
     float* v;
     int n;
     float clip;  // <= 0: no clipping
+    const float* step;  // per-chunk device step counter (torch keeps one per parameter), or nullptr
 };
 constexpr int kAdamChunksPerLaunch = 48;
 struct AdamArgs {
@@ -341,8 +351,9 @@ struct AdamArgs {
 __global__ void clip_adam_kernel(const __grid_constant__ AdamArgs A) {
     const AdamChunk& C = A.chunk[blockIdx.y];
     float bc1 = A.bc1, bc2s = A.bc2_sqrt;
-    if (A.step_ptr) {
-        const float t = __ldg(A.step_ptr);
+    const float* sp = C.step ? C.step : A.step_ptr;
+    if (sp) {
+        const float t = __ldg(sp);
         bc1 = 1.f - powf(A.beta1, t);
         bc2s = sqrtf(1.f - powf(A.beta2, t));
     }
@@ -357,6 +368,84 @@ __global__ void clip_adam_kernel(const __grid_constant__ AdamArgs A) {
         const float denom = sqrtf(v) / bc2s + A.eps;
         C.p[i] -= step_size * (m / denom);
     }
+}
+
+}  // namespace scm
+
+namespace scm {
+
+// ----------------------------------------------------------------------------------------------
+// Reward head (reference models.py:240-250): the second conv is stride-2 / valid, evaluated here as a
+// stride-1 same-size conv whose outputs are only consumed on the lattice (2a+2, 2b+2) of interior
+// coordinates.  y2: fp32 [B][3R][H][W] (class-major channels: k*R + j).
+//   r[b][j] = sum_{lattice} softmax_k(y2)[0] - softmax_k(y2)[2]
+// Optionally writes the per-pixel map [B][R][h2][w2] (visualize=True).
+// ----------------------------------------------------------------------------------------------
+__global__ void reward_head_fwd_kernel(const float* __restrict__ y2, int B, int R, int H, int W, int h2, int w2,
+                                       float* __restrict__ r, float* __restrict__ map) {
+    __shared__ float red[33];
+    const int b = blockIdx.x, j = blockIdx.y;
+    const size_t hw = size_t(H) * W;
+    const float* base = y2 + (size_t(b) * 3 * R + j) * hw;
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < h2 * w2; i += blockDim.x) {
+        const int a = i / w2, c = i - a * w2;
+        const size_t pos = size_t(2 * a + 2) * W + (2 * c + 2);
+        const float l0 = __ldg(base + pos), l1 = __ldg(base + size_t(R) * hw + pos),
+                    l2 = __ldg(base + size_t(2 * R) * hw + pos);
+        const float m = fmaxf(l0, fmaxf(l1, l2));
+        const float e0 = __expf(l0 - m), e1 = __expf(l1 - m), e2 = __expf(l2 - m);
+        const float d = (e0 - e2) / (e0 + e1 + e2);
+        if (map) map[(size_t(b) * R + j) * h2 * w2 + i] = d;
+        acc += d;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) r[b * R + j] = acc;
+}
+
+// d2 plane [B][H+2][W+2][16] (bf16): zero everywhere except lattice pixels, where for class k of reward j
+//   d logit_k = dr[b][j] * p_k * ((k==0) - (k==2) - (p_0 - p_2))
+__global__ void reward_head_bwd_kernel(const float* __restrict__ y2, const float* __restrict__ dr, int B, int R, int H,
+                                       int W, int h2, int w2, __nv_bfloat16* __restrict__ d2) {
+    const int Hp = H + 2, Wp = W + 2;
+    const long long rows = (long long)B * Hp * Wp;
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= rows) return;
+    const int b = int(p / (Hp * Wp));
+    const int rem = int(p - (long long)b * Hp * Wp);
+    const int hp = rem / Wp, wp = rem - hp * Wp;
+    const int h = hp - 1, w = wp - 1;
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.f;
+    const bool on = h >= 2 && w >= 2 && ((h & 1) == 0) && ((w & 1) == 0) && (h - 2) / 2 < h2 && (w - 2) / 2 < w2;
+    if (on) {
+        const size_t hw = size_t(H) * W;
+        const size_t pos = size_t(h) * W + w;
+        for (int j = 0; j < R; ++j) {
+            const float* base = y2 + (size_t(b) * 3 * R + j) * hw + pos;
+            const float l0 = __ldg(base), l1 = __ldg(base + size_t(R) * hw), l2 = __ldg(base + size_t(2 * R) * hw);
+            const float m = fmaxf(l0, fmaxf(l1, l2));
+            const float e0 = __expf(l0 - m), e1 = __expf(l1 - m), e2 = __expf(l2 - m);
+            const float inv = 1.f / (e0 + e1 + e2);
+            const float p0 = e0 * inv, p1 = e1 * inv, p2 = e2 * inv;
+            const float d = p0 - p2, g = __ldg(dr + b * R + j);
+            v[j] = g * p0 * (1.f - d);
+            v[R + j] = g * p1 * (-d);
+            v[2 * R + j] = g * p2 * (-1.f - d);
+        }
+    }
+    uint4 o0, o1;
+    __nv_bfloat162* w0 = reinterpret_cast<__nv_bfloat162*>(&o0);
+    __nv_bfloat162* w1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        w0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        w1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+    }
+    uint4* op = reinterpret_cast<uint4*>(d2 + p * 16);
+    op[0] = o0;
+    op[1] = o1;
 }
 
 }  // namespace scm

@@ -1,0 +1,73 @@
+"""Data-parallel gradient exchange for the world-model training step (new functionality; the reference is
+single-GPU).
+
+Every loss of reference main.py is a batch mean with a fixed denominator, so with equal shards the global gradient is
+the mean of the per-rank gradients: one sum-allreduce over the 1.17 M trainable floats per iteration, followed by
+the same clip+Adam on every rank (clipping acts on the averaged gradient, as on one GPU).
+
+All gradients live in two flat fp32 buckets (`.grad` tensors are views into them, so there is no packing copy):
+  bucket 0: reward predictor + decoder + transition - final as soon as BPTT reaches the first rollout step;
+  bucket 1: encoder                                  - final at the very end of backward.
+Bucket 0's allreduce is issued on a side stream from an autograd hook the moment its last gradient has been
+accumulated, so it overlaps the encoder's backward; bucket 1 follows on the same side stream, and the optimiser
+waits for both.  Works eagerly and under CUDA-graph capture (the fork/join is expressed with stream waits).
+"""
+import torch
+import torch.distributed as dist
+
+
+class BucketedGradSync:
+    def __init__(self, trainer, process_group=None):
+        self.pg = process_group
+        self.world_size = dist.get_world_size(process_group)
+        early, late = [], []
+        for (p, _), ni in zip(trainer.groups, trainer.net_of):
+            (late if trainer.NET_ORDER[ni] == "encoder" else early).append(p)
+        self.buckets = []
+        for params in (early, late):
+            n = sum(p.numel() for p in params)
+            flat = torch.zeros(n, dtype=torch.float32, device=params[0].device)
+            off = 0
+            for p in params:
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+            self.buckets.append({"flat": flat, "params": params, "pending": 0})
+        self.cuda = self.buckets[0]["flat"].is_cuda
+        self.side = torch.cuda.Stream() if self.cuda else None
+        self._bucket_of = {id(p): bi for bi, b in enumerate(self.buckets) for p in b["params"]}
+        self._armed = False
+        trainer.sync = self
+        trainer.world_size = self.world_size
+
+    def zero(self):
+        for b in self.buckets:
+            b["flat"].zero_()
+
+    def arm(self, profile):
+        """Call right before loss.backward(); profile: {param id: accumulations per iteration} (Trainer._profile)."""
+        self._armed = True
+        for b in self.buckets:
+            b["pending"] = sum(profile.get(id(p), 0) for p in b["params"])
+
+    def on_grad(self, p):
+        if not self._armed:
+            return
+        b = self.buckets[self._bucket_of[id(p)]]
+        b["pending"] -= 1
+        if b["pending"] == 0:
+            self._launch(b)
+
+    def _launch(self, b):
+        if not self.cuda:
+            dist.all_reduce(b["flat"], group=self.pg)
+            return
+        self.side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side):
+            dist.all_reduce(b["flat"], group=self.pg)
+
+    def finish(self):
+        """Join the side stream.  A bucket whose parameters received no gradient this iteration holds zeros on every
+        rank and is not exchanged."""
+        self._armed = False
+        if self.cuda:
+            torch.cuda.current_stream().wait_stream(self.side)

@@ -1,0 +1,356 @@
+"""Kernel sequencing for the three convolutional networks of the world model (host side, no arithmetic).
+
+Each function enqueues the hand-written kernels (scm_gan_b200.kernels -> C ABI) for one module forward or
+backward on torch's current stream and returns the tensors autograd has to keep.  Activations stay in bf16
+"planes" ([B, H+2, W+2, C], see include/scmgan.h) between layers; fp32 NCHW exists only at the module boundary.
+
+Reference semantics mirrored here (file:line in LilJing/scm-gan):
+  Encoder.forward      models.py:139-157     zero padding, SN convs 1-3, plain conv4, sigmoid
+  Transition.forward   models.py:59-119      legacy circular pad-1, SN convs 1-5, plain conv6, sigmoid, Bernoulli
+  Decoder.forward      models.py:270-291     two ConvTranspose2d(3x3, s1, p1), latent-group sum
+  SpectralNorm         spectral_normalization.py:23-35  (power iteration per call; backward uses the u, v held by
+                       the module at backward time, see DESIGN.md "SpectralNorm backward")
+"""
+import torch
+
+from . import kernels as K
+from .kernels import ACT_LRELU, ACT_NONE, ACT_SIGMOID
+
+HID = 128  # hidden width of Encoder / Transition (reference models.py:51-55, 129-133)
+
+
+def _r16(c):
+    return (c + 15) // 16 * 16
+
+
+def _conv2d_fwd_job(w, out, sigma=None, k_valid=None, n_pad=None, k_pad=None):
+    """nn.Conv2d weight [Co, Ci, 3, 3] -> forward GEMM operand [9][n_pad][k_pad] (n = co, k = ci)."""
+    co, ci = w.shape[0], w.shape[1]
+    return dict(w=w, out=out, sigma=sigma, n_pad=out.shape[1], k_pad=out.shape[2], n_valid=co,
+                k_valid=ci if k_valid is None else k_valid, s_n=ci * 9, s_k=9, flip=0)
+
+
+def _conv2d_dgrad_job(w, out, sigma=None, ci_begin=0, ci_count=None, co_valid=None):
+    """nn.Conv2d weight -> dgrad operand [9][n_pad][k_pad] with n = ci (window), k = co, taps flipped."""
+    co, ci = w.shape[0], w.shape[1]
+    ci_count = ci - ci_begin if ci_count is None else ci_count
+    # window over ci: shift the base pointer by ci_begin * 9 elements via a view
+    wv = w.view(co, ci * 9)[:, ci_begin * 9:]
+    return dict(w=wv, out=out, sigma=sigma, n_pad=out.shape[1], k_pad=out.shape[2], n_valid=ci_count,
+                k_valid=co if co_valid is None else co_valid, s_n=9, s_k=ci * 9, flip=1)
+
+
+def _convT_fwd_job(w, out):
+    """nn.ConvTranspose2d weight [Ci, Co, 3, 3] (stride 1, pad 1) -> equivalent correlation operand (flipped)."""
+    ci, co = w.shape[0], w.shape[1]
+    return dict(w=w, out=out, sigma=None, n_pad=out.shape[1], k_pad=out.shape[2], n_valid=co, k_valid=ci, s_n=9,
+                s_k=co * 9, flip=1)
+
+
+def _convT_dgrad_job(w, out):
+    ci, co = w.shape[0], w.shape[1]
+    return dict(w=w, out=out, sigma=None, n_pad=out.shape[1], k_pad=out.shape[2], n_valid=ci, k_valid=co,
+                s_n=co * 9, s_k=9, flip=0)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Transition
+# ------------------------------------------------------------------------------------------------------------
+def spectral_norm_update(wbar, u, v):
+    """One power iteration for every wrapped conv of a module (u, v updated in place); returns sigma [n]."""
+    sigma = torch.empty(len(wbar), dtype=torch.float32, device=wbar[0].device)
+    K.spectral_norm_fwd([(wbar[i], u[i], v[i], sigma[i:i + 1], None, None) for i in range(len(wbar))])
+    return sigma
+
+
+def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training):
+    """z [B,L,H,W] fp32, a [B,A] fp32.  wbar/bias: lists for conv1..conv5; sigma [5] from spectral_norm_update.
+    Returns (z_next, p, saved) with saved = [zin, buf6, buf5, act3, wd...] for backward."""
+    dev = z.device
+    B, L, H, W = z.shape
+    Lp = _r16(L)
+    A = a.shape[1]
+
+    # packed operands: forward [9][Cout][Cin] and dgrad [9][Cin][Cout] (1/sigma folded in)
+    wf = [K.packed_weight(HID, Lp, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
+          K.packed_weight(HID, HID, dev), K.packed_weight(HID, 2 * HID, dev), K.packed_weight(Lp, 2 * HID, dev)]
+    wd = [K.packed_weight(Lp, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
+          K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
+          K.packed_weight(HID, Lp, dev), K.packed_weight(HID, Lp, dev)]
+    jobs = [_conv2d_fwd_job(wbar[0], wf[0], sigma[0:1], k_valid=L)]
+    jobs += [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(1, 5)]
+    jobs += [_conv2d_fwd_job(w6, wf[5])]
+    jobs += [_conv2d_dgrad_job(wbar[0], wd[0], sigma[0:1], 0, L)]
+    jobs += [_conv2d_dgrad_job(wbar[i], wd[i], sigma[i:i + 1]) for i in range(1, 4)]
+    jobs += [_conv2d_dgrad_job(wbar[4], wd[4], sigma[4:5], 0, HID), _conv2d_dgrad_job(wbar[4], wd[5], sigma[4:5], HID, HID)]
+    jobs += [_conv2d_dgrad_job(w6, wd[6], None, 0, HID, co_valid=L), _conv2d_dgrad_job(w6, wd[7], None, HID, HID, co_valid=L)]
+    K.pack_weights(jobs)
+
+    sbias = torch.empty((B, HID), dtype=torch.float32, device=dev)
+    K.action_bias(wbar[0], sigma[0:1], bias[0], a, L, sbias)
+
+    zin = K.new_plane(B, H, W, Lp, dev)
+    K.pack_nchw(z, zin, wrap=True)
+    buf6 = K.new_plane(B, H, W, 2 * HID, dev)  # [act5 | act1]  = input of conv6 (models.py:101)
+    buf5 = K.new_plane(B, H, W, 2 * HID, dev)  # [act4 | act2]  = input of conv5 (models.py:95)
+    act3 = K.new_plane(B, H, W, HID, dev)
+    cv = dict(act=ACT_LRELU, wrap=True)
+    K.conv3x3(zin, wf[0], B, H, W, cin=Lp, sample_bias=sbias, out=buf6, out_c_off=HID, **cv)        # conv1 -> skip1
+    K.conv3x3(buf6, wf[1], B, H, W, cin=HID, x_c_off=HID, bias=bias[1], out=buf5, out_c_off=HID, **cv)  # conv2 -> skip2
+    K.conv3x3(buf5, wf[2], B, H, W, cin=HID, x_c_off=HID, bias=bias[2], out=act3, **cv)             # conv3
+    K.conv3x3(act3, wf[3], B, H, W, cin=HID, bias=bias[3], out=buf5, out_c_off=0, **cv)             # conv4
+    K.conv3x3(buf5, wf[4], B, H, W, cin=2 * HID, bias=bias[4], out=buf6, out_c_off=0, **cv)         # conv5
+    p = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    zn = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    b6p = b6 if Lp == L else torch.nn.functional.pad(b6, (0, Lp - L))
+    K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6p, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
+              uniforms=uniforms if training else None)                                              # conv6 + head
+    return zn, p, [zin, buf6, buf5, act3] + wd
+
+
+def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6):
+    """Backward of transition_forward.  dz_next: gradient w.r.t. the sampled state (straight-through => w.r.t. p,
+    reference models.py:38-40).  Returns (dz, [dWbar1..5], [db1..5], dW6, db6)."""
+    zin, buf6, buf5, act3 = saved[:4]
+    wd = saved[4:]
+    dev = dz_next.device
+    B, L, H, W = dz_next.shape
+    Lp = zin.shape[3]
+    A = a.shape[1]
+    # gradients w.r.t. the *normalised* weights / biases, one flat zeroed buffer (wgrad accumulates atomically)
+    shapes = [tuple(w.shape) for w in wbar] + [tuple(w6.shape)]
+    sizes = [w.numel() for w in wbar] + [w6.numel()]
+    nb = 5 * HID + Lp
+    flat = torch.zeros(sum(sizes) + nb + B * HID + 8, dtype=torch.float32, device=dev)
+    G, off = [], 0
+    for s, n in zip(shapes, sizes):
+        G.append(flat[off:off + n].view(s))
+        off += n
+    db = [flat[off + i * HID: off + (i + 1) * HID] for i in range(5)]
+    db6 = flat[off + 5 * HID: off + 5 * HID + Lp]
+    off += nb
+    S1 = flat[off: off + B * HID].view(B, HID)
+    off += B * HID
+    dots = flat[off: off + 8]
+
+    # d pre-activation of conv6: dz * p * (1 - p)
+    d6 = K.new_plane(B, H, W, Lp, dev)
+    K.pack_nchw(dz_next, d6, wrap=True, sig=p)
+    cin6 = 2 * HID
+    K.wgrad(d6, buf6, G[5], B, H, W, cout=Lp, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L)
+    K.plane_colsum(d6, 0, Lp, B, H, W, db=db6)
+    dg = dict(wrap=True, dgrad=True)
+    d5 = K.new_plane(B, H, W, HID, dev)
+    d1part = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d6, wd[6], B, H, W, cin=Lp, out=d5, gate=buf6, gate_c_off=0, **dg)        # d act5 -> d pre5
+    K.conv3x3(d6, wd[7], B, H, W, cin=Lp, out=d1part, **dg)                             # d skip1 (partial)
+    K.wgrad(d5, buf5, G[4], B, H, W, cout=HID, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9)
+    K.plane_colsum(d5, 0, HID, B, H, W, db=db[4])
+    d4 = K.new_plane(B, H, W, HID, dev)
+    d2part = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d5, wd[4], B, H, W, cin=HID, out=d4, gate=buf5, gate_c_off=0, **dg)       # d act4 -> d pre4
+    K.conv3x3(d5, wd[5], B, H, W, cin=HID, out=d2part, **dg)                            # d skip2 (partial)
+    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
+    K.plane_colsum(d4, 0, HID, B, H, W, db=db[3])
+    d3 = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=d3, gate=act3, **dg)
+    K.wgrad(d3, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9)
+    K.plane_colsum(d3, 0, HID, B, H, W, db=db[2])
+    d2 = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d3, wd[2], B, H, W, cin=HID, out=d2, add=d2part, gate=buf5, gate_c_off=HID, **dg)
+    K.wgrad(d2, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9)
+    K.plane_colsum(d2, 0, HID, B, H, W, db=db[1])
+    d1 = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d2, wd[1], B, H, W, cin=HID, out=d1, add=d1part, gate=buf6, gate_c_off=HID, **dg)
+    c1 = L + A
+    K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L)
+    K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])
+    K.action_wgrad(S1, a, L, G[0])
+    dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
+    # spectral norm backward with the u, v currently held by the module (= last forward call)
+    dwbar = [torch.empty_like(w) for w in wbar]
+    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1], dwbar[i]) for i in range(5)])
+    return dz, dwbar, [d.clone() for d in db], G[5].clone(), db6[:L].clone()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Encoder
+# ------------------------------------------------------------------------------------------------------------
+def encoder_forward(x, wbar, bias, sigma, w4, b4):
+    """x: [B, 3C, H, W] fp32 view (dense CHW); sigma [3] from spectral_norm_update.  Returns (z, saved)."""
+    dev = x.device
+    B, Cin, H, W = x.shape
+    Cp = _r16(Cin)
+    L = w4.shape[0]
+    Lp = _r16(L)
+    wf = [K.packed_weight(HID, Cp, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
+          K.packed_weight(Lp, HID, dev)]
+    wd = [K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, Lp, dev)]
+    jobs = [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(3)] + [_conv2d_fwd_job(w4, wf[3])]
+    jobs += [_conv2d_dgrad_job(wbar[1], wd[0], sigma[1:2]), _conv2d_dgrad_job(wbar[2], wd[1], sigma[2:3]),
+             _conv2d_dgrad_job(w4, wd[2], None, co_valid=L)]
+    K.pack_weights(jobs)
+    xin = K.new_plane(B, H, W, Cp, dev)
+    K.pack_nchw(x, xin, wrap=False)
+    a1, a2, a3 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
+    K.conv3x3(xin, wf[0], B, H, W, cin=Cp, bias=bias[0], act=ACT_LRELU, out=a1)
+    K.conv3x3(a1, wf[1], B, H, W, cin=HID, bias=bias[1], act=ACT_LRELU, out=a2)
+    K.conv3x3(a2, wf[2], B, H, W, cin=HID, bias=bias[2], act=ACT_LRELU, out=a3)
+    z = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    b4p = b4 if Lp == L else torch.nn.functional.pad(b4, (0, Lp - L))
+    K.conv3x3(a3, wf[3], B, H, W, cin=HID, bias=b4p, act=ACT_SIGMOID, out_f32=z, n_valid=L)
+    return z, [xin, a1, a2, a3] + wd
+
+
+def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4):
+    xin, a1, a2, a3 = saved[:4]
+    wd = saved[4:]
+    dev = dz.device
+    B, L, H, W = dz.shape
+    Lp = _r16(L)
+    Cp = xin.shape[3]
+    cin = wbar[0].shape[1]
+    sizes = [w.numel() for w in wbar] + [w4.numel()]
+    flat = torch.zeros(sum(sizes) + 3 * HID + Lp + 8, dtype=torch.float32, device=dev)
+    G, off = [], 0
+    for w, n in zip(list(wbar) + [w4], sizes):
+        G.append(flat[off:off + n].view(w.shape))
+        off += n
+    db = [flat[off + i * HID: off + (i + 1) * HID] for i in range(3)]
+    db4 = flat[off + 3 * HID: off + 3 * HID + Lp]
+    dots = flat[off + 3 * HID + Lp:]
+    d4 = K.new_plane(B, H, W, Lp, dev)
+    K.pack_nchw(dz, d4, wrap=False, sig=z)
+    K.wgrad(d4, a3, G[3], B, H, W, cout=Lp, cin=HID, g_s_co=HID * 9, g_s_ci=9, co_valid=L)
+    K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
+    d3, d2, d1 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
+    K.conv3x3(d4, wd[2], B, H, W, cin=Lp, out=d3, gate=a3, dgrad=True)
+    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
+    K.plane_colsum(d3, 0, HID, B, H, W, db=db[2])
+    K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
+    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
+    K.plane_colsum(d2, 0, HID, B, H, W, db=db[1])
+    K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
+    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin)
+    K.plane_colsum(d1, 0, HID, B, H, W, db=db[0])
+    dwbar = [torch.empty_like(w) for w in wbar]
+    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1], dwbar[i]) for i in range(3)])
+    return dwbar, [d.clone() for d in db], G[3].clone(), db4[:L].clone()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Decoder
+# ------------------------------------------------------------------------------------------------------------
+def decoder_forward(z, w1, b1, w2, b2):
+    """z [B,L,H,W]; w1 ConvTranspose weight [L, 4L, 3, 3]; w2 [4L, Co, 3, 3] where Co is either the folded
+    colour-channel count (latent groups pre-summed by the caller) or L*C for the visualisation path.
+    Returns (logits [B,Co,H,W], saved)."""
+    dev = z.device
+    B, L, H, W = z.shape
+    Lp = _r16(L)
+    hid = w1.shape[1]
+    co = w2.shape[1]
+    cop = _r16(co)
+    assert hid % 64 == 0 and hid <= HID
+    wf1 = K.packed_weight(HID, Lp, dev)      # hidden padded to 128 channels (upper ones are exactly zero)
+    wf2 = K.packed_weight(cop, hid, dev)
+    wd1 = K.packed_weight(Lp, hid, dev)
+    wd2 = K.packed_weight(HID, cop, dev)
+    K.pack_weights([_convT_fwd_job(w1, wf1), _convT_fwd_job(w2, wf2), _convT_dgrad_job(w1, wd1),
+                    _convT_dgrad_job(w2, wd2)])
+    zin = K.new_plane(B, H, W, Lp, dev)
+    K.pack_nchw(z, zin, wrap=False)
+    hidp = K.new_plane(B, H, W, HID, dev)
+    b1p = b1 if hid == HID else torch.nn.functional.pad(b1, (0, HID - hid))
+    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1p, act=ACT_LRELU, out=hidp)
+    logits = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+    b2p = b2 if cop == co else torch.nn.functional.pad(b2, (0, cop - co))
+    K.conv3x3(hidp, wf2, B, H, W, cin=hid, bias=b2p, act=ACT_NONE, out_f32=logits, n_valid=co)
+    return logits, [zin, hidp, wd1, wd2]
+
+
+def decoder_backward(dlogits, saved, w1, w2):
+    zin, hidp, wd1, wd2 = saved
+    dev = dlogits.device
+    B, co, H, W = dlogits.shape
+    cop = _r16(co)
+    L, hid = w1.shape[0], w1.shape[1]
+    Lp = zin.shape[3]
+    flat = torch.zeros(w1.numel() + w2.numel() + HID + cop, dtype=torch.float32, device=dev)
+    g1 = flat[:w1.numel()].view(w1.shape)
+    g2 = flat[w1.numel(): w1.numel() + w2.numel()].view(w2.shape)
+    db1 = flat[w1.numel() + w2.numel(): w1.numel() + w2.numel() + HID]
+    db2 = flat[w1.numel() + w2.numel() + HID:]
+    d2 = K.new_plane(B, H, W, cop, dev)
+    K.pack_nchw(dlogits, d2, wrap=False)
+    # ConvTranspose weight layout [Cin][Cout][3][3], taps flipped relative to the equivalent correlation
+    K.wgrad(d2, hidp, g2, B, H, W, cout=cop, cin=HID, g_s_co=9, g_s_ci=co * 9, flip=True, co_valid=co, ci_valid=hid)
+    K.plane_colsum(d2, 0, cop, B, H, W, db=db2)
+    d1 = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d2, wd2, B, H, W, cin=cop, out=d1, gate=hidp, dgrad=True)
+    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L)
+    K.plane_colsum(d1, 0, HID, B, H, W, db=db1)
+    dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True)
+    return dz, g1.clone(), db1[:hid].clone(), g2.clone(), db2[:co].clone()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RewardPredictor (reference models.py:235-250)
+# ------------------------------------------------------------------------------------------------------------
+RHID = 32  # hidden width of the reward head (models.py:230)
+
+
+def reward_forward(z, w1, b1, w2, b2, want_map):
+    """conv(L->32, valid) -> LeakyReLU -> conv(32->3R, stride 2, valid) -> softmax(3) -> p+ - p- -> spatial sum.
+    Both convs run as same-size stride-1 tcgen05 convs; valid/stride-2 positions are selected by the head kernel
+    (the footprint of every consumed output lies inside the valid region, so the results are identical)."""
+    dev = z.device
+    B, L, H, W = z.shape
+    Lp = _r16(L)
+    co = w2.shape[0]
+    R = co // 3
+    assert w1.shape[0] == RHID and co <= 16
+    wf1 = K.packed_weight(HID, Lp, dev)   # hidden padded to 128 channels (zero rows beyond 32)
+    wf2 = K.packed_weight(16, RHID, dev)
+    wd1 = K.packed_weight(Lp, RHID, dev)
+    wd2 = K.packed_weight(HID, 16, dev)
+    K.pack_weights([_conv2d_fwd_job(w1, wf1), _conv2d_fwd_job(w2, wf2),
+                    _conv2d_dgrad_job(w1, wd1), _conv2d_dgrad_job(w2, wd2)])
+    zin = K.new_plane(B, H, W, Lp, dev)
+    K.pack_nchw(z, zin, wrap=False)
+    hidp = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=torch.nn.functional.pad(b1, (0, HID - RHID)), act=ACT_LRELU, out=hidp)
+    y2 = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+    K.conv3x3(hidp, wf2, B, H, W, cin=RHID, bias=torch.nn.functional.pad(b2, (0, 16 - co)), act=ACT_NONE,
+              out_f32=y2, n_valid=co)
+    r = torch.empty((B, R), dtype=torch.float32, device=dev)
+    h2, w2s = (H - 5) // 2 + 1, (W - 5) // 2 + 1
+    rmap = torch.empty((B, R, h2, w2s), dtype=torch.float32, device=dev) if want_map else None
+    K.reward_head_fwd(y2, R, r, rmap)
+    return r, rmap, [zin, hidp, y2, wd1, wd2]
+
+
+def reward_backward(dr, saved, w1, w2):
+    zin, hidp, y2, wd1, wd2 = saved
+    dev = dr.device
+    B, co, H, W = y2.shape
+    R = co // 3
+    L = w1.shape[1]
+    Lp = zin.shape[3]
+    n1, n2 = w1.numel(), w2.numel()
+    flat = torch.zeros(n1 + n2 + HID + 16, dtype=torch.float32, device=dev)
+    g1, g2 = flat[:n1].view(w1.shape), flat[n1:n1 + n2].view(w2.shape)
+    db1, db2 = flat[n1 + n2:n1 + n2 + HID], flat[n1 + n2 + HID:]
+    d2 = K.new_plane(B, H, W, 16, dev)
+    K.reward_head_bwd(y2, dr, R, d2)
+    K.wgrad(d2, hidp, g2, B, H, W, cout=16, cin=HID, g_s_co=RHID * 9, g_s_ci=9, co_valid=co, ci_valid=RHID)
+    K.plane_colsum(d2, 0, 16, B, H, W, db=db2)
+    d1 = K.new_plane(B, H, W, HID, dev)
+    K.conv3x3(d2, wd2, B, H, W, cin=16, out=d1, gate=hidp, dgrad=True)
+    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L)
+    K.plane_colsum(d1, 0, HID, B, H, W, db=db1)
+    dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+    K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True)
+    return dz, g1.clone(), db1[:RHID].clone(), g2.clone(), db2[:co].clone()

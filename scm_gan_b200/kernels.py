@@ -13,6 +13,11 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_SIGMOID  # noqa: F401
 LRELU_SLOPE = 0.01  # F.leaky_relu default used by reference models.py:77-99
 
 
+def launch_count():
+    """Kernels launched through the C ABI so far (bench.py reports the per-step delta as gpu_launches)."""
+    return L.lib().scmgan_launch_count()
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -22,16 +27,18 @@ def new_plane(B, H, W, Cs, device):
     return torch.empty((B, H + 2, W + 2, Cs), dtype=torch.bfloat16, device=device)
 
 
-def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False):
-    """fp32 [B,C,H,W] (arbitrary batch stride, dense CHW) -> plane channels [c_off, c_off+c_pad)."""
+def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False, sig=None):
+    """fp32 [B,C,H,W] (arbitrary batch stride, dense CHW) -> plane channels [c_off, c_off+c_pad).
+    sig: optional contiguous fp32 [B,C,H,W]; the packed value is src * sig * (1 - sig)."""
     B, Cc, H, W = src.shape
     assert src.dtype == torch.float32 and src.is_cuda
     assert src.stride(3) == 1 and src.stride(2) == W and src.stride(1) == H * W, "dense CHW required"
     Cs = dst_plane.shape[3]
     if c_pad is None:
         c_pad = (Cc + 15) // 16 * 16
+    assert sig is None or (sig.is_contiguous() and sig.shape == src.shape)
     L.check(L.lib().scmgan_pack_nchw(src.data_ptr(), src.stride(0), Cc, B, H, W, dst_plane.data_ptr(), Cs, c_off,
-                                     c_pad, int(wrap), _stream()), "scmgan_pack_nchw")
+                                     c_pad, int(wrap), L.ptr(sig), _stream()), "scmgan_pack_nchw")
 
 
 def pack_weights(jobs):
@@ -135,10 +142,25 @@ def bce_logits(x, y, mask, loss, dx=None):
                                       L.ptr(dx), _stream()), "scmgan_bce_logits")
 
 
+def reward_head_fwd(y2, R, r, rmap=None):
+    B, _, H, W = y2.shape
+    L.check(L.lib().scmgan_reward_head_fwd(y2.data_ptr(), B, R, H, W, r.data_ptr(), L.ptr(rmap), _stream()),
+            "scmgan_reward_head_fwd")
+
+
+def reward_head_bwd(y2, dr, R, d2_plane):
+    B, _, H, W = y2.shape
+    assert d2_plane.shape[3] == 16
+    L.check(L.lib().scmgan_reward_head_bwd(y2.data_ptr(), dr.data_ptr(), B, R, H, W, d2_plane.data_ptr(), _stream()),
+            "scmgan_reward_head_bwd")
+
+
 def clip_adam(chunks, lr, beta1, beta2, eps, step, step_dev=None, gscale=1.0):
-    """chunks: list of (p, g, m, v, clip)."""
+    """chunks: list of (p, g, m, v, clip[, step_tensor])."""
     arr = (L.AdamChunk * len(chunks))()
-    for i, (p, g, m, v, clip) in enumerate(chunks):
-        arr[i] = L.AdamChunk(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), clip)
+    for i, c in enumerate(chunks):
+        p, g, m, v, clip = c[:5]
+        st = c[5] if len(c) > 5 else None
+        arr[i] = L.AdamChunk(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(), clip, L.ptr(st))
     L.check(L.lib().scmgan_clip_adam(len(chunks), arr, lr, beta1, beta2, eps, step, L.ptr(step_dev), gscale,
                                      _stream()), "scmgan_clip_adam")

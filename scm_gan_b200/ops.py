@@ -1,0 +1,223 @@
+"""torch.library custom ops (`scmgan::*`) with registered autograd.
+
+One forward op and one backward op per network; the bodies only sequence hand-written kernels
+(scm_gan_b200.engine).  There is no eager/CPU fallback: calling any op with non-CUDA tensors raises.
+"""
+from typing import List, Optional, Sequence
+
+import torch
+from torch import Tensor
+
+from . import engine as E
+from . import kernels as K
+
+
+# (u list, v list) of the module issuing the next differentiable forward op; consumed by setup_context.
+# The power-iteration vectors are module state read at *backward* time (reference semantics), so they travel
+# beside the op instead of through its functional signature.
+_UV_SOURCE = []
+
+
+def _require_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("scmgan ops run only on CUDA tensors (sm_100a); there is no CPU fallback")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Transition
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::spectral_norm_update", mutates_args=("u", "v"))
+def spectral_norm_update(wbar: Sequence[Tensor], u: Sequence[Tensor], v: Sequence[Tensor]) -> Tensor:
+    """Power iteration of every SpectralNorm-wrapped conv of one module (reference spectral_normalization.py:28-31);
+    u, v advance in place exactly like the reference's `.data` assignments.  Returns sigma per layer."""
+    _require_cuda(*wbar)
+    return E.spectral_norm_update(list(wbar), list(u), list(v))
+
+
+@torch.library.custom_op("scmgan::transition_fwd", mutates_args=())
+def transition_fwd(z: Tensor, a: Tensor, wbar: Sequence[Tensor], bias: Sequence[Tensor], sigma: Tensor,
+                   w6: Tensor, b6: Tensor, uniforms: Optional[Tensor], training: bool) -> List[Tensor]:
+    _require_cuda(z, a, w6)
+    zn, p, saved = E.transition_forward(z.contiguous().float(), a.contiguous().float(), list(wbar), list(bias),
+                                        sigma, w6, b6,
+                                        None if uniforms is None else uniforms.contiguous().float(), training)
+    return [zn, p] + saved
+
+
+@torch.library.custom_op("scmgan::transition_bwd", mutates_args=())
+def transition_bwd(dz_next: Tensor, p: Tensor, a: Tensor, saved: Sequence[Tensor], wbar: Sequence[Tensor],
+                   sigma: Tensor, u: Sequence[Tensor], v: Sequence[Tensor], w6: Tensor) -> List[Tensor]:
+    _require_cuda(dz_next)
+    dz, dwbar, db, dw6, db6 = E.transition_backward(dz_next.contiguous().float(), p, a.contiguous().float(),
+                                                    list(saved), list(wbar), sigma, list(u), list(v), w6)
+    return [dz] + dwbar + db + [dw6, db6]
+
+
+def _transition_setup(ctx, inputs, output):
+    z, a, wbar, bias, sigma, w6, b6, uniforms, training = inputs
+    ctx.training = training
+    ctx.a, ctx.sigma = a, sigma
+    ctx.wbar, ctx.w6 = list(wbar), w6
+    ctx.nw = len(wbar)
+    # u, v are attached by the calling module (ctx.uv_source) and deliberately NOT saved with version tracking:
+    # the reference's backward reads whatever u, v the module holds at backward time.
+    ctx.uv = _UV_SOURCE.pop()
+    ctx.save_for_backward(*output[1:])
+
+
+def _transition_backward(ctx, grads):
+    saved = list(ctx.saved_tensors)
+    p, rest = saved[0], saved[1:]
+    dz_next = grads[0]
+    n = ctx.nw
+    if dz_next is None or not ctx.training:
+        return (None,) * 9
+    u, v = ctx.uv
+    out = torch.ops.scmgan.transition_bwd(dz_next, p, ctx.a, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w6)
+    dz = out[0]
+    dwbar = list(out[1:1 + n])
+    db = list(out[1 + n:1 + 2 * n])
+    dw6, db6 = out[1 + 2 * n], out[2 + 2 * n]
+    return dz, None, dwbar, db, None, dw6, db6, None, None
+
+
+transition_fwd.register_autograd(_transition_backward, setup_context=_transition_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Encoder
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::encoder_fwd", mutates_args=())
+def encoder_fwd(x: Tensor, wbar: Sequence[Tensor], bias: Sequence[Tensor], sigma: Tensor, w4: Tensor,
+                b4: Tensor) -> List[Tensor]:
+    _require_cuda(x, w4)
+    B, Cc, H, W = x.shape
+    if not (x.dtype == torch.float32 and x.stride(3) == 1 and x.stride(2) == W and x.stride(1) == H * W):
+        x = x.contiguous().float()
+    z, saved = E.encoder_forward(x, list(wbar), list(bias), sigma, w4, b4)
+    return [z] + saved
+
+
+@torch.library.custom_op("scmgan::encoder_bwd", mutates_args=())
+def encoder_bwd(dz: Tensor, z: Tensor, saved: Sequence[Tensor], wbar: Sequence[Tensor], sigma: Tensor,
+                u: Sequence[Tensor], v: Sequence[Tensor], w4: Tensor) -> List[Tensor]:
+    _require_cuda(dz)
+    dwbar, db, dw4, db4 = E.encoder_backward(dz.contiguous().float(), z, list(saved), list(wbar), sigma, list(u),
+                                             list(v), w4)
+    return dwbar + db + [dw4, db4]
+
+
+def _encoder_setup(ctx, inputs, output):
+    x, wbar, bias, sigma, w4, b4 = inputs
+    ctx.wbar, ctx.sigma, ctx.w4 = list(wbar), sigma, w4
+    ctx.nw = len(wbar)
+    ctx.uv = _UV_SOURCE.pop()
+    ctx.save_for_backward(*output)
+
+
+def _encoder_backward(ctx, grads):
+    saved = list(ctx.saved_tensors)
+    z, rest = saved[0], saved[1:]
+    if grads[0] is None:
+        return (None,) * 6
+    n = ctx.nw
+    u, v = ctx.uv
+    out = torch.ops.scmgan.encoder_bwd(grads[0], z, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w4)
+    return None, list(out[:n]), list(out[n:2 * n]), None, out[2 * n], out[2 * n + 1]
+
+
+encoder_fwd.register_autograd(_encoder_backward, setup_context=_encoder_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Decoder
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::decoder_fwd", mutates_args=())
+def decoder_fwd(z: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> List[Tensor]:
+    _require_cuda(z, w1)
+    logits, saved = E.decoder_forward(z.contiguous().float(), w1, b1, w2.contiguous(), b2.contiguous())
+    return [logits] + saved
+
+
+@torch.library.custom_op("scmgan::decoder_bwd", mutates_args=())
+def decoder_bwd(dlogits: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor) -> List[Tensor]:
+    _require_cuda(dlogits)
+    return list(E.decoder_backward(dlogits.contiguous().float(), list(saved), w1, w2.contiguous()))
+
+
+def _decoder_setup(ctx, inputs, output):
+    z, w1, b1, w2, b2 = inputs
+    ctx.w1, ctx.w2 = w1, w2
+    ctx.save_for_backward(*output[1:])
+
+
+def _decoder_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 5
+    dz, g1, db1, g2, db2 = torch.ops.scmgan.decoder_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2)
+    return dz, g1, db1, g2, db2
+
+
+decoder_fwd.register_autograd(_decoder_backward, setup_context=_decoder_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Fused sigmoid + BCE + masked mean (used by scm_gan_b200.train_step; main.py keeps its own torch ops)
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::bce_logits", mutates_args=())
+def bce_logits(logits: Tensor, target: Tensor, mask: Tensor) -> List[Tensor]:
+    _require_cuda(logits, target, mask)
+    logits = logits.contiguous().float()
+    B = logits.shape[0]
+    if not (target.dtype == torch.float32 and target[0].is_contiguous()):
+        target = target.contiguous().float()
+    loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+    dx = torch.empty_like(logits)
+    K.bce_logits(logits, target, mask.contiguous().float(), loss, dx)
+    return [loss.view(()), dx]
+
+
+def _bce_setup(ctx, inputs, output):
+    ctx.save_for_backward(output[1])
+
+
+def _bce_backward(ctx, grads):
+    (dx,) = ctx.saved_tensors
+    g = grads[0]
+    return (None if g is None else dx * g), None, None
+
+
+bce_logits.register_autograd(_bce_backward, setup_context=_bce_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RewardPredictor
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::reward_fwd", mutates_args=())
+def reward_fwd(z: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> List[Tensor]:
+    _require_cuda(z, w1)
+    r, rmap, saved = E.reward_forward(z.contiguous().float(), w1, b1, w2, b2, True)
+    return [r, rmap] + saved
+
+
+@torch.library.custom_op("scmgan::reward_bwd", mutates_args=())
+def reward_bwd(dr: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor) -> List[Tensor]:
+    _require_cuda(dr)
+    return list(E.reward_backward(dr.contiguous().float(), list(saved), w1, w2))
+
+
+def _reward_setup(ctx, inputs, output):
+    z, w1, b1, w2, b2 = inputs
+    ctx.w1, ctx.w2 = w1, w2
+    ctx.save_for_backward(*output[2:])
+
+
+def _reward_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 5
+    dz, g1, db1, g2, db2 = torch.ops.scmgan.reward_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2)
+    return dz, g1, db1, g2, db2
+
+
+reward_fwd.register_autograd(_reward_backward, setup_context=_reward_setup)

@@ -1,0 +1,284 @@
+"""Host-side mirror of one training iteration of the reference (main.py:143-296), built to be CUDA-graph
+capturable: no host<->device synchronisation, no per-step host uploads, no Python-side randomness inside.
+
+  loss = sum_t [ theta*reward_coef*rewardMSE_t + BCE_t ]  (+ CF disentanglement) (+ CF action control)
+  loss.backward(); clip_grad_value_(enc/trans/dec, 0.1); Adam on reward/enc/dec/trans
+
+Differences from running main.py itself (all outside the arithmetic):
+  * actions arrive once as an int64 device tensor [B, Hn] (reference: CPU one-hot + H2D every step, main.py:206);
+  * counterfactual indices / the action shuffle are passed in as tensors (reference: np.random, main.py:249-250,275);
+  * sigmoid + BCE + means are one fused kernel (scmgan::bce_logits) and clip + Adam is one multi-tensor kernel;
+  * loss terms stay on the device (reference: ts.collect() syncs per term).
+"""
+import os
+import sys
+
+import torch
+
+_DROPIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
+
+CF_REGULARIZATION_LAMBDA = 0.01  # reference main.py:55
+CLIP_VALUE = 0.1                 # reference main.py:288-290
+
+
+def import_dropin_models():
+    """Import the drop-in `models` module (and its siblings) the way main.py would: by bare name."""
+    if _DROPIN not in sys.path:
+        sys.path.insert(0, _DROPIN)
+    import models  # noqa: E402
+    if not os.path.abspath(models.__file__).startswith(_DROPIN):
+        raise RuntimeError(f"`models` resolved to {models.__file__}, not the scm_gan_b200 drop-in")
+    return models
+
+
+def build_nets(color_channels, num_actions, num_rewards, latent_dim=16, seed=None):
+    """Construct the four trained networks in the order of reference main.py:73-77 (same RNG consumption)."""
+    m = import_dropin_models()
+    if seed is not None:
+        torch.manual_seed(seed)
+    # construct on the CPU generator (bit-identical to the reference's seeded init), then move
+    enc = m.Encoder(latent_dim, color_channels)
+    dec = m.Decoder(latent_dim, color_channels)
+    rew = m.RewardPredictor(latent_dim, num_rewards)
+    tr = m.Transition(latent_dim, num_actions)
+    return {"encoder": enc, "decoder": dec, "reward_predictor": rew, "transition": tr}
+
+
+def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e-3, truncate_bptt=False,
+                 enable_disentanglement=False, enable_action_control=False, cf_now=False, counterfactual_horizon=1,
+                 cf_indices=None, cf_perm=None, uniforms=None, collect=None):
+    """Loss of one iteration (reference main.py:155-283).  All arguments are device tensors.
+
+    states [B,Hn,C,H,W] f32, rewards [B,Hn,R] f32, dones [B,Hn] f32, actions [B,Hn] int64.
+    cf_indices [B,2] int64, cf_perm [B] int64 (when the CF losses fire); uniforms: optional list of [B,L,H,W]
+    tensors consumed by successive Transition calls (parity tests), else torch's CUDA generator is used.
+    """
+    enc, dec, rew, tr = nets["encoder"], nets["decoder"], nets["reward_predictor"], nets["transition"]
+    B, Hn = states.shape[0], states.shape[1]
+    A = tr.conv1.module.weight_bar.shape[1] - tr.latent_size
+    eye = torch.eye(A, dtype=torch.float32, device=states.device)
+    it = iter(uniforms) if uniforms is not None else None
+
+    def step(z, a_idx):
+        if it is not None:
+            tr._uniforms = next(it)
+        return tr(z, eye[a_idx])
+
+    z = enc(states[:, 0:3])
+    z_orig = z.clone()
+    # active_mask_t = prod_{s<=t} (1 - done_s)   (main.py:178)
+    masks = torch.cumprod(1.0 - dones[:, 1:], dim=1)
+    loss = torch.zeros((), dtype=torch.float32, device=states.device)
+    for t in range(1, Hn - 1):
+        mask = masks[:, t - 1]
+        expected = rew(z)
+        rd = torch.mean(torch.mean((expected - rewards[:, t]) ** 2, dim=1) * mask)
+        loss = loss + (theta * reward_coef) * rd
+        rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
+        if truncate_bptt and t > 1:
+            z = z.detach()
+        loss = loss + rec
+        if collect is not None:
+            collect[f"Rd Loss t={t}"] = rd
+            collect[f"Reconstruction t={t}"] = rec
+        z = step(z, actions[:, t])
+    mask = masks[:, Hn - 3] if Hn > 2 else torch.ones(B, device=states.device)
+
+    if enable_disentanglement and cf_now:  # main.py:242-262
+        z_cf_a = z.clone()
+        z_cf_b = z_orig
+        L = z.shape[1]
+        ar = torch.arange(B, device=z.device)
+        unswapped = torch.ones((B, L), dtype=torch.float32, device=z.device)
+        unswapped[ar, cf_indices[:, 0]] = 0
+        unswapped[ar, cf_indices[:, 1]] = 0
+        # main.py:253 assigns through views: net effect z[i, idx_a] <- z[i, idx_b], in place on z_orig
+        z_cf_b[ar, cf_indices[:, 0]] = z_cf_b[ar, cf_indices[:, 1]]
+        for t in range(1, counterfactual_horizon):
+            z_cf_b = step(z_cf_b, actions[:, t])
+        cf = torch.abs(z_cf_a - z_cf_b).mean(-1).mean(-1) * unswapped
+        cf = CF_REGULARIZATION_LAMBDA * torch.mean(cf.mean(-1) * mask)
+        loss = loss + cf
+        if collect is not None:
+            collect["CF Disentanglement Loss"] = cf
+
+    if enable_action_control and cf_now:  # main.py:268-283
+        z_cf_a = z.clone()
+        z_cf_b = z_orig
+        cf_actions = actions[cf_perm]
+        for t in range(1, counterfactual_horizon):
+            z_cf_b = step(z_cf_b, cf_actions[:, t])
+        cf = -torch.log(torch.abs(z_cf_a - z_cf_b).mean(-1).mean(-1).mean(-1) + 0.001)
+        cf = CF_REGULARIZATION_LAMBDA * torch.mean(cf * mask)
+        loss = loss + cf
+        if collect is not None:
+            collect["CF Control Bias Loss"] = cf
+    return loss, z
+
+
+class Trainer:
+    """zero_grad -> rollout_loss -> backward -> (gradient exchange) -> fused clip+Adam, optionally replayed as one
+    CUDA graph per (horizon, cf) configuration.  Mirrors reference main.py:125-129, 150-153, 285-296."""
+
+    NET_ORDER = ("reward_predictor", "encoder", "decoder", "transition")  # opt_pred first (main.py:292-296)
+
+    def __init__(self, nets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, reward_coef=1e-3, loss_kwargs=None):
+        from . import kernels as K
+        self.K = K
+        self.nets = nets
+        self.lr, self.betas, self.eps = lr, betas, eps
+        self.reward_coef = reward_coef
+        self.loss_kwargs = dict(loss_kwargs or {})
+        self.groups = []  # (param, clip)
+        self.net_of = []  # index of the owning network (= of the reference's per-network Adam instance)
+        for ni, name in enumerate(self.NET_ORDER):
+            clip = 0.0 if name == "reward_predictor" else CLIP_VALUE
+            for p in nets[name].parameters():
+                if p.requires_grad:
+                    self.groups.append((p, clip))
+                    self.net_of.append(ni)
+        dev = self.groups[0][0].device
+        self.m = [torch.zeros_like(p) for p, _ in self.groups]
+        self.v = [torch.zeros_like(p) for p, _ in self.groups]
+        # torch.optim.Adam counts steps per parameter and skips parameters without a gradient; gradients appear
+        # per network (e.g. Transition gets none at horizon 3), so one counter per network reproduces it.
+        self.step_dev = torch.zeros(len(self.NET_ORDER), dtype=torch.float32, device=dev)
+        for p, _ in self.groups:
+            p.grad = torch.zeros_like(p)
+            p.register_post_accumulate_grad_hook(self._on_grad)
+        self._counting = False
+        self._counts = {}
+        self._profiles = {}   # (Hn, cf_now) -> {param id: number of gradient accumulations per iteration}
+        self._graphs = {}
+        self.sync = None      # dp.BucketedGradSync, attached by the data-parallel launcher
+        self.world_size = 1
+        self.launches_per_step = {}
+
+    def params(self):
+        return [p for p, _ in self.groups]
+
+    def _on_grad(self, p):
+        if self._counting:
+            self._counts[id(p)] = self._counts.get(id(p), 0) + 1
+        elif self.sync is not None:
+            self.sync.on_grad(p)
+
+    def _zero_grads(self):
+        if self.sync is not None:
+            self.sync.zero()
+            return
+        for p, _ in self.groups:
+            p.grad.zero_()
+
+    def _loss(self, batch, theta, cf_now):
+        loss, _ = rollout_loss(self.nets, batch["states"], batch["rewards"], batch["dones"], batch["actions"],
+                               theta=theta, reward_coef=self.reward_coef, cf_now=cf_now,
+                               cf_indices=batch.get("cf_indices"), cf_perm=batch.get("cf_perm"), **self.loss_kwargs)
+        return loss
+
+    def _profile(self, batch, theta, cf_now):
+        """One dry run of forward+backward (state restored afterwards) to learn which parameters receive gradients
+        in this configuration and how many times autograd accumulates into each."""
+        key = (batch["states"].shape[1], bool(cf_now))
+        if key in self._profiles:
+            return self._profiles[key]
+        snap = self._snapshot_sn()
+        rng = torch.cuda.get_rng_state() if torch.cuda.is_available() else None
+        self._counting, self._counts = True, {}
+        try:
+            self._loss(batch, theta, cf_now).backward()
+        finally:
+            self._counting = False
+        self._restore_sn(snap)
+        if rng is not None:
+            torch.cuda.set_rng_state(rng)
+        self._profiles[key] = dict(self._counts)
+        return self._profiles[key]
+
+    def _iteration(self, batch, theta, cf_now, profile):
+        """Everything from zero_grad to the optimizer step (graph-capturable)."""
+        self._zero_grads()
+        loss = self._loss(batch, theta, cf_now)
+        if self.sync is not None:
+            self.sync.arm(profile)
+        loss.backward()
+        if self.sync is not None:
+            self.sync.finish()
+        live = sorted({ni for (p, _), ni in zip(self.groups, self.net_of) if id(p) in profile})
+        for ni in live:
+            self.step_dev[ni:ni + 1] += 1.0
+        # parameters without a gradient in this configuration are skipped entirely, like torch.optim.Adam does for
+        # grad=None (the unused bn_conv1 affine; Transition at horizon 3)
+        chunks = [(p, p.grad, m, v, clip, self.step_dev[ni:ni + 1])
+                  for (p, clip), m, v, ni in zip(self.groups, self.m, self.v, self.net_of) if id(p) in profile]
+        self.K.clip_adam(chunks, self.lr, self.betas[0], self.betas[1], self.eps, 0, step_dev=self.step_dev,
+                         gscale=1.0 / self.world_size)
+        return loss
+
+    def _snapshot_sn(self):
+        out = []
+        for net in self.nets.values():
+            for n, p in net.named_parameters():
+                if n.endswith("weight_u") or n.endswith("weight_v"):
+                    out.append((p, p.detach().clone()))
+        return out
+
+    @staticmethod
+    def _restore_sn(snap):
+        with torch.no_grad():
+            for p, val in snap:
+                p.copy_(val)
+
+    def step(self, batch, theta, cf_now=False, use_graph=False):
+        """batch: dict of device tensors.  Returns the (device) loss tensor of this iteration."""
+        if not use_graph:
+            return self._iteration(batch, theta, cf_now, self._profile(batch, theta, cf_now))
+        key = (tuple(batch["states"].shape), bool(cf_now), float(theta))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(batch, theta, cf_now)
+            self._graphs[key] = g
+        graph, static, loss = g
+        for k, v in batch.items():
+            if static[k] is not v:
+                static[k].copy_(v, non_blocking=True)
+        graph.replay()
+        return loss
+
+    def static_inputs(self, batch, theta, cf_now=False):
+        """Capture (if needed) and return the graph's static input tensors, so callers can fill them in place."""
+        key = (tuple(batch["states"].shape), bool(cf_now), float(theta))
+        if key not in self._graphs:
+            self._graphs[key] = self._capture(batch, theta, cf_now)
+        return self._graphs[key][1]
+
+    def _capture(self, batch, theta, cf_now):
+        static = {k: v.clone() for k, v in batch.items()}
+        profile = self._profile(static, theta, cf_now)
+        # warm-up on a side stream (allocator pools, lazy init); training state is restored afterwards
+        snap_sn = self._snapshot_sn()
+        snap_p = [(p, p.detach().clone()) for p, _ in self.groups]
+        snap_m = [t.clone() for t in self.m]
+        snap_v = [t.clone() for t in self.v]
+        step0 = self.step_dev.clone()
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._iteration(static, theta, cf_now, profile)
+        torch.cuda.current_stream().wait_stream(s)
+        with torch.no_grad():
+            self._restore_sn(snap_sn)
+            for p, val in snap_p:
+                p.copy_(val)
+            for t, val in zip(self.m, snap_m):
+                t.copy_(val)
+            for t, val in zip(self.v, snap_v):
+                t.copy_(val)
+            self.step_dev.copy_(step0)
+        n0 = self.K.launch_count()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            loss = self._iteration(static, theta, cf_now, profile)
+        self.launches_per_step[(static["states"].shape[1], bool(cf_now))] = self.K.launch_count() - n0
+        return graph, static, loss
