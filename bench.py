@@ -271,11 +271,13 @@ def main():
     n0 = K.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync_all()
+    torch.cuda.nvtx.range_push("timed")  # lets `ncu --nvtx --nvtx-include timed/` select exactly this region
     e0.record()
     for i in range(args.steps):
         loss = run_step(i)
     e1.record()
     sync_all()
+    torch.cuda.nvtx.range_pop()
     ms_total = e0.elapsed_time(e1)
     # ---------------- end-to-end timing: host buffers in, loss out, every step ----------------
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()

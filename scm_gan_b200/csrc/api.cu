@@ -2,6 +2,7 @@
 // TMA tensor-map encoding, launch-geometry selection, kernel launches.  No allocation, no synchronisation.
 #include "../../include/scmgan.h"
 #include "conv_igemm.cuh"
+#include "conv_igemm_v2.cuh"
 #include "conv_wgrad.cuh"
 #include "elementwise.cuh"
 #include "host_util.cuh"
@@ -9,6 +10,7 @@
 #include <algorithm>
 #include <atomic>
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace scm {
@@ -109,6 +111,100 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Igem
     return SCM_OK;
 }
 
+constexpr int kSmemMax = 227 * 1024;
+
+// Weight-stationary kernel (conv_igemm_v2.cuh).  Returns 1 when the shape does not fit (caller falls back to v1).
+template <int CK, int TPG>
+static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& P, const IgemmV2Geom& G,
+                          int gx, int nsplit, int smem, cudaStream_t st) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<CK, TPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemMax));
+        attr_set = true;
+    }
+    conv3x3_igemm_v2_kernel<CK, TPG><<<dim3(gx, nsplit), kV2Threads, smem, st>>>(ta, tb, P, G);
+    SCM_CUDA(cudaGetLastError());
+    return SCM_OK;
+}
+
+template <int CK>
+static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long long rows, cudaStream_t st) {
+    constexpr int RB = CK * 2;
+    const int chunks = d->cin / CK;
+    const int budget_b = 150 * 1024;
+    int n_cta = d->n, nsplit = 1;
+    while (9 * chunks * n_cta * RB > budget_b && n_cta % 32 == 0 && n_cta > 64) { n_cta /= 2; nsplit *= 2; }
+    if (9 * chunks * n_cta * RB > budget_b) return 1;
+    IgemmV2Geom G;
+    memset(&G, 0, sizeof(G));
+    G.n_total = d->n; G.n_cta = n_cta; G.b_tile_bytes = n_cta * RB;
+    const int b_res = (9 * chunks * G.b_tile_bytes + 1023) & ~1023;
+    const int fixed = b_res + kV2EpiWarps * (kV2StageWarpBytes + 32 * 16) + 1024 + 256 + 1024;
+    const int avail = kSmemMax - fixed;
+    const int Wp = d->W + 2;
+    int tpg = 0;
+    if (CK == 64) {
+        // shifted-row reuse of one super tile: all 9 taps if two stages fit, else the 3 taps of one filter row
+        static const char* tpg_env = getenv("SCMGAN_TPG");
+        for (int cand : {9, 3}) {
+            if (tpg_env && atoi(tpg_env) == 3 && cand == 9) continue;
+            const int extent = cand == 9 ? 2 * Wp + 2 : 2;
+            const int R = 128 + extent;
+            const int pieces = (R + 255) / 256;
+            const int piece_rows = (((R + pieces - 1) / pieces) + 7) & ~7;
+            const int stage_bytes = (pieces * piece_rows * RB + 1023) & ~1023;
+            const int stages = std::min(6, avail / stage_bytes);
+            if (stages < 2) continue;
+            tpg = cand;
+            G.loads = pieces; G.box_rows = piece_rows; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
+            for (int l = 0; l < pieces; ++l) { G.ld_row[l] = l * piece_rows; G.ld_smem[l] = l * piece_rows * RB; }
+            for (int t = 0; t < cand; ++t) G.a_off16[t] = uint32_t(((t / 3) * Wp + (t % 3)) * RB) >> 4;
+            break;
+        }
+    } else {
+        // narrow K chunk (Cin = 16): nine separate 128-row boxes, one per tap, share a stage (one barrier round
+        // trip per tile instead of nine)
+        const int tile_bytes = 128 * RB;
+        const int stage_bytes = 9 * tile_bytes;
+        const int stages = std::min(6, avail / stage_bytes);
+        if (stages >= 2 && chunks == 1) {
+            tpg = 9;
+            G.loads = 9; G.box_rows = 128; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
+            for (int t = 0; t < 9; ++t) {
+                G.ld_row[t] = (t / 3) * Wp + (t % 3);
+                G.ld_smem[t] = t * tile_bytes;
+                G.a_off16[t] = uint32_t(t * tile_bytes) >> 4;
+            }
+        }
+    }
+    if (!tpg) return 1;
+    G.groups = 9 / tpg;
+    const int gx = std::max(1, std::min(P.num_tiles, num_sms() / nsplit));
+    G.tiles_stride = gx;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};
+        uint64_t str[1] = {uint64_t(d->x_cs) * 2};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(G.box_rows)};
+        int rc = encode_tmap_bf16(&ta, d->x, 2, dims, str, box, RB);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {uint64_t(d->cin), uint64_t(9 * d->n)};
+        uint64_t str[1] = {uint64_t(d->cin) * 2};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(n_cta)};
+        int rc = encode_tmap_bf16(&tb, d->w, 2, dims, str, box, RB);
+        if (rc) return rc;
+    }
+    const int smem = fixed + G.num_stages * G.a_stage_bytes;
+    if (CK == 64) {
+        return tpg == 9 ? launch_v2_inst<64, 9>(ta, tb, P, G, gx, nsplit, smem, st)
+                        : launch_v2_inst<64, 3>(ta, tb, P, G, gx, nsplit, smem, st);
+    }
+    return launch_v2_inst<16, 9>(ta, tb, P, G, gx, nsplit, smem, st);
+}
+
 static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     SCM_REQUIRE(d != nullptr, "conv3x3: null descriptor");
     SCM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "conv3x3: bad geometry B=%d H=%d W=%d", d->B, d->H, d->W);
@@ -148,7 +244,18 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     P.add = reinterpret_cast<const __nv_bfloat16*>(d->add); P.add_cs = d->add_cs; P.add_c_off = d->add_c_off;
     P.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate); P.gate_cs = d->gate_cs; P.gate_c_off = d->gate_c_off;
     P.out_f32 = d->out_f32; P.n_valid = d->n_valid; P.sample_out = d->sample_out; P.uniforms = d->uniforms;
+    {
+        const char* dbg = getenv("SCMGAN_DEBUG");
+        P.debug = dbg ? atoi(dbg) : 0;
+    }
 
+    {
+        static const char* v1env = getenv("SCMGAN_IGEMM_V1");
+        if (!(v1env && atoi(v1env))) {
+            const int rc = CK == 64 ? launch_igemm_v2<64>(d, P, rows, st) : launch_igemm_v2<16>(d, P, rows, st);
+            if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape does not fit -> first-generation kernel
+        }
+    }
     CUtensorMap ta, tb;
     {
         uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};

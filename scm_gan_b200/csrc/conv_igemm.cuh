@@ -54,6 +54,7 @@ struct IgemmParams {
     // Bernoulli head (Transition conv6): z = (u < p) in training, (p > 0.5) in eval
     float* sample_out;      // fp32 NCHW [B][n_valid][H][W] or nullptr
     const float* uniforms;  // fp32 NCHW or nullptr (nullptr => threshold at 0.5)
+    int debug;              // profiling aid (env SCMGAN_DEBUG): bit0 skip global stores, bit1 skip TMEM loads
 };
 
 template <int CK>
@@ -200,9 +201,14 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 
             for (int n0 = 0; n0 < P.n; n0 += 16) {
                 float v[16];
-                tmem_ld16(taddr + uint32_t(n0), v);
-                tmem_ld_wait();
-                if (!valid) continue;
+                if (!(P.debug & 2)) {
+                    tmem_ld16(taddr + uint32_t(n0), v);
+                    tmem_ld_wait();
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = float(i);
+                }
+                if (!valid || (P.debug & 1)) continue;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float x = v[i] * P.scale;

@@ -1,0 +1,347 @@
+// 3x3 implicit-GEMM convolution, second generation: weight-stationary persistent CTAs.
+//
+// Measured on B200 (profiles/r01_microbench_v1.txt): the first kernel re-streams weights and one activation tile
+// per filter tap through the L2->SM fabric (576 KB per 128-row tile, ~40 B/cycle/SM - the fabric limit) and spends
+// as long again in an epilogue of half-sector stores.  This version removes both:
+//   * the packed weights of the CTA's N slice stay RESIDENT in shared memory for the whole (persistent) kernel:
+//     one TMA burst at start, zero weight traffic per tile.  N is split across CTAs (blockIdx.y) until the slice
+//     fits (9 * Cin * n_cta * 2 bytes <= ~147 KB);
+//   * one activation "super tile" per K chunk serves SEVERAL filter taps: in the flattened plane the tap (ky,kx)
+//     operand is the same rows shifted by ky*(W+2)+kx, i.e. the same shared-memory tile at a row offset.  UMMA
+//     descriptors address it directly (start address + 128 B per row; the swizzle phase travels in the
+//     descriptor's base-offset field), so A traffic drops 3x (kx reuse) or ~4.5x (ky+kx reuse);
+//   * the epilogue stages 32-column groups through swizzled shared memory and writes full 64-byte row segments
+//     (whole sectors) with every lane active; bias lives in shared memory.
+// Warp roles and the double-buffered TMEM accumulator are as in conv_igemm.cuh.
+#pragma once
+#include "conv_igemm.cuh"
+
+namespace scm {
+
+struct IgemmV2Geom {
+    int n_total;      // packed weight rows per tap (GEMM N of the whole layer)
+    int n_cta;        // N slice per CTA (multiple of 16)
+    int groups;       // 9 / TPG stages per K chunk and tile
+    int loads;        // TMA loads per stage
+    int box_rows;     // box rows of the activation tensor map
+    int ld_row[9];    // per load: row delta relative to the group's first tap row
+    int ld_smem[9];   // per load: byte offset inside the stage
+    uint32_t a_off16[9];  // per tap of a group: operand start inside the stage, in 16-byte units
+    int a_stage_bytes;
+    int b_tile_bytes;    // n_cta * row bytes
+    int num_stages;
+    int tiles_stride;    // == gridDim.x
+};
+
+constexpr int kV2StageWarpBytes = 2048;  // epilogue staging: 32 rows x 32 columns bf16 per warp
+// A lone warp per scheduler issues one dependent instruction every ~4 cycles, which made the 4-warp epilogue the
+// bottleneck (measured); eight epilogue warps = two per TMEM lane quarter, interleaving the 32-column groups.
+constexpr int kV2EpiWarps = 8;
+constexpr int kV2Threads = 64 + 32 * kV2EpiWarps;
+
+// CK: channels per K chunk (64 -> 128B swizzle, 16 -> 32B swizzle).  TPG: filter taps served by one stage.
+template <int CK, int TPG>
+__global__ void __launch_bounds__(kV2Threads, 1)
+conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                        const __grid_constant__ IgemmParams P, const __grid_constant__ IgemmV2Geom G) {
+    using Cfg = IgemmCfg<CK>;
+    constexpr int RB = Cfg::kRowBytes;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int chunks = P.cin_chunks;
+    const int b_res_bytes = 9 * chunks * G.b_tile_bytes;
+    uint8_t* s_b = smem;
+    uint8_t* s_a = smem + ((b_res_bytes + 1023) & ~1023);
+    uint8_t* s_stage = s_a + size_t(G.num_stages) * G.a_stage_bytes;           // kV2EpiWarps x 2 KB
+    int* s_rowinfo = reinterpret_cast<int*>(s_stage + kV2EpiWarps * kV2StageWarpBytes);  // per warp: 32 rows x 4 ints
+    float* s_bias = reinterpret_cast<float*>(s_rowinfo + kV2EpiWarps * 32 * 4);          // [256]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
+    uint64_t* full_bar = bars;                  // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;    // [kMaxStages]
+    uint64_t* acc_full = bars + 2 * kMaxStages;       // [2]
+    uint64_t* acc_empty = bars + 2 * kMaxStages + 2;  // [2]
+    uint64_t* b_full = bars + 2 * kMaxStages + 4;     // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 5);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int n0 = blockIdx.y * G.n_cta;  // first output channel of this CTA's slice
+    constexpr int kGroups = 9 / TPG;
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tmap(&tmap_a);
+        prefetch_tmap(&tmap_b);
+        for (int s = 0; s < G.num_stages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&acc_full[s], 1);
+            mbar_init(&acc_empty[s], kV2EpiWarps);
+        }
+        mbar_init(b_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kV2EpiWarps) s_bias[i] = P.bias ? P.bias[n0 + i] : 0.f;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one
+        // elected lane issues.
+        if (elect_one()) {
+            // resident weights: [tap][chunk] tiles of n_cta rows
+            mbar_arrive_expect_tx(b_full, uint32_t(9 * chunks * G.n_cta * RB));
+            for (int tap = 0; tap < 9; ++tap)
+                for (int c = 0; c < chunks; ++c)
+                    tma_load_2d(s_b + size_t(tap * chunks + c) * G.b_tile_bytes, &tmap_b, b_full, c * CK,
+                                tap * G.n_total + n0);
+        }
+        __syncwarp();
+        int stage = 0;
+        uint32_t phase = 0;
+        const uint32_t tx = uint32_t(G.loads * G.box_rows * RB);
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+            const int m0 = tile * 128;
+            for (int g = 0; g < kGroups; ++g) {
+                const int tap0 = g * TPG;
+                const int row0 = m0 + (tap0 / 3 - 1) * P.Wp + (tap0 % 3 - 1);
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (elect_one()) {
+                        uint8_t* sa = s_a + size_t(stage) * G.a_stage_bytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], tx);
+                        for (int l = 0; l < G.loads; ++l)
+                            tma_load_2d(sa + G.ld_smem[l], &tmap_a, &full_bar[stage], P.a_c_off + c * CK,
+                                        row0 + G.ld_row[l]);
+                    }
+                    __syncwarp();
+                    if (++stage == G.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------ MMA issuer ------------------------------
+        // One elected lane issues every tcgen05.mma; with N = 64 an instruction retires in ~32 cycles, so the issue
+        // loop is fully unrolled, descriptor arithmetic is one 64-bit add per operand, and control flow stays
+        // warp-uniform so that the descriptors live in uniform registers (no per-instruction convergence loop).
+        const uint32_t idesc = make_idesc_f16(128, G.n_cta, /*bf16*/ 1, 0, 0);
+        const uint64_t bdesc0 = make_smem_desc(smem_u32(s_b), 16, Cfg::kSbo, Cfg::kLayout);
+        const uint64_t adesc0 = make_smem_desc(smem_u32(s_a), 16, Cfg::kSbo, Cfg::kLayout);
+        const uint32_t b_tile16 = uint32_t(G.b_tile_bytes) >> 4;
+        const uint32_t a_stage16 = uint32_t(G.a_stage_bytes) >> 4;
+        uint32_t a_off[TPG];
+#pragma unroll
+        for (int t = 0; t < TPG; ++t) a_off[t] = G.a_off16[t];
+        int stage = 0;
+        uint32_t phase = 0;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        mbar_wait(b_full, 0);
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+            mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + uint32_t(acc * kAccStageCols);
+            uint32_t accumulate = 0;
+#pragma unroll 1
+            for (int g = 0; g < kGroups; ++g) {
+#pragma unroll 1
+                for (int c = 0; c < chunks; ++c) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * a_stage16);
+                    const uint64_t b_st = bdesc0 + uint64_t(uint32_t(g * TPG * chunks + c) * b_tile16);
+                    if (elect_one()) {
+#pragma unroll
+                        for (int t = 0; t < TPG; ++t) {
+                            const uint64_t at = a_st + uint64_t(a_off[t]);
+                            const uint64_t bt = b_st + uint64_t(uint32_t(t * chunks) * b_tile16);
+#pragma unroll
+                            for (int k = 0; k < Cfg::kKSteps; ++k)
+                                umma_f16(tmem_d, at + uint64_t(2 * k), bt + uint64_t(2 * k), idesc,
+                                         (t == 0 && k == 0) ? accumulate : 1u);
+                        }
+                        umma_commit(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    accumulate = 1;
+                    if (++stage == G.num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
+            if (elect_one()) umma_commit(&acc_full[acc]);
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ------------------------------ epilogue ------------------------------
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        const int ew = warp - 2;
+        const int half = ew >> 2;  // which of the two warps sharing this lane quarter
+        uint8_t* stg = s_stage + ew * kV2StageWarpBytes;
+        int* rinfo = s_rowinfo + ew * 32 * 4;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        const int plane = P.Hp * P.Wp;
+        const size_t hw = size_t(P.H) * P.W;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+            const int p = tile * 128 + q * 32 + lane;
+            const bool valid = p < P.rows;
+            int b = 0, hp = 0, wp = 0;
+            if (valid) {
+                b = p / plane;
+                const int rem = p - b * plane;
+                hp = rem / P.Wp;
+                wp = rem - hp * P.Wp;
+            }
+            const bool interior = valid && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
+            // destinations of this row in the output plane: itself, and up to three wrapped halo copies
+            int d0 = -1, d1 = -1, d2 = -1, d3 = -1;
+            if (interior || (valid && !P.wrap)) d0 = p;  // zero-padding planes: halo rows are written (as zeros)
+            if (P.wrap && interior) {
+                int hp2 = -1, wp2 = -1;
+                if (hp == 1) hp2 = P.H + 1; else if (hp == P.H) hp2 = 0;
+                if (wp == 1) wp2 = P.W + 1; else if (wp == P.W) wp2 = 0;
+                if (hp2 >= 0) d1 = b * plane + hp2 * P.Wp + wp;
+                if (wp2 >= 0) d2 = b * plane + hp * P.Wp + wp2;
+                if (hp2 >= 0 && wp2 >= 0) d3 = b * plane + hp2 * P.Wp + wp2;
+            }
+            if (P.out) {
+                __syncwarp();
+                reinterpret_cast<int4*>(rinfo)[lane] = make_int4(d0, d1, d2, d3);
+                __syncwarp();
+            }
+            const float* sbp = (P.sample_bias && valid) ? P.sample_bias + size_t(b) * G.n_total + n0 : nullptr;
+
+            mbar_wait(&acc_full[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
+
+            for (int c0 = half * 32; c0 < G.n_cta; c0 += 64) {
+                const int ncols = min(32, G.n_cta - c0);  // 16 or 32
+                float v[32];
+                if (!(P.debug & 2)) {
+                    tmem_ld16(taddr + uint32_t(c0), v);
+                    if (ncols > 16) tmem_ld16(taddr + uint32_t(c0 + 16), v + 16);
+                    tmem_ld_wait();
+                }
+                if (P.debug & 1) continue;
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], P.scale, s_bias[c0 + (i < ncols ? i : 0)]);
+                if (sbp) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        if (j * 4 < ncols) {
+                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sbp + c0) + j);
+                            v[4 * j] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
+                        }
+                    }
+                }
+                if (interior && P.add) {
+                    const uint4* ap =
+                        reinterpret_cast<const uint4*>(P.add + size_t(p) * P.add_cs + P.add_c_off + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j * 8 < ncols) {
+                            const uint4 r = __ldg(ap + j);
+                            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&r);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[8 * j + i] += __bfloat162float(h[i]);
+                        }
+                    }
+                }
+                if (P.act == ACT_LRELU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
+                } else if (P.act == ACT_SIGMOID) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+                }
+                if (interior && P.gate) {
+                    const uint4* gp =
+                        reinterpret_cast<const uint4*>(P.gate + size_t(p) * P.gate_cs + P.gate_c_off + n0 + c0);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        if (j * 8 < ncols) {
+                            const uint4 r = __ldg(gp + j);
+                            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&r);
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) v[8 * j + i] *= (__bfloat162float(h[i]) > 0.f) ? 1.f : P.slope;
+                        }
+                    }
+                }
+                if (P.out) {
+                    // stage this lane's row (64 B) with a 16-byte-chunk swizzle, then store whole row segments
+                    const int sw = (lane >> 1) & 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        uint4 o;
+                        __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&o);
+                        if (interior) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) w2[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
+                        } else {
+                            o = make_uint4(0, 0, 0, 0);
+                        }
+                        *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) = o;
+                    }
+                    __syncwarp();
+                    const int chunk = lane & 3;
+                    const int nchunks = ncols >> 3;  // 16-byte chunks per row in this group: 2 or 4
+                    if (chunk < nchunks) {
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            const int r = it * 8 + (lane >> 2);
+                            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4));
+                            const int4 d = reinterpret_cast<const int4*>(rinfo)[r];
+                            const size_t coff = size_t(P.out_c_off + n0 + c0 + chunk * 8);
+                            if (d.x >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.x) * P.out_cs + coff) = val;
+                            if (d.y >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.y) * P.out_cs + coff) = val;
+                            if (d.z >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.z) * P.out_cs + coff) = val;
+                            if (d.w >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.w) * P.out_cs + coff) = val;
+                        }
+                    }
+                    __syncwarp();
+                }
+                if (P.out_f32 && interior) {
+                    const size_t base = (size_t(b) * P.n_valid) * hw + size_t(hp - 1) * P.W + (wp - 1);
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int n = n0 + c0 + i;
+                        if (i < ncols && n < P.n_valid) {
+                            const size_t idx = base + size_t(n) * hw;
+                            P.out_f32[idx] = v[i];
+                            if (P.sample_out) {
+                                // training: z = (u < p) ; eval: z = (p > 0.5)
+                                const float z = P.uniforms ? (__ldg(P.uniforms + idx) < v[i] ? 1.f : 0.f)
+                                                           : (v[i] > 0.5f ? 1.f : 0.f);
+                                P.sample_out[idx] = z;
+                            }
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+}  // namespace scm

@@ -149,14 +149,16 @@ __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int fmt, int
 
 constexpr uint64_t kLayoutSw128 = 2, kLayoutSw64 = 4, kLayoutSw32 = 6;
 
-// Shared-memory matrix descriptor.  lbo/sbo are byte offsets (multiples of 16).
+// Shared-memory matrix descriptor.  lbo/sbo are byte offsets (multiples of 16).  The base-offset field stays 0:
+// measured on B200, the tensor core applies the 32/64/128B swizzle XOR to the *absolute* shared-memory address
+// (exactly like TMA), so a descriptor may start at any 16-byte-aligned row of a swizzled tile (conv_igemm_v2.cuh
+// relies on this to address one activation tile at nine different row shifts).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint64_t layout) {
     uint64_t d = 0;
     d |= uint64_t((saddr & 0x3FFFFu) >> 4);
     d |= uint64_t((lbo >> 4) & 0x3FFFu) << 16;
     d |= uint64_t((sbo >> 4) & 0x3FFFu) << 32;
     d |= uint64_t(1) << 46;  // descriptor version for sm_100
-    d |= uint64_t((saddr >> 7) & 0x7u) << 49;  // base offset: zero whenever the tile is 1024B-aligned
     d |= layout << 61;
     return d;
 }

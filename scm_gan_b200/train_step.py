@@ -89,9 +89,9 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         z_cf_b = z_orig
         L = z.shape[1]
         ar = torch.arange(B, device=z.device)
-        unswapped = torch.ones((B, L), dtype=torch.float32, device=z.device)
-        unswapped[ar, cf_indices[:, 0]] = 0
-        unswapped[ar, cf_indices[:, 1]] = 0
+        hit = torch.zeros((B, L), dtype=torch.float32, device=z.device)
+        hit.scatter_(1, cf_indices, 1.0)  # both intervened factors of every sample (graph-capturable)
+        unswapped = 1.0 - hit
         # main.py:253 assigns through views: net effect z[i, idx_a] <- z[i, idx_b], in place on z_orig
         z_cf_b[ar, cf_indices[:, 0]] = z_cf_b[ar, cf_indices[:, 1]]
         for t in range(1, counterfactual_horizon):
