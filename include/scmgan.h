@@ -109,8 +109,12 @@ typedef struct {
     int flip;
     int co_valid, ci_valid;
     float scale;
+    void* workspace; /* optional split-K scratch (scmgan_wgrad_workspace_bytes()); with it the reduction is a second,
+                        deterministic kernel instead of fp32 atomics */
+    long long workspace_bytes;
 } scmgan_wgrad_desc;
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* desc_host, scmgan_stream_t stream);
+long long scmgan_wgrad_workspace_bytes(void);
 
 /* S[b][c] += sum over the interior of plane channels [c_off, c_off+n); db[c] += the same summed over b.
  * Bias gradients (cuDNN bias backward) and the folded action-channel gradient. */

@@ -38,7 +38,8 @@ class WgradDesc(C.Structure):
                 ("dy", C.c_void_p), ("dy_cs", C.c_int), ("dy_c_off", C.c_int), ("cout", C.c_int),
                 ("x", C.c_void_p), ("x_cs", C.c_int), ("x_c_off", C.c_int), ("cin", C.c_int),
                 ("g", C.c_void_p), ("g_s_co", C.c_longlong), ("g_s_ci", C.c_longlong), ("g_s_tap", C.c_longlong),
-                ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float)]
+                ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 class SnLayer(C.Structure):
@@ -69,6 +70,7 @@ SIGNATURES = {
     "scmgan_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "scmgan_conv3x3_dgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "scmgan_conv3x3_wgrad": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "scmgan_wgrad_workspace_bytes": (C.c_longlong, []),
     "scmgan_plane_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_spectral_norm_fwd": (C.c_int, [C.c_int, C.POINTER(SnLayer), C.c_void_p]),

@@ -277,7 +277,8 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
 // one wgrad launch: P = 128 channels of `pp` (view per p_interior), Q = n channels of `qp`
 static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_off, bool p_interior, const void* qp,
                         int q_cs, int q_c_off, int n, int q_sign, int flip, float scale, float* g, long long g_sm,
-                        long long g_sn, long long g_st, int m_valid, int n_valid, cudaStream_t st) {
+                        long long g_sn, long long g_st, int m_valid, int n_valid, float* ws, long long ws_bytes,
+                        cudaStream_t st) {
     const int Hp = H + 2, Wp = W + 2;
     const int Wd = p_interior ? W : Wp, Hd = p_interior ? H : Hp;
     // pixel box: BW covers a row of P's view, KP = BW*BH multiple of 16, ~64 pixels
@@ -328,6 +329,12 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     P.tap0_stride = tg; P.n = n; P.q_aw = q_aw; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.q_sign = q_sign;
     P.flip = flip; P.scale = scale; P.g = g; P.g_sm = g_sm; P.g_sn = g_sn; P.g_st = g_st;
     P.m_valid = m_valid; P.n_valid = n_valid;
+    {
+        static const char* dbg = getenv("SCMGAN_DEBUG");
+        P.debug = dbg ? (atoi(dbg) & 8) : 0;
+    }
+    const long long ws_need = (long long)splits * 9 * n * 128 * 4;
+    P.ws = (ws && ws_bytes >= ws_need) ? ws : nullptr;
 
     auto make_view = [&](CUtensorMap* t, const void* base, int cs, bool interior, int box_c, int swz) -> int {
         const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base);
@@ -352,6 +359,13 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
+    if (P.ws) {
+        const int total = 9 * n * 128;
+        wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
+                                                                  n_valid, scale);
+        SCM_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
     return SCM_OK;
 }
 
@@ -431,7 +445,8 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
                 int rc = wgrad_launch(d->B, d->H, d->W, d->dy, d->dy_cs, d->dy_c_off + m0, true, d->x, d->x_cs,
                                       d->x_c_off + c0, n, +1, d->flip, d->scale,
                                       d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci, d->g_s_tap,
-                                      std::min(128, d->co_valid - m0), nv, st);
+                                      std::min(128, d->co_valid - m0), nv, (float*)d->workspace, d->workspace_bytes,
+                                      st);
                 if (rc) return rc;
             }
         }
@@ -443,13 +458,19 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
             if (mv <= 0) break;
             int rc = wgrad_launch(d->B, d->H, d->W, d->x, d->x_cs, d->x_c_off + c0, false, d->dy, d->dy_cs,
                                   d->dy_c_off, d->cout, -1, d->flip, d->scale, d->g + c0 * d->g_s_ci, d->g_s_ci,
-                                  d->g_s_co, d->g_s_tap, mv, d->co_valid, st);
+                                  d->g_s_co, d->g_s_tap, mv, d->co_valid, (float*)d->workspace, d->workspace_bytes,
+                                  st);
             if (rc) return rc;
         }
         return SCM_OK;
     }
     set_error("wgrad: one of cout (%d) / cin (%d) must be a multiple of 128", d->cout, d->cin);
     return SCM_EUNSUPPORTED;
+}
+
+long long scmgan_wgrad_workspace_bytes(void) {
+    // upper bound over all shapes: (#CTAs of one launch) x (taps per CTA group) x 128 x n floats, n <= 128
+    return (long long)(num_sms() + 8) * 9 * 128 * 128 * 4 / 3 + (1 << 20);
 }
 
 int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int H, int W, float* S, float* db,

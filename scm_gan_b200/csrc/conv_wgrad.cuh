@@ -38,6 +38,8 @@ struct WgradParams {
     float* g;          // gradient tensor (fp32, accumulated atomically)
     long long g_sm, g_sn, g_st;  // element strides for m, n, tap
     int m_valid, n_valid;
+    int debug;  // profiling aid (env SCMGAN_DEBUG bit3): skip the reduction
+    float* ws;  // split-K partials [split][tap][n][128] (fp32) or nullptr => red.global.add straight into g
 };
 
 constexpr int kWgradThreads = 192;
@@ -91,14 +93,15 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
 
     if (nkb > 0) {
         if (warp == 0) {
-            if (lane == 0) {
-                const uint32_t tx = uint32_t(2 * KP * 128 + ntaps * q_atoms * KP * P.q_aw * 2);
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int kb = kb_begin; kb < kb_end; ++kb) {
-                    const int b = kb / P.nby;
-                    const int h0 = (kb - b * P.nby) * P.BH;
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+            // warp-uniform loop, one elected lane issues the TMA loads
+            const uint32_t tx = uint32_t(2 * KP * 128 + ntaps * q_atoms * KP * P.q_aw * 2);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb) {
+                const int b = kb / P.nby;
+                const int h0 = (kb - b * P.nby) * P.BH;
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                if (elect_one()) {
                     uint8_t* sp = smem + size_t(stage) * stage_bytes;
                     mbar_arrive_expect_tx(&full_bar[stage], tx);
                     tma_load_4d(sp, &tmap_p, &full_bar[stage], P.p_c_off, 0, h0, b);
@@ -111,35 +114,42 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                             tma_load_4d(sq + j * q_atom_bytes, &tmap_q, &full_bar[stage], P.q_c_off + j * P.q_aw, dx,
                                         h0 + dy, b);
                     }
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
-                const uint32_t idesc = make_idesc_f16(128, P.n, 1, 1, 1);
-                const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
-                const uint32_t q_sbo = 8u * P.q_aw * 2u;
-                const uint32_t q_kstep = 16u * P.q_aw * 2u;
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int i = 0; i < nkb; ++i) {
-                    mbar_wait(&full_bar[stage], phase);
-                    tc_fence_after();
-                    const uint32_t sp = smem_u32(smem + size_t(stage) * stage_bytes);
+            const uint32_t idesc = make_idesc_f16(128, P.n, 1, 1, 1);
+            const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
+            const uint32_t q_sbo = 8u * P.q_aw * 2u;
+            const uint32_t q_kstep16 = (16u * P.q_aw * 2u) >> 4;
+            const uint32_t q_tap16 = uint32_t(q_tap_bytes) >> 4;
+            const uint64_t adesc0 = make_smem_desc(smem_u32(smem), p_atom_bytes, 1024, kLayoutSw128);
+            const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + p_bytes, q_atom_bytes, q_sbo, q_layout);
+            const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
+            const int ksteps = KP / 16;
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * stage16);
+                const uint64_t b_st = bdesc0 + uint64_t(uint32_t(stage) * stage16);
+                if (elect_one()) {
                     for (int t = 0; t < ntaps; ++t) {
-                        const uint32_t sq = sp + p_bytes + t * q_tap_bytes;
                         const uint32_t tmem_d = tmem_base + uint32_t(t * P.n);
-                        for (int k = 0; k < KP / 16; ++k) {
-                            const uint64_t adesc = make_smem_desc(sp + k * 2048, p_atom_bytes, 1024, kLayoutSw128);
-                            const uint64_t bdesc = make_smem_desc(sq + k * q_kstep, q_atom_bytes, q_sbo, q_layout);
-                            umma_f16(tmem_d, adesc, bdesc, idesc, (i > 0 || k > 0) ? 1u : 0u);
-                        }
+                        const uint64_t bt = b_st + uint64_t(uint32_t(t) * q_tap16);
+                        for (int k = 0; k < ksteps; ++k)
+                            umma_f16(tmem_d, a_st + uint64_t(k * 128), bt + uint64_t(uint32_t(k) * q_kstep16), idesc,
+                                     (i > 0 || k > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
-                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(acc_full);
+                __syncwarp();
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
+            if (elect_one()) umma_commit(acc_full);
+            __syncwarp();
         } else {
             const int q = warp & 3;
             const int m = q * 32 + lane;
@@ -152,7 +162,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                     float v[16];
                     tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(t * P.n + n0), v);
                     tmem_ld_wait();
-                    if (m < P.m_valid) {
+                    if (P.ws) {
+                        // deterministic path: coalesced partials (m fastest), summed by wgrad_reduce_kernel
+                        float* wp = P.ws + ((size_t(blockIdx.x) * 9 + tap) * P.n + n0) * 128 + m;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) wp[size_t(i) * 128] = v[i];
+                    } else if (m < P.m_valid && !P.debug) {
                         float* gp = P.g + (long long)m * P.g_sm + (long long)gtap * P.g_st;
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
@@ -170,6 +185,25 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
+}
+
+// Sum the split-K partials and scatter into the caller's gradient layout:
+//   g[m*g_sm + n*g_sn + tap'*g_st] += scale * sum_split ws[split][tap][n][m]
+__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n, float* __restrict__ g,
+                                    long long g_sm, long long g_sn, long long g_st, int flip, int m_valid,
+                                    int n_valid, float scale) {
+    const int total = 9 * n * 128;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int m = idx & 127;
+    const int nn = (idx >> 7) % n;
+    const int tap = idx / (128 * n);
+    if (m >= m_valid || nn >= n_valid) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(ws + size_t(s) * total + idx);
+    const int gtap = flip ? 8 - tap : tap;
+    float* gp = g + (long long)m * g_sm + (long long)nn * g_sn + (long long)gtap * g_st;
+    *gp += acc * scale;
 }
 
 }  // namespace scm

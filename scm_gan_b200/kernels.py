@@ -80,6 +80,20 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
 
 
+_WGRAD_WS = {}
+
+
+def _wgrad_workspace(device):
+    """Per-device split-K scratch for the weight-gradient kernel (allocated once, reused by every launch: launches
+    on one stream are ordered, and the reduce kernel consumes the partials before the next wgrad overwrites them)."""
+    key = (device.type, device.index)
+    ws = _WGRAD_WS.get(key)
+    if ws is None:
+        ws = torch.empty(L.lib().scmgan_wgrad_workspace_bytes() // 4, dtype=torch.float32, device=device)
+        _WGRAD_WS[key] = ws
+    return ws
+
+
 def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
           co_valid=None, ci_valid=None, scale=1.0):
     d = L.WgradDesc()
@@ -91,6 +105,8 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
     d.co_valid = cout if co_valid is None else co_valid
     d.ci_valid = cin if ci_valid is None else ci_valid
     d.scale = scale
+    ws = _wgrad_workspace(g.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
     L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
 
 
