@@ -1,0 +1,67 @@
+"""CPU tests of the drop-in boundary: libscmgan.so loads without a GPU/driver, exports every symbol that
+include/scmgan.h declares, the ctypes table covers them all, and argument validation reports errors through the
+C ABI's return codes (no compute is launched here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "scmgan.h")
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as ge
+    ge.build()
+    from scm_gan_b200 import _lib
+    return _lib
+
+
+def declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(scmgan_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = declared_functions()
+    for must in ("scmgan_conv3x3_fwd", "scmgan_conv3x3_dgrad", "scmgan_conv3x3_wgrad", "scmgan_spectral_norm_fwd",
+                 "scmgan_spectral_norm_bwd", "scmgan_clip_adam", "scmgan_bce_logits", "scmgan_reward_head_fwd",
+                 "scmgan_reward_head_bwd", "scmgan_version", "scmgan_last_error"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(lib):
+    handle = C.CDLL(lib.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(handle, name), f"{name} declared in scmgan.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib):
+    assert sorted(lib.SIGNATURES) == declared_functions()
+
+
+def test_version_and_error_reporting_without_gpu(lib):
+    l = lib.lib()
+    assert l.scmgan_version() >= 100
+    assert l.scmgan_conv3x3_fwd(None, None) == -1  # SCMGAN_EINVAL
+    assert b"null descriptor" in l.scmgan_last_error()
+    d = lib.ConvDesc()
+    d.B, d.H, d.W, d.cin, d.n = 1, 4, 4, 20, 16  # cin not a multiple of 16
+    d.x, d.w = 16, 16
+    assert l.scmgan_conv3x3_fwd(C.byref(d), None) == -1
+    assert b"multiple of 16" in l.scmgan_last_error()
+    w = lib.WgradDesc()
+    assert l.scmgan_conv3x3_wgrad(C.byref(w), None) == -1
+    assert l.scmgan_clip_adam(1, None, 1e-4, 0.9, 0.999, 1e-8, 1, None, 1.0, None) == -1
+    assert l.scmgan_spectral_norm_fwd(0, None, None) == -1
+
+
+def test_struct_layouts_match_header_sizes(lib):
+    # pointer/int/float/long long packing as a C compiler lays out the structs of scmgan.h (x86-64 SysV)
+    assert C.sizeof(lib.PackJob) == 64
+    assert C.sizeof(lib.SnLayer) == 56
+    assert C.sizeof(lib.SnBwdLayer) == 64
+    assert C.sizeof(lib.AdamChunk) == 48
