@@ -107,8 +107,13 @@ def cpu_reference_run(workload, horizon, sample_batch, steps, warmup, threads=No
     import torch
     from oracle import restated as R
     C, H, W, A, Rw = WORKLOADS[workload]
-    if threads:
-        torch.set_num_threads(threads)
+    # all host cores (torchrun exports OMP_NUM_THREADS=1, which would otherwise throttle the baseline)
+    if not threads:
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
     cores = torch.get_num_threads()
     torch.manual_seed(0)
     nets = {"encoder": R.init_encoder(16, C), "decoder": R.init_decoder(16, C),
@@ -215,6 +220,7 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("SCMGAN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as ge
     if rank == 0:
@@ -343,8 +349,14 @@ def main():
                                              f"2 timed iterations ({ms:.0f} ms each)"}
         print(json.dumps(out), flush=True)
     if world > 1:
+        # captured CUDA graphs keep references into the NCCL communicator; tearing the process group down in that
+        # state can block, so synchronise, flush and leave without running the destructors.
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -146,6 +146,10 @@ class Trainer:
         for p, _ in self.groups:
             p.grad = torch.zeros_like(p)
             p.register_post_accumulate_grad_hook(self._on_grad)
+        try:  # gradients are accumulated on whichever stream runs backward (side stream during graph warm-up)
+            torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+        except AttributeError:
+            pass
         self._counting = False
         self._counts = {}
         self._profiles = {}   # (Hn, cf_now) -> {param id: number of gradient accumulations per iteration}
