@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--cpu-sample-batch", type=int, default=2)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--cf-phase", type=int, default=0,
+                    help="iteration i applies the CF losses when (i + cf_phase) %% 5 == 0 (profiling aid)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -249,7 +251,7 @@ def main():
     theta = 1.0
 
     def run_step(i, from_host=False):
-        cf_now = (i % CF_RATE == 0)
+        cf_now = ((i + args.cf_phase) % CF_RATE == 0)
         if from_host:
             tgt = trainer.static_inputs(batch, theta, cf_now) if use_graph else batch
             for k, v in host.items():
@@ -310,14 +312,14 @@ def main():
 
     if use_graph:
         per = trainer.launches_per_step
-        n_cf = len([i for i in range(args.steps) if i % CF_RATE == 0])
+        n_cf = len([i for i in range(args.steps) if (i + args.cf_phase) % CF_RATE == 0])
         launches = per.get((Hn, True), 0) * n_cf + per.get((Hn, False), 0) * (args.steps - n_cf)
     else:
         launches = (K.launch_count() - n0) // 2
 
     if rank == 0:
         peaks = read_peaks()
-        n_cf = len([i for i in range(args.steps) if i % CF_RATE == 0])
+        n_cf = len([i for i in range(args.steps) if (i + args.cf_phase) % CF_RATE == 0])
         t_cf_avg = 2 * (CF_HORIZON - 1) * n_cf / args.steps
         flops_iter = algorithmic_flops_per_iter(C, H, W, A, Rw, B, T, t_cf_avg)
         step_tflops = flops_iter * world / (ms_total / args.steps * 1e-3) / 1e12

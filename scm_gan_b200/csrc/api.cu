@@ -3,6 +3,7 @@
 #include "../../include/scmgan.h"
 #include "conv_igemm.cuh"
 #include "conv_igemm_v2.cuh"
+#include "conv_igemm_v3.cuh"
 #include "conv_wgrad.cuh"
 #include "elementwise.cuh"
 #include "host_util.cuh"
@@ -128,6 +129,82 @@ static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const Ig
     return SCM_OK;
 }
 
+// CTA-pair kernel (conv_igemm_v3.cuh): N = 128, Cin in {64, 128}.  Returns 1 when the shape does not qualify.
+static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, long long rows, cudaStream_t st) {
+    constexpr int CK = 64, RB = 128;
+    static const char* off = getenv("SCMGAN_NO_PAIR");
+    if (off && atoi(off)) return 1;
+    if (d->n != 128 || d->cin % 64 != 0) return 1;
+    const int chunks = d->cin / CK;
+    const int n_half = d->n / 2;
+    if (9 * chunks * n_half * RB > 150 * 1024) return 1;
+    IgemmParams P = P0;
+    P.num_tiles = int((rows + 255) / 256);
+    IgemmV2Geom G;
+    memset(&G, 0, sizeof(G));
+    G.n_total = d->n; G.n_cta = n_half; G.b_tile_bytes = n_half * RB;
+    const int b_res = (9 * chunks * G.b_tile_bytes + 1023) & ~1023;
+    const int fixed = b_res + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
+    const int avail = kSmemMax - fixed;
+    const int Wp = d->W + 2;
+    int tpg = 0;
+    static const char* tpg_env = getenv("SCMGAN_TPG");
+    for (int cand : {9, 3}) {
+        if (tpg_env && atoi(tpg_env) == 3 && cand == 9) continue;
+        const int extent = cand == 9 ? 2 * Wp + 2 : 2;
+        const int R = 128 + extent;
+        const int pieces = (R + 255) / 256;
+        const int piece_rows = (((R + pieces - 1) / pieces) + 7) & ~7;
+        const int stage_bytes = (pieces * piece_rows * RB + 1023) & ~1023;
+        const int stages = std::min(6, avail / stage_bytes);
+        if (stages < (cand == 9 ? 2 : 3)) continue;
+        tpg = cand;
+        G.loads = pieces; G.box_rows = piece_rows; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
+        for (int l = 0; l < pieces; ++l) { G.ld_row[l] = l * piece_rows; G.ld_smem[l] = l * piece_rows * RB; }
+        for (int t = 0; t < cand; ++t) G.a_off16[t] = uint32_t(((t / 3) * Wp + (t % 3)) * RB) >> 4;
+        break;
+    }
+    if (!tpg) return 1;
+    G.groups = 9 / tpg;
+    const int pairs = std::max(1, std::min(P.num_tiles, num_sms() / 2));
+    G.tiles_stride = pairs;
+    CUtensorMap ta, tb;
+    {
+        uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};
+        uint64_t str[1] = {uint64_t(d->x_cs) * 2};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(G.box_rows)};
+        int rc = encode_tmap_bf16(&ta, d->x, 2, dims, str, box, RB);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {uint64_t(d->cin), uint64_t(9 * d->n)};
+        uint64_t str[1] = {uint64_t(d->cin) * 2};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(n_half)};
+        int rc = encode_tmap_bf16(&tb, d->w, 2, dims, str, box, RB);
+        if (rc) return rc;
+    }
+    const int smem = fixed + G.num_stages * G.a_stage_bytes;
+    static bool attr9 = false, attr3 = false;
+    if (tpg == 9) {
+        if (!attr9) {
+            SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v3_kernel<64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSmemMax));
+            attr9 = true;
+        }
+        conv3x3_igemm_v3_kernel<64, 9><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
+    } else {
+        if (!attr3) {
+            SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v3_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          kSmemMax));
+            attr3 = true;
+        }
+        conv3x3_igemm_v3_kernel<64, 3><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
+    }
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 template <int CK>
 static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long long rows, cudaStream_t st) {
     constexpr int RB = CK * 2;
@@ -140,7 +217,7 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
     memset(&G, 0, sizeof(G));
     G.n_total = d->n; G.n_cta = n_cta; G.b_tile_bytes = n_cta * RB;
     const int b_res = (9 * chunks * G.b_tile_bytes + 1023) & ~1023;
-    const int fixed = b_res + kV2EpiWarps * (kV2StageWarpBytes + 32 * 16) + 1024 + 256 + 1024;
+    const int fixed = b_res + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
     const int avail = kSmemMax - fixed;
     const int Wp = d->W + 2;
     int tpg = 0;
@@ -252,6 +329,10 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     {
         static const char* v1env = getenv("SCMGAN_IGEMM_V1");
         if (!(v1env && atoi(v1env))) {
+            if (CK == 64) {
+                const int rc3 = launch_igemm_v3(d, P, rows, st);
+                if (rc3 <= 0) return rc3;
+            }
             const int rc = CK == 64 ? launch_igemm_v2<64>(d, P, rows, st) : launch_igemm_v2<16>(d, P, rows, st);
             if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape does not fit -> first-generation kernel
         }
@@ -360,8 +441,8 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     if (P.ws) {
-        const int total = 9 * n * 128;
-        wgrad_reduce_kernel<<<(total + 255) / 256, 256, 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
+        const int total = 9 * n * 32;
+        wgrad_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
                                                                   n_valid, scale);
         SCM_CUDA(cudaGetLastError());
         ++g_launches;

@@ -10,11 +10,11 @@
 //     operand is the same rows shifted by ky*(W+2)+kx, i.e. the same shared-memory tile at a row offset.  UMMA
 //     descriptors address it directly (start address + 128 B per row; the swizzle phase travels in the
 //     descriptor's base-offset field), so A traffic drops 3x (kx reuse) or ~4.5x (ky+kx reuse);
-//   * the epilogue stages 32-column groups through swizzled shared memory and writes full 64-byte row segments
-//     (whole sectors) with every lane active; bias lives in shared memory.
+//   * eight epilogue warps write their rows with 256-bit stores (igemm_epilogue.cuh); bias lives in shared memory.
 // Warp roles and the double-buffered TMEM accumulator are as in conv_igemm.cuh.
 #pragma once
 #include "conv_igemm.cuh"
+#include "igemm_epilogue.cuh"
 
 namespace scm {
 
@@ -33,7 +33,6 @@ struct IgemmV2Geom {
     int tiles_stride;    // == gridDim.x
 };
 
-constexpr int kV2StageWarpBytes = 2048;  // epilogue staging: 32 rows x 32 columns bf16 per warp
 // A lone warp per scheduler issues one dependent instruction every ~4 cycles, which made the 4-warp epilogue the
 // bottleneck (measured); eight epilogue warps = two per TMEM lane quarter, interleaving the 32-column groups.
 constexpr int kV2EpiWarps = 8;
@@ -52,9 +51,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const int b_res_bytes = 9 * chunks * G.b_tile_bytes;
     uint8_t* s_b = smem;
     uint8_t* s_a = smem + ((b_res_bytes + 1023) & ~1023);
-    uint8_t* s_stage = s_a + size_t(G.num_stages) * G.a_stage_bytes;           // kV2EpiWarps x 2 KB
-    int* s_rowinfo = reinterpret_cast<int*>(s_stage + kV2EpiWarps * kV2StageWarpBytes);  // per warp: 32 rows x 4 ints
-    float* s_bias = reinterpret_cast<float*>(s_rowinfo + kV2EpiWarps * 32 * 4);          // [256]
+    float* s_bias = reinterpret_cast<float*>(s_a + size_t(G.num_stages) * G.a_stage_bytes);  // [256]
     uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 256);
     uint64_t* full_bar = bars;                  // [kMaxStages]
     uint64_t* empty_bar = bars + kMaxStages;    // [kMaxStages]
@@ -182,153 +179,21 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
-        // ------------------------------ epilogue ------------------------------
+        // ------------------------------ epilogue (igemm_epilogue.cuh) ------------------------------
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int ew = warp - 2;
         const int half = ew >> 2;  // which of the two warps sharing this lane quarter
-        uint8_t* stg = s_stage + ew * kV2StageWarpBytes;
-        int* rinfo = s_rowinfo + ew * 32 * 4;
         int acc = 0;
         uint32_t acc_phase = 0;
-        const int plane = P.Hp * P.Wp;
-        const size_t hw = size_t(P.H) * P.W;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
             const int p = tile * 128 + q * 32 + lane;
-            const bool valid = p < P.rows;
-            int b = 0, hp = 0, wp = 0;
-            if (valid) {
-                b = p / plane;
-                const int rem = p - b * plane;
-                hp = rem / P.Wp;
-                wp = rem - hp * P.Wp;
-            }
-            const bool interior = valid && hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W;
-            // destinations of this row in the output plane: itself, and up to three wrapped halo copies
-            int d0 = -1, d1 = -1, d2 = -1, d3 = -1;
-            if (interior || (valid && !P.wrap)) d0 = p;  // zero-padding planes: halo rows are written (as zeros)
-            if (P.wrap && interior) {
-                int hp2 = -1, wp2 = -1;
-                if (hp == 1) hp2 = P.H + 1; else if (hp == P.H) hp2 = 0;
-                if (wp == 1) wp2 = P.W + 1; else if (wp == P.W) wp2 = 0;
-                if (hp2 >= 0) d1 = b * plane + hp2 * P.Wp + wp;
-                if (wp2 >= 0) d2 = b * plane + hp * P.Wp + wp2;
-                if (hp2 >= 0 && wp2 >= 0) d3 = b * plane + hp2 * P.Wp + wp2;
-            }
-            if (P.out) {
-                __syncwarp();
-                reinterpret_cast<int4*>(rinfo)[lane] = make_int4(d0, d1, d2, d3);
-                __syncwarp();
-            }
-            const float* sbp = (P.sample_bias && valid) ? P.sample_bias + size_t(b) * G.n_total + n0 : nullptr;
-
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
-
-            for (int c0 = half * 32; c0 < G.n_cta; c0 += 64) {
-                const int ncols = min(32, G.n_cta - c0);  // 16 or 32
-                float v[32];
-                if (!(P.debug & 2)) {
-                    tmem_ld16(taddr + uint32_t(c0), v);
-                    if (ncols > 16) tmem_ld16(taddr + uint32_t(c0 + 16), v + 16);
-                    tmem_ld_wait();
-                }
-                if (P.debug & 1) continue;
-#pragma unroll
-                for (int i = 0; i < 32; ++i) v[i] = fmaf(v[i], P.scale, s_bias[c0 + (i < ncols ? i : 0)]);
-                if (sbp) {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        if (j * 4 < ncols) {
-                            const float4 s4 = __ldg(reinterpret_cast<const float4*>(sbp + c0) + j);
-                            v[4 * j] += s4.x; v[4 * j + 1] += s4.y; v[4 * j + 2] += s4.z; v[4 * j + 3] += s4.w;
-                        }
-                    }
-                }
-                if (interior && P.add) {
-                    const uint4* ap =
-                        reinterpret_cast<const uint4*>(P.add + size_t(p) * P.add_cs + P.add_c_off + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j * 8 < ncols) {
-                            const uint4 r = __ldg(ap + j);
-                            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&r);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[8 * j + i] += __bfloat162float(h[i]);
-                        }
-                    }
-                }
-                if (P.act == ACT_LRELU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = v[i] > 0.f ? v[i] : v[i] * P.slope;
-                } else if (P.act == ACT_SIGMOID) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
-                }
-                if (interior && P.gate) {
-                    const uint4* gp =
-                        reinterpret_cast<const uint4*>(P.gate + size_t(p) * P.gate_cs + P.gate_c_off + n0 + c0);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        if (j * 8 < ncols) {
-                            const uint4 r = __ldg(gp + j);
-                            const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&r);
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) v[8 * j + i] *= (__bfloat162float(h[i]) > 0.f) ? 1.f : P.slope;
-                        }
-                    }
-                }
-                if (P.out) {
-                    // stage this lane's row (64 B) with a 16-byte-chunk swizzle, then store whole row segments
-                    const int sw = (lane >> 1) & 3;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        uint4 o;
-                        __nv_bfloat162* w2 = reinterpret_cast<__nv_bfloat162*>(&o);
-                        if (interior) {
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) w2[i] = __floats2bfloat162_rn(v[8 * j + 2 * i], v[8 * j + 2 * i + 1]);
-                        } else {
-                            o = make_uint4(0, 0, 0, 0);
-                        }
-                        *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ sw) << 4)) = o;
-                    }
-                    __syncwarp();
-                    const int chunk = lane & 3;
-                    const int nchunks = ncols >> 3;  // 16-byte chunks per row in this group: 2 or 4
-                    if (chunk < nchunks) {
-#pragma unroll
-                        for (int it = 0; it < 4; ++it) {
-                            const int r = it * 8 + (lane >> 2);
-                            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((chunk ^ ((r >> 1) & 3)) << 4));
-                            const int4 d = reinterpret_cast<const int4*>(rinfo)[r];
-                            const size_t coff = size_t(P.out_c_off + n0 + c0 + chunk * 8);
-                            if (d.x >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.x) * P.out_cs + coff) = val;
-                            if (d.y >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.y) * P.out_cs + coff) = val;
-                            if (d.z >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.z) * P.out_cs + coff) = val;
-                            if (d.w >= 0) *reinterpret_cast<uint4*>(P.out + size_t(d.w) * P.out_cs + coff) = val;
-                        }
-                    }
-                    __syncwarp();
-                }
-                if (P.out_f32 && interior) {
-                    const size_t base = (size_t(b) * P.n_valid) * hw + size_t(hp - 1) * P.W + (wp - 1);
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        const int n = n0 + c0 + i;
-                        if (i < ncols && n < P.n_valid) {
-                            const size_t idx = base + size_t(n) * hw;
-                            P.out_f32[idx] = v[i];
-                            if (P.sample_out) {
-                                // training: z = (u < p) ; eval: z = (p > 0.5)
-                                const float z = P.uniforms ? (__ldg(P.uniforms + idx) < v[i] ? 1.f : 0.f)
-                                                           : (v[i] > 0.5f ? 1.f : 0.f);
-                                P.sample_out[idx] = z;
-                            }
-                        }
-                    }
-                }
-            }
+            if ((G.n_cta & 31) == 0)
+                igemm_epilogue_tile<32>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+            else
+                igemm_epilogue_tile<16>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);

@@ -189,21 +189,42 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
 
 // Sum the split-K partials and scatter into the caller's gradient layout:
 //   g[m*g_sm + n*g_sn + tap'*g_st] += scale * sum_split ws[split][tap][n][m]
-__global__ void wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n, float* __restrict__ g,
-                                    long long g_sm, long long g_sn, long long g_st, int flip, int m_valid,
-                                    int n_valid, float scale) {
-    const int total = 9 * n * 128;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= total) return;
-    const int m = idx & 127;
-    const int nn = (idx >> 7) % n;
-    const int tap = idx / (128 * n);
+// Block = 32 float4 columns (512 contiguous bytes of one split row) x 8 split lanes: every split lane sums the
+// splits congruent to it, the eight partial sums are combined through shared memory in a fixed order.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n,
+                                                            float* __restrict__ g, long long g_sm, long long g_sn,
+                                                            long long g_st, int flip, int m_valid, int n_valid,
+                                                            float scale) {
+    __shared__ float4 part[8][32];
+    const int total4 = 9 * n * 32;  // float4 groups per split
+    const int i4 = blockIdx.x * 32 + threadIdx.x;
+    const int lane_s = threadIdx.y;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i4 < total4) {
+        const float4* src = reinterpret_cast<const float4*>(ws) + i4;
+        for (int s = lane_s; s < splits; s += 8) {
+            const float4 a = __ldg(src + size_t(s) * total4);
+            acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+        }
+    }
+    part[lane_s][threadIdx.x] = acc;
+    __syncthreads();
+    if (lane_s != 0 || i4 >= total4) return;
+#pragma unroll
+    for (int j = 1; j < 8; ++j) {
+        const float4 a = part[j][threadIdx.x];
+        acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+    const int m = (i4 & 31) * 4;
+    const int nn = (i4 >> 5) % n;
+    const int tap = i4 / (32 * n);
     if (m >= m_valid || nn >= n_valid) return;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += __ldg(ws + size_t(s) * total + idx);
     const int gtap = flip ? 8 - tap : tap;
     float* gp = g + (long long)m * g_sm + (long long)nn * g_sn + (long long)gtap * g_st;
-    *gp += acc * scale;
+    const float r[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        if (m + j < m_valid) gp[(long long)j * g_sm] += r[j] * scale;
 }
 
 }  // namespace scm

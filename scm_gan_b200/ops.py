@@ -55,6 +55,7 @@ def transition_bwd(dz_next: Tensor, p: Tensor, a: Tensor, saved: Sequence[Tensor
 
 
 def _transition_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     z, a, wbar, bias, sigma, w6, b6, uniforms, training = inputs
     ctx.training = training
     ctx.a, ctx.sigma = a, sigma
@@ -109,6 +110,7 @@ def encoder_bwd(dz: Tensor, z: Tensor, saved: Sequence[Tensor], wbar: Sequence[T
 
 
 def _encoder_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     x, wbar, bias, sigma, w4, b4 = inputs
     ctx.wbar, ctx.sigma, ctx.w4 = list(wbar), sigma, w4
     ctx.nw = len(wbar)
@@ -147,6 +149,7 @@ def decoder_bwd(dlogits: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor
 
 
 def _decoder_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     z, w1, b1, w2, b2 = inputs
     ctx.w1, ctx.w2 = w1, w2
     ctx.save_for_backward(*output[1:])
@@ -179,6 +182,7 @@ def bce_logits(logits: Tensor, target: Tensor, mask: Tensor) -> List[Tensor]:
 
 
 def _bce_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     ctx.save_for_backward(output[1])
 
 
@@ -208,6 +212,7 @@ def reward_bwd(dr: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor) -> L
 
 
 def _reward_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     z, w1, b1, w2, b2 = inputs
     ctx.w1, ctx.w2 = w1, w2
     ctx.save_for_backward(*output[2:])
