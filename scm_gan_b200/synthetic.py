@@ -1,0 +1,62 @@
+"""Synthetic trajectory source honouring the reference's datasource contract (datasource.py:8-120,
+envs/minipacman.py:122-164): `get_trajectories(batch_size, timesteps, random_start, training)` returns numpy
+`(states [B,T,C,H,W] float, rewards [B,T,R] float, dones [B,T] bool, actions [B,T] int)`.
+
+The reference's environments (gym_minipacman, SC2, ...) cannot be installed offline; this stand-in produces frames of
+the same shapes with learnable, action-conditional dynamics on a torus (which is what Transition's circular padding
+models): a few "agent" pixels move by the chosen action, "food" pixels are static and are eaten (reward +1) when an
+agent lands on them, a "ghost" drifts and costs -1 on contact.
+"""
+import numpy as np
+
+MOVES = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1), (1, 1), (-1, -1)]  # action -> (dy, dx); extra actions reuse entries
+
+
+class MovingDots:
+    def __init__(self, channels=3, height=15, width=19, num_actions=5, num_rewards=2, seed=0, p_done=0.0):
+        self.conv_input_channels = channels
+        self.conv_output_channels = channels
+        self.binary_input_channels = num_actions
+        self.scalar_output_channels = num_rewards
+        self.height, self.width = height, width
+        self.rng = np.random.RandomState(seed)
+        self.p_done = p_done
+
+    def make_env(self):
+        raise NotImplementedError("synthetic source: trajectories only")
+
+    def convert_frame(self, state, **kwargs):
+        return state
+
+    def get_trajectories(self, batch_size=32, timesteps=10, random_start=True, training=True):
+        C, H, W = self.conv_input_channels, self.height, self.width
+        A, R = self.binary_input_channels, self.scalar_output_channels
+        rng = self.rng
+        states = np.zeros((batch_size, timesteps, C, H, W), dtype=np.float32)
+        rewards = np.zeros((batch_size, timesteps, R), dtype=np.float32)
+        dones = np.zeros((batch_size, timesteps), dtype=bool)
+        actions = rng.randint(A, size=(batch_size, timesteps))
+        for b in range(batch_size):
+            agent = np.array([rng.randint(H), rng.randint(W)])
+            ghost = np.array([rng.randint(H), rng.randint(W)])
+            gdir = np.array(MOVES[1 + rng.randint(4)])
+            food = rng.rand(H, W) < 0.08
+            done = False
+            for t in range(timesteps):
+                a = actions[b, t]
+                agent = (agent + np.array(MOVES[a % len(MOVES)])) % (H, W)
+                ghost = (ghost + gdir) % (H, W)
+                if food[agent[0], agent[1]]:
+                    food[agent[0], agent[1]] = False
+                    rewards[b, t, 0] = 1.0
+                if R > 1 and (agent == ghost).all():
+                    rewards[b, t, 1] = -1.0
+                states[b, t, 0, agent[0], agent[1]] = 1.0
+                states[b, t, 1 % C][food] = 1.0
+                states[b, t, 2 % C, ghost[0], ghost[1]] = 1.0
+                if C > 3:
+                    states[b, t, 3, :, :] = 0.0
+                if not done and rng.rand() < self.p_done:
+                    done = True
+                dones[b, t] = done
+        return states, rewards, dones, actions
