@@ -41,6 +41,15 @@ def algorithmic_flops_per_iter(C, H, W, A, R, B, T, t_cf):
     return 3 * B * (f_enc + (T + t_cf) * f_tr + T * (f_dec + f_rew))
 
 
+def read_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (or None)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f)["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
 def read_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -333,9 +342,9 @@ def main():
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_kernel<64> (128->128 ch, one Transition conv)",
+            "roofline": {"bound": "tensor", "kernel": "conv3x3_igemm_v3_kernel<64,9> (CTA-pair tcgen05 conv, 128->128 ch, one Transition conv)",
                          "achieved": achieved, "peak": peaks["bf16_burst"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["bf16_burst"], "traffic": None,
+                         "frac": achieved / peaks["bf16_burst"], "traffic": read_traffic(),
                          "peak_source": peaks["source"] + " (burst: kernel timed alone)",
                          "kernel_ms": k_ms, "kernel_flops": k_flops},
             "step_tflops": {"achieved": step_tflops / world, "peak": peaks["bf16_sustained"],

@@ -5,7 +5,7 @@
 using namespace scm;
 
 template <int PAIR>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int row_shift, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int row_shift, long long* out, int mn_major = 0) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -17,16 +17,18 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int n, int iters, int row_
     tc_fence_before(); __syncthreads(); if (PAIR) cluster_sync_all(); tc_fence_after();
     const uint32_t tmem = slot;
     if (warp == 0 && rank == 0) {
-        const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, n, 1, 0, 0);
-        const uint64_t a0 = make_smem_desc(smem_u32(smem) + row_shift * 128, 16, 1024, kLayoutSw128);
-        const uint64_t b0 = make_smem_desc(smem_u32(smem) + 64 * 1024, 16, 1024, kLayoutSw128);
+        const uint32_t idesc = make_idesc_f16(PAIR ? 256 : 128, n, 1, mn_major, mn_major);
+        // MN-major: two 64-channel atoms 16 KB apart (LBO), 8-pixel groups 1024 B apart (SBO)
+        const uint64_t a0 = make_smem_desc(smem_u32(smem) + row_shift * 128, mn_major ? 16384 : 16, 1024, kLayoutSw128);
+        const uint64_t b0 = make_smem_desc(smem_u32(smem) + 64 * 1024, mn_major ? 16384 : 16, 1024, kLayoutSw128);
         long long t0 = clock64();
         if (elect_one()) {
             for (int i = 0; i < iters; ++i) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
-                    if (PAIR) umma_f16_pair(tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);
-                    else umma_f16(tmem, a0 + 2 * k, b0 + 2 * k, idesc, 1);
+                    const int adv = mn_major ? 128 * k : 2 * k;  // 16 pixel rows (2048 B) vs 32 B along K
+                    if (PAIR) umma_f16_pair(tmem, a0 + adv, b0 + adv, idesc, 1);
+                    else umma_f16(tmem, a0 + adv, b0 + adv, idesc, 1);
                 }
             }
             if (PAIR) umma_commit_pair(&bar, 1); else umma_commit(&bar);
@@ -54,13 +56,20 @@ int main() {
                 printf("1-CTA grid=%3d N=%3d shift=%d: %7.1f cycles/MMA (%s)\n", grid, n, shift, double(out[0]) / (4.0 * iters), cudaGetErrorString(e));
             }
         }
+        for (int n : {16, 64, 128}) {
+            for (int shift : {0, 1}) {
+                rate_kernel<0><<<grid, 128, smem>>>(n, iters, shift, out, 1);
+                cudaError_t e = cudaDeviceSynchronize();
+                printf("1-CTA MN-major grid=%3d N=%3d shift=%d: %7.1f cycles/MMA (%s)\n", grid, n, shift, double(out[0]) / (4.0 * iters), cudaGetErrorString(e));
+            }
+        }
         for (int n : {128, 256}) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(grid == 1 ? 2 : 148); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = smem;
             cudaLaunchAttribute at[1]; at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim = {2, 1, 1};
             cfg.attrs = at; cfg.numAttrs = 1;
             int shift = 0;
-            cudaLaunchKernelEx(&cfg, rate_kernel<1>, n, iters, shift, out);
+            cudaLaunchKernelEx(&cfg, rate_kernel<1>, n, iters, shift, out, 0);
             cudaError_t e = cudaDeviceSynchronize();
             printf("2-CTA grid=%3d N=%3d (M=256): %7.1f cycles/MMA (%s)\n", cfg.gridDim.x, n, double(out[0]) / (4.0 * iters), cudaGetErrorString(e));
         }

@@ -5,6 +5,7 @@
 #include "conv_igemm_v2.cuh"
 #include "conv_igemm_v3.cuh"
 #include "conv_wgrad.cuh"
+#include "conv_wgrad_v2.cuh"
 #include "elementwise.cuh"
 #include "host_util.cuh"
 
@@ -355,6 +356,72 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     return CK == 64 ? launch_igemm<64>(ta, tb, P, st) : launch_igemm<16>(ta, tb, P, st);
 }
 
+// Second-generation wgrad (conv_wgrad_v2.cuh): P = dY (interior view, 128 channels), Q = X (padded view, n channels),
+// W % 16 == 0, workspace required.  Returns 1 when the shape does not qualify.
+static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_c_off, const void* qp, int q_cs,
+                           int q_c_off, int n, int flip, float scale, float* g, long long g_sm, long long g_sn,
+                           long long g_st, int m_valid, int n_valid, float* ws, long long ws_bytes, cudaStream_t st) {
+    static const char* off = getenv("SCMGAN_WGRAD_V1");
+    if (off && atoi(off)) return 1;
+    if (!ws || W % 16 != 0 || W > 256 || n > 128 || n % 16 != 0) return 1;
+    const int Hp = H + 2, Wp = W + 2;
+    const int BH = std::max(1, std::min(128 / W, H));
+    const int KP = W * BH;
+    const int q_aw = (n % 64 == 0) ? 64 : (n % 32 == 0 ? 32 : 16);
+    const int q_atoms = n / q_aw;
+    const int wq = (Wp + 7) & ~7;
+    if (wq > 256) return 1;
+    const int q_atom_bytes = (wq * q_aw * 2 + 1023) & ~1023;
+    const int stage_bytes = 2 * KP * 128 + BH * q_atoms * q_atom_bytes;
+    const int stages = std::min(4, (kSmemMax - 2048) / stage_bytes);
+    if (stages < 2) return 1;
+    WgradV2Params P;
+    memset(&P, 0, sizeof(P));
+    P.B = B; P.W = W; P.BH = BH;
+    P.nby = (H + BH - 1) / BH;
+    P.num_kblocks = B * P.nby;
+    int splits = std::max(1, std::min(P.num_kblocks / 4, std::max(1, num_sms() / 3)));
+    P.kb_per_cta = (P.num_kblocks + splits - 1) / splits;
+    splits = (P.num_kblocks + P.kb_per_cta - 1) / P.kb_per_cta;
+    if ((long long)splits * 9 * n * 128 * 4 > ws_bytes) return 1;
+    P.n = n; P.q_aw = q_aw; P.wq = wq; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.ws = ws;
+    {
+        static const char* dbg = getenv("SCMGAN_DEBUG");
+        P.debug = dbg ? (atoi(dbg) & (8 | 16)) : 0;
+    }
+    CUtensorMap tp, tq;
+    {
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(pp) + (size_t(Wp) + 1) * p_cs;
+        uint64_t dims[4] = {uint64_t(p_cs), uint64_t(W), uint64_t(H), uint64_t(B)};
+        uint64_t str[3] = {uint64_t(p_cs) * 2, uint64_t(Wp) * p_cs * 2, uint64_t(Hp) * Wp * p_cs * 2};
+        uint32_t box[4] = {64, uint32_t(W), uint32_t(BH), 1};
+        int rc = encode_tmap_bf16(&tp, bp, 4, dims, str, box, 128);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[4] = {uint64_t(q_cs), uint64_t(Wp), uint64_t(Hp), uint64_t(B)};
+        uint64_t str[3] = {uint64_t(q_cs) * 2, uint64_t(Wp) * q_cs * 2, uint64_t(Hp) * Wp * q_cs * 2};
+        uint32_t box[4] = {uint32_t(q_aw), uint32_t(wq), 1, 1};
+        int rc = encode_tmap_bf16(&tq, qp, 4, dims, str, box, q_aw * 2);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr_set = true;
+    }
+    const int smem = stages * stage_bytes + 1024 + 256;
+    conv3x3_wgrad_v2_kernel<<<dim3(splits, 3), kWgradThreads, smem, st>>>(tp, tq, P, stages);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    const int total = 9 * n * 32;
+    wgrad_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
+                                                                   n_valid, scale);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 // one wgrad launch: P = 128 channels of `pp` (view per p_interior), Q = n channels of `qp`
 static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_off, bool p_interior, const void* qp,
                         int q_cs, int q_c_off, int n, int q_sign, int flip, float scale, float* g, long long g_sm,
@@ -523,6 +590,15 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
                 const int n = std::min(128, d->cin - c0);
                 const int nv = std::min(n, d->ci_valid - c0);
                 if (nv <= 0) break;
+                {
+                    const int rc2 = wgrad_launch_v2(d->B, d->H, d->W, d->dy, d->dy_cs, d->dy_c_off + m0, d->x, d->x_cs,
+                                                    d->x_c_off + c0, n, d->flip, d->scale,
+                                                    d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci,
+                                                    d->g_s_tap, std::min(128, d->co_valid - m0), nv,
+                                                    (float*)d->workspace, d->workspace_bytes, st);
+                    if (rc2 < 0) return rc2;
+                    if (rc2 == 0) continue;
+                }
                 int rc = wgrad_launch(d->B, d->H, d->W, d->dy, d->dy_cs, d->dy_c_off + m0, true, d->x, d->x_cs,
                                       d->x_c_off + c0, n, +1, d->flip, d->scale,
                                       d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci, d->g_s_tap,

@@ -193,6 +193,10 @@ WGRAD_CASES = [
     (3, 15, 19, 256, 16, True),
     (2, 16, 16, 128, 16, False),
     (2, 15, 19, 128, 48, False),
+    # widths that are multiples of 16 take the row-shifted-reuse kernel (conv_wgrad_v2.cuh)
+    (2, 16, 16, 16, 128, False),
+    (2, 12, 32, 256, 128, True),
+    (3, 10, 48, 64, 128, True),
 ]
 
 
