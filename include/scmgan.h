@@ -112,6 +112,7 @@ typedef struct {
     void* workspace; /* optional split-K scratch (scmgan_wgrad_workspace_bytes()); with it the reduction is a second,
                         deterministic kernel instead of fp32 atomics */
     long long workspace_bytes;
+    float* db; /* optional bias gradient: db[co] += sum over interior pixels of dy[p][co] (co < cout) */
 } scmgan_wgrad_desc;
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* desc_host, scmgan_stream_t stream);
 long long scmgan_wgrad_workspace_bytes(void);

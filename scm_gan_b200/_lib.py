@@ -39,7 +39,7 @@ class WgradDesc(C.Structure):
                 ("x", C.c_void_p), ("x_cs", C.c_int), ("x_c_off", C.c_int), ("cin", C.c_int),
                 ("g", C.c_void_p), ("g_s_co", C.c_longlong), ("g_s_ci", C.c_longlong), ("g_s_tap", C.c_longlong),
                 ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("db", C.c_void_p)]
 
 
 class SnLayer(C.Structure):

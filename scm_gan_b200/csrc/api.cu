@@ -360,7 +360,8 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
 // W % 16 == 0, workspace required.  Returns 1 when the shape does not qualify.
 static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_c_off, const void* qp, int q_cs,
                            int q_c_off, int n, int flip, float scale, float* g, long long g_sm, long long g_sn,
-                           long long g_st, int m_valid, int n_valid, float* ws, long long ws_bytes, cudaStream_t st) {
+                           long long g_st, int m_valid, int n_valid, float* ws, long long ws_bytes, float* db,
+                           cudaStream_t st) {
     static const char* off = getenv("SCMGAN_WGRAD_V1");
     if (off && atoi(off)) return 1;
     if (!ws || W % 16 != 0 || W > 256 || n > 128 || n % 16 != 0) return 1;
@@ -383,8 +384,11 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     int splits = std::max(1, std::min(P.num_kblocks / 4, std::max(1, num_sms() / 3)));
     P.kb_per_cta = (P.num_kblocks + splits - 1) / splits;
     splits = (P.num_kblocks + P.kb_per_cta - 1) / P.kb_per_cta;
-    if ((long long)splits * 9 * n * 128 * 4 > ws_bytes) return 1;
+    const long long main_floats = (long long)splits * 9 * n * 128;
+    if ((main_floats + (long long)splits * 128) * 4 > ws_bytes) return 1;
+    if (db && 3 * n + 16 > 512) return 1;
     P.n = n; P.q_aw = q_aw; P.wq = wq; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.ws = ws;
+    P.ws_bias = db ? ws + main_floats : nullptr;
     {
         static const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? (atoi(dbg) & (8 | 16)) : 0;
@@ -410,7 +414,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
         SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
         attr_set = true;
     }
-    const int smem = stages * stage_bytes + 1024 + 256;
+    const int smem = stages * stage_bytes + 1024 + 1024;
     conv3x3_wgrad_v2_kernel<<<dim3(splits, 3), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
@@ -419,6 +423,11 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
                                                                    n_valid, scale);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
+    if (db) {
+        wgrad_bias_reduce_kernel<<<1, 128, 0, st>>>(P.ws_bias, splits, db, m_valid, 1.0f);
+        SCM_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
     return SCM_OK;
 }
 
@@ -583,9 +592,16 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
                 "wgrad: bad channel strides");
     SCM_REQUIRE(d->dy_c_off + d->cout <= d->dy_cs && d->x_c_off + d->cin <= d->x_cs, "wgrad: channel window");
     cudaStream_t st = (cudaStream_t)stream;
+    // bias gradient (optional): folded into the first v2 launch of every 128-channel output block, otherwise a
+    // separate interior column sum over the gradient plane
+    auto bias_fallback = [&](int m0, int mcount) -> int {
+        const int n8 = (mcount + 7) & ~7;
+        return scmgan_plane_colsum(d->dy, d->dy_cs, d->dy_c_off + m0, n8, d->B, d->H, d->W, nullptr, d->db + m0, stream);
+    };
     if (d->cout % 128 == 0) {
         for (int m0 = 0; m0 < d->cout; m0 += 128) {
             if (m0 >= d->co_valid) break;
+            bool bias_done = (d->db == nullptr);
             for (int c0 = 0; c0 < d->cin; c0 += 128) {
                 const int n = std::min(128, d->cin - c0);
                 const int nv = std::min(n, d->ci_valid - c0);
@@ -595,15 +611,20 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
                                                     d->x_c_off + c0, n, d->flip, d->scale,
                                                     d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci,
                                                     d->g_s_tap, std::min(128, d->co_valid - m0), nv,
-                                                    (float*)d->workspace, d->workspace_bytes, st);
+                                                    (float*)d->workspace, d->workspace_bytes,
+                                                    bias_done ? nullptr : d->db + m0, st);
                     if (rc2 < 0) return rc2;
-                    if (rc2 == 0) continue;
+                    if (rc2 == 0) { bias_done = true; continue; }
                 }
                 int rc = wgrad_launch(d->B, d->H, d->W, d->dy, d->dy_cs, d->dy_c_off + m0, true, d->x, d->x_cs,
                                       d->x_c_off + c0, n, +1, d->flip, d->scale,
                                       d->g + m0 * d->g_s_co + c0 * d->g_s_ci, d->g_s_co, d->g_s_ci, d->g_s_tap,
                                       std::min(128, d->co_valid - m0), nv, (float*)d->workspace, d->workspace_bytes,
                                       st);
+                if (rc) return rc;
+            }
+            if (!bias_done) {
+                int rc = bias_fallback(m0, 128);
                 if (rc) return rc;
             }
         }
@@ -619,6 +640,10 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
                                   st);
             if (rc) return rc;
         }
+        if (d->db) {
+            int rc = bias_fallback(0, d->cout);
+            if (rc) return rc;
+        }
         return SCM_OK;
     }
     set_error("wgrad: one of cout (%d) / cin (%d) must be a multiple of 128", d->cout, d->cin);
@@ -627,7 +652,7 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
 
 long long scmgan_wgrad_workspace_bytes(void) {
     // upper bound over all shapes: (#CTAs of one launch) x (taps per CTA group) x 128 x n floats, n <= 128
-    return (long long)(num_sms() + 8) * 9 * 128 * 128 * 4 / 3 + (1 << 20);
+    return (long long)(num_sms() + 8) * 9 * 128 * 128 * 4 / 3 + (2 << 20);
 }
 
 int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int H, int W, float* S, float* db,

@@ -227,4 +227,14 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
         if (m + j < m_valid) gp[(long long)j * g_sm] += r[j] * scale;
 }
 
+// db[m] += scale * sum_split ws_bias[split][m]   (bias gradient partials of conv_wgrad_v2.cuh)
+__global__ void wgrad_bias_reduce_kernel(const float* __restrict__ ws_bias, int splits, float* __restrict__ db,
+                                         int m_valid, float scale) {
+    const int m = threadIdx.x;
+    if (m >= m_valid) return;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += __ldg(ws_bias + size_t(s) * 128 + m);
+    db[m] += acc * scale;
+}
+
 }  // namespace scm

@@ -7,6 +7,10 @@
 // UMMA descriptor start address advances by one 128-byte pixel row; swizzle is applied on absolute addresses, see
 // conv_igemm_v2.cuh).  A stage covers BH image rows (KP = W*BH pixels) so that ~24 MMAs amortise one barrier
 // round trip.  P = dY through the interior-view map (zero outside the H x W interior), Q = X through the padded view.
+//
+// Bias gradient for free: db[m] = sum_p dY[p][m] is one more GEMM column, dY x ones.  The CTAs of the middle filter row
+// issue one extra N=16 MMA per K step against a constant all-ones tile; the kernel is bound by the L2->SM fabric, not
+// by the tensor pipe, so these MMAs are hidden, and a separate pass over the 36 MB gradient plane disappears.
 #pragma once
 #include "conv_wgrad.cuh"
 
@@ -23,6 +27,7 @@ struct WgradV2Params {
     int wq;           // rows of one Q row tile (>= W + 2, multiple of 8)
     int p_c_off, q_c_off;
     float* ws;        // split-K partials [split][tap][n][128]
+    float* ws_bias;   // optional bias-gradient partials [split][128] (nullptr: not requested)
     int debug;
 };
 
@@ -44,10 +49,14 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
     uint64_t* empty_bar = bars + 8;
     uint64_t* acc_full = bars + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars + 32);  // 512 B: 16 pixels x 16 channels of bf16 1.0
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ky = blockIdx.y;  // this CTA's filter row: taps ky*3 + {0,1,2}
+    const bool do_bias = (P.ws_bias != nullptr) && ky == 1;
+    if (do_bias && threadIdx.x < 128) reinterpret_cast<uint32_t*>(s_ones)[threadIdx.x] = 0x3F803F80u;
+    if (do_bias) fence_proxy_async_smem();  // generic-proxy writes must be visible to the tensor core (async proxy)
     const int kb_begin = blockIdx.x * P.kb_per_cta;
     const int kb_end = min(P.num_kblocks, kb_begin + P.kb_per_cta);
     const int nkb = max(0, kb_end - kb_begin);
@@ -104,6 +113,9 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
             const uint32_t q_tile16 = uint32_t(q_tile_bytes) >> 4;
             const uint32_t q_row16 = uint32_t(q_row_bytes) >> 4;
             const int ksteps = P.W / 16;
+            const uint32_t idesc_b = make_idesc_f16(128, 16, 1, 1, 1);
+            const uint64_t ones_desc = make_smem_desc(smem_u32(s_ones), 512, 256, kLayoutSw32);
+            const uint32_t tmem_b = tmem_base + uint32_t(3 * P.n);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nkb; ++i) {
@@ -123,6 +135,10 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
                                 umma_f16(tmem_d, aj + uint64_t(k * 128), bj + uint64_t(uint32_t(k * 16) * q_row16), idesc,
                                          (i > 0 || j > 0 || k > 0) ? 1u : 0u);
                         }
+                    }
+                    if (do_bias) {
+                        for (int jk = 0; jk < P.BH * ksteps; ++jk)  // pixel rows are contiguous across image rows
+                            umma_f16(tmem_b, a_st + uint64_t(jk * 128), ones_desc, idesc_b, (i > 0 || jk > 0) ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[stage]);
                 }
@@ -147,6 +163,12 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
 #pragma unroll
                     for (int i = 0; i < 16; ++i) wp[size_t(i) * 128] = v[i];
                 }
+            }
+            if (do_bias) {
+                float v[16];
+                tmem_ld16(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(3 * P.n), v);
+                tmem_ld_wait();
+                P.ws_bias[size_t(blockIdx.x) * 128 + m] = v[0];
             }
         }
     }

@@ -144,22 +144,18 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6):
     d1part = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d6, wd[6], B, H, W, cin=Lp, out=d5, gate=buf6, gate_c_off=0, **dg)        # d act5 -> d pre5
     K.conv3x3(d6, wd[7], B, H, W, cin=Lp, out=d1part, **dg)                             # d skip1 (partial)
-    K.wgrad(d5, buf5, G[4], B, H, W, cout=HID, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9)
-    K.plane_colsum(d5, 0, HID, B, H, W, db=db[4])
+    K.wgrad(d5, buf5, G[4], B, H, W, cout=HID, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9, db=db[4])
     d4 = K.new_plane(B, H, W, HID, dev)
     d2part = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d5, wd[4], B, H, W, cin=HID, out=d4, gate=buf5, gate_c_off=0, **dg)       # d act4 -> d pre4
     K.conv3x3(d5, wd[5], B, H, W, cin=HID, out=d2part, **dg)                            # d skip2 (partial)
-    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
-    K.plane_colsum(d4, 0, HID, B, H, W, db=db[3])
+    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[3])
     d3 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=d3, gate=act3, **dg)
-    K.wgrad(d3, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9)
-    K.plane_colsum(d3, 0, HID, B, H, W, db=db[2])
+    K.wgrad(d3, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
     d2 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d3, wd[2], B, H, W, cin=HID, out=d2, add=d2part, gate=buf5, gate_c_off=HID, **dg)
-    K.wgrad(d2, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9)
-    K.plane_colsum(d2, 0, HID, B, H, W, db=db[1])
+    K.wgrad(d2, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd[1], B, H, W, cin=HID, out=d1, add=d1part, gate=buf6, gate_c_off=HID, **dg)
     c1 = L + A
@@ -226,14 +222,11 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4):
     K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
     d3, d2, d1 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
     K.conv3x3(d4, wd[2], B, H, W, cin=Lp, out=d3, gate=a3, dgrad=True)
-    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
-    K.plane_colsum(d3, 0, HID, B, H, W, db=db[2])
+    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
     K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
-    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9)
-    K.plane_colsum(d2, 0, HID, B, H, W, db=db[1])
+    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
     K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
-    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin)
-    K.plane_colsum(d1, 0, HID, B, H, W, db=db[0])
+    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0])
     dwbar = [torch.empty_like(w) for w in wbar]
     K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1], dwbar[i]) for i in range(3)])
     return dwbar, [d.clone() for d in db], G[3].clone(), db4[:L].clone()
@@ -289,8 +282,8 @@ def decoder_backward(dlogits, saved, w1, w2):
     K.plane_colsum(d2, 0, cop, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=cop, out=d1, gate=hidp, dgrad=True)
-    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L)
-    K.plane_colsum(d1, 0, HID, B, H, W, db=db1)
+    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L,
+            db=db1)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True)
     return dz, g1.clone(), db1[:hid].clone(), g2.clone(), db2[:co].clone()
@@ -349,8 +342,7 @@ def reward_backward(dr, saved, w1, w2):
     K.plane_colsum(d2, 0, 16, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=16, out=d1, gate=hidp, dgrad=True)
-    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L)
-    K.plane_colsum(d1, 0, HID, B, H, W, db=db1)
+    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True)
     return dz, g1.clone(), db1[:RHID].clone(), g2.clone(), db2[:co].clone()

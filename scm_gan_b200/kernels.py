@@ -95,7 +95,7 @@ def _wgrad_workspace(device):
 
 
 def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
-          co_valid=None, ci_valid=None, scale=1.0):
+          co_valid=None, ci_valid=None, scale=1.0, db=None):
     d = L.WgradDesc()
     d.B, d.H, d.W = B, H, W
     d.dy, d.dy_cs, d.dy_c_off, d.cout = dy_plane.data_ptr(), dy_plane.shape[3], dy_c_off, cout
@@ -107,6 +107,7 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
     d.scale = scale
     ws = _wgrad_workspace(g.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    d.db = L.ptr(db)  # bias gradient accumulated alongside (zero-initialised by the caller)
     L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
 
 

@@ -211,11 +211,14 @@ def test_wgrad(case):
     xp = make_plane(x, Ci, 0, wrap)
     dyp = make_plane(dy, Co, 0, wrap)  # halo deliberately non-zero in wrap mode: must be ignored
     g = torch.zeros(Co, Ci, 3, 3, device=DEV)
-    K.wgrad(dyp, xp, g, B, H, W, cout=Co, cin=Ci, g_s_co=Ci * 9, g_s_ci=9)
+    db = torch.zeros(Co, device=DEV)
+    K.wgrad(dyp, xp, g, B, H, W, cout=Co, cin=Ci, g_s_co=Ci * 9, g_s_ci=9, db=db)
     w = torch.zeros(Co, Ci, 3, 3, device=DEV, requires_grad=True)
     y = ref_conv(x, w, wrap)
     (gw,) = torch.autograd.grad(y, w, dy)
     assert report(f"wgrad {case}", g, gw, 1e-4)
+    # fused bias gradient (all-ones GEMM column in the v2 kernel, column-sum fallback otherwise)
+    assert report(f"wgrad bias {case}", db, dy.sum((0, 2, 3)), 1e-4)
 
 
 def test_spectral_norm_fwd_bwd():
