@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--workload", default="pong64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (reference default, main.py:31)")
     ap.add_argument("--horizon", type=int, default=10, help="prediction horizon Hn (T = Hn - 2 rollout steps)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    ap.add_argument("--cpu-sample-batch", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cf-phase", type=int, default=0,
@@ -354,10 +354,12 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:
             sb = args.cpu_sample_batch
-            fps, ms, cores = cpu_reference_run(args.workload, Hn, sb, 2, 1)
+            n_it = 8
+            fps, ms, cores = cpu_reference_run(args.workload, Hn, sb, n_it, 1)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",
-                                   "sample": f"oracle port of the reference step, batch {sb}, same frame shape/horizon, "
-                                             f"2 timed iterations ({ms:.0f} ms each)"}
+                                   "sample": f"oracle port of the reference step (fp32 torch CPU, all host threads), batch "
+                                             f"{sb} of the same frame shape/horizon, {n_it} timed iterations "
+                                             f"({ms:.0f} ms each) after 1 warm-up"}
         print(json.dumps(out), flush=True)
     if world > 1:
         # captured CUDA graphs keep references into the NCCL communicator; tearing the process group down in that
