@@ -231,7 +231,12 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("SCMGAN_NCCL_DEBUG", "WARN")  # keep stdout to the one JSON line
+        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at any NCCL_DEBUG level
+        if "SCMGAN_NCCL_DEBUG" in os.environ:
+            os.environ["NCCL_DEBUG"] = os.environ["SCMGAN_NCCL_DEBUG"]
+        else:
+            os.environ.pop("NCCL_DEBUG", None)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as ge
     if rank == 0:

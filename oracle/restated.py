@@ -273,8 +273,10 @@ def prediction_horizon(train_iter, train_iters, hmin=3, hmax=10):
 
 def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta, reward_coef=1e-3,
                     uniforms=None, truncate_bptt=False, enable_disentanglement=False, enable_action_control=False,
-                    cf_now=False, counterfactual_horizon=1, cf_indices=None, cf_perm=None, latent_dim=16):
-    """reference main.py:155-283 (loss construction of one training iteration; latent overshooting omitted).
+                    cf_now=False, counterfactual_horizon=1, cf_indices=None, cf_perm=None, latent_dim=16,
+                    latent_overshooting=False, td_lambda=0.9):
+    """reference main.py:155-283 (loss construction of one training iteration, incl. the optional latent
+    overshooting of main.py:217-234).
 
     nets: dict with reference-format state_dicts 'encoder', 'transition', 'decoder', 'reward_predictor'
           (tensors with requires_grad where a gradient is wanted; SN u/v are advanced in place).
@@ -298,6 +300,8 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
     z_orig = z.clone()  # main.py:163
     active_mask = torch.ones(bsz, dtype=states.dtype, device=states.device)
     loss = 0
+    lo_loss = 0
+    lo_z_set = {}
     terms = {}
     for t in range(1, hn - 1):  # main.py:177
         active_mask = active_mask * (1 - dones[:, t])
@@ -313,6 +317,18 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
         terms[f"Reconstruction t={t}"] = rec_loss
         loss = loss + rec_loss
         z = trans(z, eye[actions[:, t]])  # main.py:206-207
+
+        if latent_overshooting:  # main.py:217-230
+            lo_z_set[t] = encoder_forward(nets["encoder"], states[:, t - 1:t + 2])
+            for t_left in range(1, t):
+                lo_z_set[t_left] = trans(lo_z_set[t_left], eye[actions[:, t - 1]])
+            for t_a in range(2, t - 1):
+                lo_loss_batch = latent_state_loss(lo_z_set[t].detach(), lo_z_set[t_a])
+                lo_loss = lo_loss + td_lambda * torch.mean(lo_loss_batch * active_mask)
+
+    if latent_overshooting:  # main.py:232-234
+        terms["LO total"] = lo_loss
+        loss = loss + theta * lo_loss
 
     if enable_disentanglement and cf_now:  # main.py:242-262
         z_cf_a = z.clone()

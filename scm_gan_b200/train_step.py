@@ -46,7 +46,8 @@ def build_nets(color_channels, num_actions, num_rewards, latent_dim=16, seed=Non
 
 def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e-3, truncate_bptt=False,
                  enable_disentanglement=False, enable_action_control=False, cf_now=False, counterfactual_horizon=1,
-                 cf_indices=None, cf_perm=None, uniforms=None, collect=None):
+                 cf_indices=None, cf_perm=None, uniforms=None, collect=None, latent_overshooting=False,
+                 td_lambda=0.9):
     """Loss of one iteration (reference main.py:155-283).  All arguments are device tensors.
 
     states [B,Hn,C,H,W] f32, rewards [B,Hn,R] f32, dones [B,Hn] f32, actions [B,Hn] int64.
@@ -69,6 +70,8 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     # active_mask_t = prod_{s<=t} (1 - done_s)   (main.py:178)
     masks = torch.cumprod(1.0 - dones[:, 1:], dim=1)
     loss = torch.zeros((), dtype=torch.float32, device=states.device)
+    lo_loss = torch.zeros((), dtype=torch.float32, device=states.device)
+    lo_z = {}
     for t in range(1, Hn - 1):
         mask = masks[:, t - 1]
         expected = rew(z)
@@ -82,7 +85,19 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
             collect[f"Rd Loss t={t}"] = rd
             collect[f"Reconstruction t={t}"] = rec
         z = step(z, actions[:, t])
+
+        if latent_overshooting:  # Hafner et al., reference main.py:217-230
+            lo_z[t] = enc(states[:, t - 1:t + 2])
+            for t_left in range(1, t):
+                lo_z[t_left] = step(lo_z[t_left], actions[:, t - 1])
+            for t_a in range(2, t - 1):
+                lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
+                lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
     mask = masks[:, Hn - 3] if Hn > 2 else torch.ones(B, device=states.device)
+    if latent_overshooting:  # main.py:232-234
+        loss = loss + theta * lo_loss
+        if collect is not None:
+            collect["LO total"] = lo_loss
 
     if enable_disentanglement and cf_now:  # main.py:242-262
         z_cf_a = z.clone()
@@ -122,12 +137,14 @@ class Trainer:
 
     NET_ORDER = ("reward_predictor", "encoder", "decoder", "transition")  # opt_pred first (main.py:292-296)
 
-    def __init__(self, nets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, reward_coef=1e-3, loss_kwargs=None):
+    def __init__(self, nets, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, reward_coef=1e-3, loss_kwargs=None,
+                 finetune_reward=False):
         from . import kernels as K
         self.K = K
         self.nets = nets
         self.lr, self.betas, self.eps = lr, betas, eps
         self.reward_coef = reward_coef
+        self.finetune_reward = finetune_reward  # --finetune-reward: only opt_pred steps (main.py:292-296)
         self.loss_kwargs = dict(loss_kwargs or {})
         self.groups = []  # (param, clip)
         self.net_of = []  # index of the owning network (= of the reference's per-network Adam instance)
@@ -208,6 +225,9 @@ class Trainer:
         loss.backward()
         if self.sync is not None:
             self.sync.finish()
+        if self.finetune_reward:
+            profile = {id(p): c for (p, _), ni in zip(self.groups, self.net_of)
+                       if self.NET_ORDER[ni] == "reward_predictor" and id(p) in profile for c in [profile[id(p)]]}
         live = sorted({ni for (p, _), ni in zip(self.groups, self.net_of) if id(p) in profile})
         for ni in live:
             self.step_dev[ni:ni + 1] += 1.0

@@ -269,3 +269,43 @@ def test_reference_main_loop_runs_on_dropin_modules():
         losses.append(loss.item())
     print("losses", losses)
     assert all(torch.isfinite(torch.tensor(losses))) and losses[-1] < losses[0]
+
+
+def test_latent_overshooting_and_truncated_bptt_vs_oracle():
+    """Optional flags of the reference step: --latent-overshooting (main.py:217-234) and --truncate-bptt (192-193)."""
+    _setup()
+    from scm_gan_b200.train_step import rollout_loss
+    from oracle import restated as R
+    cfg = load("minipacman")["config"]
+    # horizon 7: the overshooting loss only has terms from t = 4 on (range(2, t - 1), main.py:225)
+    st, rw, dn, ac = R.synthetic_batch(2, 7, cfg["C"], cfg["H"], cfg["W"], cfg["A"], cfg["R"], seed=77)
+    states, rewards, dones = st.to(DEV), rw.to(DEV), dn.to(DEV)
+    actions = torch.as_tensor(ac).to(DEV)
+    for flags in (dict(latent_overshooting=True, td_lambda=0.9), dict(truncate_bptt=True)):
+        nets = build(cfg)
+        for n in nets.values():
+            n.train()
+        gen = torch.Generator(device=DEV).manual_seed(11)
+        used = []
+        onets = oracle_nets(nets, requires_grad=True)
+        oloss, oterms, oz = R.train_step_loss(onets, states, rewards, dones, actions.cpu().numpy(),
+                                              num_actions=cfg["A"], theta=0.7, uniforms=_margin_hook(gen, 0.02, used),
+                                              **flags)
+        oloss.backward()
+        terms = {}
+        loss, z = rollout_loss(nets, states, rewards, dones, actions, theta=0.7, uniforms=copy.copy(used),
+                               collect=terms, **flags)
+        loss.backward()
+        print(flags, "loss", loss.item(), "oracle", oloss.item(), {k: v.item() for k, v in terms.items() if "LO" in k})
+        assert bool((z == oz).all())
+        assert abs(loss.item() - oloss.item()) <= 2e-3 * abs(oloss.item())
+        if "latent_overshooting" in flags:
+            assert abs(terms["LO total"].item() - oterms["LO total"].item()) <= 2e-2 * abs(oterms["LO total"].item()) + 1e-6
+            assert oterms["LO total"].item() > 0
+        for net, m in nets.items():
+            for k, p in m.named_parameters():
+                og = onets[net][k].grad
+                if not p.requires_grad or og is None or og.abs().max().item() == 0:
+                    continue
+                cos = torch.nn.functional.cosine_similarity(p.grad.flatten(), og.flatten(), dim=0).item()
+                assert cos >= 0.99 and rel(p.grad, og) <= GRAD_TOL_VS_FP32, f"{flags} {net}.{k}: cos {cos}"
