@@ -138,13 +138,13 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
     if (d->n != 128 || d->cin % 64 != 0) return 1;
     const int chunks = d->cin / CK;
     const int n_half = d->n / 2;
-    if (9 * chunks * n_half * RB > 150 * 1024) return 1;
+    const bool streamed = 9 * chunks * n_half * RB > 150 * 1024;  // e.g. Cin = 256: weights ride in the stages
     IgemmParams P = P0;
     P.num_tiles = int((rows + 255) / 256);
     IgemmV2Geom G;
     memset(&G, 0, sizeof(G));
-    G.n_total = d->n; G.n_cta = n_half; G.b_tile_bytes = n_half * RB;
-    const int b_res = (9 * chunks * G.b_tile_bytes + 1023) & ~1023;
+    G.n_total = d->n; G.n_cta = n_half; G.b_tile_bytes = n_half * RB; G.b_streamed = streamed ? 1 : 0;
+    const int b_res = streamed ? 0 : ((9 * chunks * G.b_tile_bytes + 1023) & ~1023);
     const int fixed = b_res + 1024 /*bias*/ + 256 /*barriers*/ + 1024 /*alignment slack*/;
     const int avail = kSmemMax - fixed;
     const int Wp = d->W + 2;
@@ -152,14 +152,17 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
     static const char* tpg_env = getenv("SCMGAN_TPG");
     for (int cand : {9, 3}) {
         if (tpg_env && atoi(tpg_env) == 3 && cand == 9) continue;
+        if (streamed && cand != 9) continue;
         const int extent = cand == 9 ? 2 * Wp + 2 : 2;
         const int R = 128 + extent;
         const int pieces = (R + 255) / 256;
         const int piece_rows = (((R + pieces - 1) / pieces) + 7) & ~7;
-        const int stage_bytes = (pieces * piece_rows * RB + 1023) & ~1023;
+        const int a_part = (pieces * piece_rows * RB + 1023) & ~1023;
+        const int stage_bytes = a_part + (streamed ? 9 * G.b_tile_bytes : 0);
         const int stages = std::min(6, avail / stage_bytes);
         if (stages < (cand == 9 ? 2 : 3)) continue;
         tpg = cand;
+        G.a_part_bytes = a_part;
         G.loads = pieces; G.box_rows = piece_rows; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
         for (int l = 0; l < pieces; ++l) { G.ld_row[l] = l * piece_rows; G.ld_smem[l] = l * piece_rows * RB; }
         for (int t = 0; t < cand; ++t) G.a_off16[t] = uint32_t(((t / 3) * Wp + (t % 3)) * RB) >> 4;
@@ -246,7 +249,7 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
         const int tile_bytes = 128 * RB;
         const int stage_bytes = 9 * tile_bytes;
         const int stages = std::min(6, avail / stage_bytes);
-        if (stages >= 2 && chunks == 1) {
+        if (stages >= 2 && chunks <= 4) {
             tpg = 9;
             G.loads = 9; G.box_rows = 128; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
             for (int t = 0; t < 9; ++t) {

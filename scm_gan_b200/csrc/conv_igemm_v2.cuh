@@ -27,7 +27,9 @@ struct IgemmV2Geom {
     int ld_row[9];    // per load: row delta relative to the group's first tap row
     int ld_smem[9];   // per load: byte offset inside the stage
     uint32_t a_off16[9];  // per tap of a group: operand start inside the stage, in 16-byte units
-    int a_stage_bytes;
+    int a_stage_bytes;   // bytes of one pipeline stage (activation super tile [+ streamed weight tiles])
+    int a_part_bytes;    // v3 streamed-weights mode: offset of the weight tiles inside a stage
+    int b_streamed;      // v3: 0 = weights resident for the whole kernel, 1 = the chunk's 9 weight tiles ride in each stage
     int b_tile_bytes;    // n_cta * row bytes
     int num_stages;
     int tiles_stride;    // == gridDim.x

@@ -27,7 +27,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int chunks = P.cin_chunks;
-    const int b_res_bytes = 9 * chunks * G.b_tile_bytes;
+    const int b_res_bytes = G.b_streamed ? 0 : 9 * chunks * G.b_tile_bytes;
     uint8_t* s_b = smem;
     uint8_t* s_a = smem + ((b_res_bytes + 1023) & ~1023);
     float* s_bias = reinterpret_cast<float*>(s_a + size_t(G.num_stages) * G.a_stage_bytes);  // [256]
@@ -78,7 +78,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 
     if (warp == 0) {
         // ------------------------------ TMA producer (both CTAs) ------------------------------
-        if (elect_one()) {
+        if (!G.b_streamed && elect_one()) {
             // resident weights: this CTA's N half of every [tap][chunk] tile
             const uint32_t bytes = uint32_t(9 * chunks * G.n_cta * RB);
             if (rank == 0) mbar_arrive_expect_tx(b_full, 2 * bytes); else mbar_arrive_remote(b_full_L);
@@ -90,7 +90,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = uint32_t(G.loads * G.box_rows * RB);
+        const uint32_t tx = uint32_t(G.loads * G.box_rows * RB) + (G.b_streamed ? 9u * uint32_t(G.n_cta * RB) : 0u);
         for (int tile = pair; tile < P.num_tiles; tile += G.tiles_stride) {
             const int m0 = tile * 256 + int(rank) * 128;
             for (int g = 0; g < kGroups; ++g) {
@@ -108,6 +108,11 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                             for (int l = 0; l < G.loads; ++l)
                                 tma_load_2d_pair(sa + G.ld_smem[l], &tmap_a, full_L, P.a_c_off + c * CK,
                                                  row0 + G.ld_row[l]);
+                            if (G.b_streamed) {  // Cin too large for resident weights: this chunk's nine tiles
+                                for (int t = 0; t < 9; ++t)
+                                    tma_load_2d_pair(sa + G.a_part_bytes + t * G.b_tile_bytes, &tmap_b, full_L, c * CK,
+                                                     t * n_full + int(rank) * G.n_cta);
+                            }
                         }
                     }
                     __syncwarp();
@@ -130,7 +135,9 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            mbar_wait(b_full, 0);
+            if (!G.b_streamed) mbar_wait(b_full, 0);
+            const uint32_t a_part16 = uint32_t(G.a_part_bytes) >> 4;
+            const uint32_t b_tap16 = G.b_streamed ? b_tile16 : uint32_t(chunks) * b_tile16;
             for (int tile = pair; tile < P.num_tiles; tile += G.tiles_stride) {
                 mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                 tc_fence_after();
@@ -143,12 +150,14 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
                         const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * a_stage16);
-                        const uint64_t b_st = bdesc0 + uint64_t(uint32_t(g * TPG * chunks + c) * b_tile16);
+                        const uint64_t b_st = G.b_streamed
+                                                  ? a_st + uint64_t(a_part16)
+                                                  : bdesc0 + uint64_t(uint32_t(g * TPG * chunks + c) * b_tile16);
                         if (elect_one()) {
 #pragma unroll
                             for (int t = 0; t < TPG; ++t) {
                                 const uint64_t at = a_st + uint64_t(a_off[t]);
-                                const uint64_t bt = b_st + uint64_t(uint32_t(t * chunks) * b_tile16);
+                                const uint64_t bt = b_st + uint64_t(uint32_t(t) * b_tap16);
                                 if (P.debug & 16) continue;  // profiling: no MMAs, commits only
 #pragma unroll
                                 for (int k = 0; k < Cfg::kKSteps; ++k)

@@ -101,6 +101,9 @@ CONV_CASES = [
     (1, 64, 64, 256, 128, True, 1),
     (5, 9, 7, 256, 16, True, 0),
     (2, 16, 16, 128, 48, False, 0),
+    (2, 9, 11, 32, 16, False, 0),      # two 16-channel chunks (reward head)
+    (2, 64, 64, 256, 128, True, 1),    # Cin = 256: CTA-pair kernel with streamed weights
+    (2, 64, 64, 64, 128, False, 1),
 ]
 
 
