@@ -159,6 +159,27 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
 int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
                       float* loss, float* dx, scmgan_stream_t stream);
 
+/* Separate forward / backward entry points of the same fused kernel (the names SURVEY.md section 8b lists). */
+int scmgan_decoder_bce_fwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
+                           long long per, float* loss, scmgan_stream_t stream);
+int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
+                           long long per, float* loss_scratch, float* dx, scmgan_stream_t stream);
+
+/* Counterfactual regularisers (reference main.py:242-283) on fp32 latents za, zb [B][L][H*W]:
+ *   mode 0, disentanglement (258-260): loss += lambda * mean_b( mask[b] * mean_l( mean_hw|za-zb| * unswapped[b][l] ) )
+ *   mode 1, action control   (279-281): loss += lambda * mean_b( mask[b] * -log( mean_{l,hw}|za-zb| + 1e-3 ) )
+ * rowmean [B][L] receives mean_hw|za-zb| (needed by the backward); gscale is the device scalar d(total)/d(loss). */
+int scmgan_cf_loss_fwd(const float* za, const float* zb, const float* unswapped, const float* mask, int B, int L,
+                       int HW, int mode, float lambda, float* rowmean, float* loss, scmgan_stream_t stream);
+int scmgan_cf_loss_bwd(const float* za, const float* zb, const float* unswapped, const float* mask,
+                       const float* rowmean, const float* gscale, int B, int L, int HW, int mode, float lambda,
+                       float* dza, float* dzb, scmgan_stream_t stream);
+
+/* Stand-alone Transition tail (reference models.py:103-112): p = sigmoid(x); z = (uniforms < p), or (p > 0.5) when
+ * uniforms == NULL.  The training step uses the fused conv6 epilogue instead. */
+int scmgan_transition_tail(const float* x, const float* uniforms, long long n, float* p, float* z,
+                           scmgan_stream_t stream);
+
 /* Reward head of RewardPredictor (reference models.py:240-250): softmax over the 3 classes of each reward,
  * p(+1) - p(-1), summed over the stride-2 valid lattice of the second conv.  y2 is that conv evaluated as a
  * stride-1 same-size conv, fp32 [B][3R][H][W]; r [B][R]; map (optional) [B][R][h2][w2].

@@ -85,6 +85,15 @@ SIGNATURES = {
                                          C.c_void_p]),
     "scmgan_reward_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p]),
+    "scmgan_decoder_bce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
+                                         C.c_void_p, C.c_void_p]),
+    "scmgan_decoder_bce_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_cf_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_cf_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_clip_adam": (C.c_int, [C.c_int, C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_float, C.c_void_p]),
 }

@@ -771,6 +771,51 @@ int scmgan_reward_head_bwd(const float* y2, const float* dr, int B, int R, int H
     return SCM_OK;
 }
 
+int scmgan_cf_loss_fwd(const float* za, const float* zb, const float* unswapped, const float* mask, int B, int L,
+                       int HW, int mode, float lambda, float* rowmean, float* loss, scmgan_stream_t stream) {
+    SCM_REQUIRE(za && zb && mask && rowmean && loss && B > 0 && L > 0 && L <= 64 && HW > 0, "cf_loss_fwd: bad arguments");
+    SCM_REQUIRE(mode == 1 || (mode == 0 && unswapped), "cf_loss_fwd: mode 0 needs the unswapped-factor map");
+    cf_loss_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(za, zb, unswapped, mask, B, L, HW, mode, lambda, rowmean,
+                                                           loss);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_cf_loss_bwd(const float* za, const float* zb, const float* unswapped, const float* mask,
+                       const float* rowmean, const float* gscale, int B, int L, int HW, int mode, float lambda,
+                       float* dza, float* dzb, scmgan_stream_t stream) {
+    SCM_REQUIRE(za && zb && mask && rowmean && gscale && (dza || dzb) && B > 0 && L > 0 && HW > 0,
+                "cf_loss_bwd: bad arguments");
+    const int bx = std::max(1, std::min((HW + 255) / 256, 8));
+    cf_loss_bwd_kernel<<<dim3(bx, B, L), 256, 0, (cudaStream_t)stream>>>(za, zb, unswapped, mask, rowmean, gscale, B, L,
+                                                                        HW, mode, lambda, dza, dzb);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_transition_tail(const float* x, const float* uniforms, long long n, float* p, float* z,
+                           scmgan_stream_t stream) {
+    SCM_REQUIRE(x && z && n > 0, "transition_tail: bad arguments");
+    const int blocks = int(std::min<long long>((n + 255) / 256, 4LL * num_sms()));
+    transition_tail_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, uniforms, n, p, z);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_decoder_bce_fwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
+                           long long per, float* loss, scmgan_stream_t stream) {
+    return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss, nullptr, stream);
+}
+
+int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
+                           long long per, float* loss_scratch, float* dx, scmgan_stream_t stream) {
+    SCM_REQUIRE(dx != nullptr && loss_scratch != nullptr, "decoder_bce_bwd: dx and a scratch scalar are required");
+    return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss_scratch, dx, stream);
+}
+
 int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float beta1, float beta2, float eps,
                      int step, const float* step_dev, float gscale, scmgan_stream_t stream) {
     SCM_REQUIRE(count >= 0 && (count == 0 || chunks), "clip_adam: bad arguments");

@@ -449,3 +449,84 @@ __global__ void reward_head_bwd_kernel(const float* __restrict__ y2, const float
 }
 
 }  // namespace scm
+
+namespace scm {
+
+// ----------------------------------------------------------------------------------------------
+// Counterfactual losses (reference main.py:258-262 and 279-283), fused abs-diff / mean / mask reductions.
+//   za, zb: fp32 [B][L][H][W].  rowmean[b][l] = mean_{h,w} |za - zb|   (written for the backward pass)
+//   mode 0 (disentanglement): loss += lambda/B * mask[b] * (1/L) * sum_l rowmean[b][l] * unswapped[b][l]
+//   mode 1 (action control):  loss += lambda/B * mask[b] * -log( (1/L) * sum_l rowmean[b][l] + 1e-3 )
+// grid = B, block = 256.
+// ----------------------------------------------------------------------------------------------
+__global__ void cf_loss_fwd_kernel(const float* __restrict__ za, const float* __restrict__ zb,
+                                   const float* __restrict__ unswapped, const float* __restrict__ mask, int B, int L,
+                                   int HW, int mode, float lambda, float* __restrict__ rowmean,
+                                   float* __restrict__ loss) {
+    __shared__ float red[33];
+    __shared__ float s_row[64];
+    const int b = blockIdx.x;
+    const float inv_hw = 1.f / float(HW);
+    for (int l = 0; l < L; ++l) {
+        const float* pa = za + (size_t(b) * L + l) * HW;
+        const float* pb = zb + (size_t(b) * L + l) * HW;
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < HW; i += blockDim.x) acc += fabsf(__ldg(pa + i) - __ldg(pb + i));
+        acc = block_sum(acc, red);
+        if (threadIdx.x == 0) {
+            s_row[l] = acc * inv_hw;
+            rowmean[b * L + l] = acc * inv_hw;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        float s = 0.f;
+        for (int l = 0; l < L; ++l) s += s_row[l] * (mode == 0 ? __ldg(unswapped + b * L + l) : 1.f);
+        s /= float(L);
+        const float m = __ldg(mask + b);
+        const float term = (mode == 0) ? s : -logf(s + 1e-3f);
+        atomicAdd(loss, lambda / float(B) * m * term);
+    }
+}
+
+// d loss / d za (and the negative for zb): gscale * coef[b][l] * sign(za - zb) / HW
+//   mode 0: coef = lambda/B * mask[b] * unswapped[b][l] / L
+//   mode 1: coef = -lambda/B * mask[b] / (L * (mean_l rowmean[b][l] + 1e-3))
+__global__ void cf_loss_bwd_kernel(const float* __restrict__ za, const float* __restrict__ zb,
+                                   const float* __restrict__ unswapped, const float* __restrict__ mask,
+                                   const float* __restrict__ rowmean, const float* __restrict__ gscale, int B, int L,
+                                   int HW, int mode, float lambda, float* __restrict__ dza, float* __restrict__ dzb) {
+    const int b = blockIdx.y, l = blockIdx.z;
+    float coef;
+    if (mode == 0) {
+        coef = lambda / float(B) * __ldg(mask + b) * __ldg(unswapped + b * L + l) / float(L);
+    } else {
+        float s = 0.f;
+        for (int j = 0; j < L; ++j) s += __ldg(rowmean + b * L + j);
+        s /= float(L);
+        coef = -lambda / float(B) * __ldg(mask + b) / (float(L) * (s + 1e-3f));
+    }
+    coef *= __ldg(gscale) / float(HW);
+    const size_t base = (size_t(b) * L + l) * HW;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < HW; i += gridDim.x * blockDim.x) {
+        const float d = __ldg(za + base + i) - __ldg(zb + base + i);
+        const float g = d > 0.f ? coef : (d < 0.f ? -coef : 0.f);
+        if (dza) dza[base + i] = g;
+        if (dzb) dzb[base + i] = -g;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Stand-alone Transition tail (reference models.py:103-112): p = sigmoid(x); z = (u < p) in training or (p > 0.5)
+// in eval.  The hot path fuses this into the conv6 epilogue; exported for callers that hold fp32 logits.
+// ----------------------------------------------------------------------------------------------
+__global__ void transition_tail_kernel(const float* __restrict__ x, const float* __restrict__ u, long long n,
+                                       float* __restrict__ p, float* __restrict__ z) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float pv = 1.f / (1.f + __expf(-__ldg(x + i)));
+        if (p) p[i] = pv;
+        z[i] = u ? (__ldg(u + i) < pv ? 1.f : 0.f) : (pv > 0.5f ? 1.f : 0.f);
+    }
+}
+
+}  // namespace scm

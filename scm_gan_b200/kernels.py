@@ -172,6 +172,26 @@ def reward_head_bwd(y2, dr, R, d2_plane):
             "scmgan_reward_head_bwd")
 
 
+def cf_loss_fwd(za, zb, unswapped, mask, mode, lam, rowmean, loss):
+    B, Lz = za.shape[0], za.shape[1]
+    HW = za.numel() // (B * Lz)
+    L.check(L.lib().scmgan_cf_loss_fwd(za.data_ptr(), zb.data_ptr(), L.ptr(unswapped), mask.data_ptr(), B, Lz, HW, mode,
+                                       lam, rowmean.data_ptr(), loss.data_ptr(), _stream()), "scmgan_cf_loss_fwd")
+
+
+def cf_loss_bwd(za, zb, unswapped, mask, rowmean, gscale, mode, lam, dza, dzb):
+    B, Lz = za.shape[0], za.shape[1]
+    HW = za.numel() // (B * Lz)
+    L.check(L.lib().scmgan_cf_loss_bwd(za.data_ptr(), zb.data_ptr(), L.ptr(unswapped), mask.data_ptr(),
+                                       rowmean.data_ptr(), gscale.data_ptr(), B, Lz, HW, mode, lam, L.ptr(dza),
+                                       L.ptr(dzb), _stream()), "scmgan_cf_loss_bwd")
+
+
+def transition_tail(x, uniforms, p, z):
+    L.check(L.lib().scmgan_transition_tail(x.data_ptr(), L.ptr(uniforms), x.numel(), L.ptr(p), z.data_ptr(), _stream()),
+            "scmgan_transition_tail")
+
+
 def clip_adam(chunks, lr, beta1, beta2, eps, step, step_dev=None, gscale=1.0):
     """chunks: list of (p, g, m, v, clip[, step_tensor])."""
     arr = (L.AdamChunk * len(chunks))()

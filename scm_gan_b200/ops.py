@@ -226,3 +226,47 @@ def _reward_backward(ctx, grads):
 
 
 reward_fwd.register_autograd(_reward_backward, setup_context=_reward_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# Counterfactual regularisers (reference main.py:242-283), one fused reduction kernel each way
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::cf_loss", mutates_args=())
+def cf_loss(za: Tensor, zb: Tensor, unswapped: Optional[Tensor], mask: Tensor, mode: int, lam: float) -> List[Tensor]:
+    _require_cuda(za, zb, mask)
+    za, zb = za.contiguous().float(), zb.contiguous().float()
+    loss = torch.zeros(1, dtype=torch.float32, device=za.device)
+    rowmean = torch.empty((za.shape[0], za.shape[1]), dtype=torch.float32, device=za.device)
+    K.cf_loss_fwd(za, zb, None if unswapped is None else unswapped.contiguous().float(), mask.contiguous().float(),
+                  mode, lam, rowmean, loss)
+    return [loss.view(()), rowmean]
+
+
+@torch.library.custom_op("scmgan::cf_loss_bwd", mutates_args=())
+def cf_loss_bwd(za: Tensor, zb: Tensor, unswapped: Optional[Tensor], mask: Tensor, rowmean: Tensor, gscale: Tensor,
+                mode: int, lam: float) -> List[Tensor]:
+    _require_cuda(za, zb)
+    za, zb = za.contiguous().float(), zb.contiguous().float()
+    dza, dzb = torch.empty_like(za), torch.empty_like(zb)
+    K.cf_loss_bwd(za, zb, None if unswapped is None else unswapped.contiguous().float(), mask.contiguous().float(),
+                  rowmean, gscale.reshape(1).contiguous().float(), mode, lam, dza, dzb)
+    return [dza, dzb]
+
+
+def _cf_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    za, zb, unswapped, mask, mode, lam = inputs
+    ctx.mode, ctx.lam = mode, lam
+    ctx.unswapped, ctx.mask = unswapped, mask
+    ctx.save_for_backward(za, zb, output[1])
+
+
+def _cf_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 6
+    za, zb, rowmean = ctx.saved_tensors
+    dza, dzb = torch.ops.scmgan.cf_loss_bwd(za, zb, ctx.unswapped, ctx.mask, rowmean, grads[0], ctx.mode, ctx.lam)
+    return dza, dzb, None, None, None, None
+
+
+cf_loss.register_autograd(_cf_backward, setup_context=_cf_setup)

@@ -111,8 +111,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         z_cf_b[ar, cf_indices[:, 0]] = z_cf_b[ar, cf_indices[:, 1]]
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, actions[:, t])
-        cf = torch.abs(z_cf_a - z_cf_b).mean(-1).mean(-1) * unswapped
-        cf = CF_REGULARIZATION_LAMBDA * torch.mean(cf.mean(-1) * mask)
+        cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
         loss = loss + cf
         if collect is not None:
             collect["CF Disentanglement Loss"] = cf
@@ -123,8 +122,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         cf_actions = actions[cf_perm]
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, cf_actions[:, t])
-        cf = -torch.log(torch.abs(z_cf_a - z_cf_b).mean(-1).mean(-1).mean(-1) + 0.001)
-        cf = CF_REGULARIZATION_LAMBDA * torch.mean(cf * mask)
+        cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
         loss = loss + cf
         if collect is not None:
             collect["CF Control Bias Loss"] = cf

@@ -355,3 +355,38 @@ if __name__ == "__main__":
         run(test_colsum_action_bce_adam)
     print("failures:", fails)
     sys.exit(1 if fails else 0)
+
+
+def test_cf_losses_and_transition_tail():
+    """Fused counterfactual-loss kernels (reference main.py:258-262, 279-283) and the stand-alone Transition tail."""
+    _setup()
+    import scm_gan_b200.ops  # noqa: F401
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(8)
+    B, Lz, H, W = 5, 16, 15, 19
+    za = (torch.rand(B, Lz, H, W, device=DEV) < 0.5).float().requires_grad_(True)
+    zb = torch.rand(B, Lz, H, W, device=DEV).requires_grad_(True)
+    mask = torch.tensor([1.0, 1.0, 0.0, 1.0, 1.0], device=DEV)
+    unsw = (torch.rand(B, Lz, device=DEV) < 0.8).float()
+    lam = 0.01
+    for mode in (0, 1):
+        if mode == 0:
+            ref = torch.abs(za - zb).mean(-1).mean(-1) * unsw
+            ref = lam * torch.mean(ref.mean(-1) * mask)
+        else:
+            ref = -torch.log(torch.abs(za - zb).mean(-1).mean(-1).mean(-1) + 0.001)
+            ref = lam * torch.mean(ref * mask)
+        ga, gb = torch.autograd.grad(ref * 3.0, (za, zb))
+        got = torch.ops.scmgan.cf_loss(za, zb, unsw if mode == 0 else None, mask, mode, lam)[0]
+        ha, hb = torch.autograd.grad(got * 3.0, (za, zb))
+        assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-9, mode
+        assert report(f"cf_loss mode {mode} dza", ha, ga, 1e-5)
+        assert report(f"cf_loss mode {mode} dzb", hb, gb, 1e-5)
+    x = torch.randn(B, Lz, H, W, device=DEV)
+    u = torch.rand_like(x)
+    p, z = torch.empty_like(x), torch.empty_like(x)
+    K.transition_tail(x, u, p, z)
+    assert report("tail p", p, torch.sigmoid(x), 1e-6)
+    assert torch.equal(z, (u < p).float())
+    K.transition_tail(x, None, p, z)
+    assert torch.equal(z, (p > 0.5).float())
