@@ -250,6 +250,7 @@ def main():
     nets = build_nets(C, A, Rw, seed=0)  # identical weights on every rank
     for n in nets.values():
         n.train()
+    nets["transition"]._rng_state[0] += rank  # independent Bernoulli streams per rank
     trainer = Trainer(nets, loss_kwargs=dict(enable_disentanglement=True, enable_action_control=True,
                                              counterfactual_horizon=CF_HORIZON))
     if world > 1:

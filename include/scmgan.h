@@ -68,7 +68,7 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs_host, scmgan_stre
  * and, with flipped/transposed packed weights, their data gradient (cuDNN dgrad under main.py:285).
  * Epilogue: y = acc*scale + bias[n] + sample_bias[b][n]; y += add; y = act(y); y *= lrelu'(gate);
  *   -> bf16 plane `out` (interior + wrapped halo, or zero halo) and/or fp32 NCHW `out_f32`
- *   -> optional Bernoulli head: sample_out = (uniforms < y) or (y > 0.5) when uniforms == NULL
+ *   -> optional Bernoulli head: sample_out = (uniforms < y), or (philox(rng_state) < y), or (y > 0.5)
  *      (reference models.py:30-40, 107-112). */
 typedef struct {
     int B, H, W;
@@ -91,6 +91,8 @@ typedef struct {
     int n_valid;
     float* sample_out;     /* [B][n_valid][H][W] or NULL */
     const float* uniforms; /* [B][n_valid][H][W] or NULL */
+    unsigned long long* rng_state; /* device {seed, offset}: with sample_out and uniforms == NULL the Bernoulli draw uses an
+                                      in-kernel Philox4x32-10 stream and the offset is advanced; NULL => threshold 0.5 */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);

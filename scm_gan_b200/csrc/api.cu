@@ -286,7 +286,21 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
     return launch_v2_inst<16, 9>(ta, tb, P, G, gx, nsplit, smem, st);
 }
 
+static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st);
+
 static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
+    const int rc = conv_impl_inner(d, st);
+    if (rc == SCM_OK && d->sample_out && d->rng_state && !d->uniforms) {
+        // one Philox counter per 4 elements
+        const unsigned long long n = ((unsigned long long)d->B * d->n_valid * d->H * d->W + 3) / 4;
+        rng_advance_kernel<<<1, 1, 0, st>>>(d->rng_state, n);
+        SCM_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
+    return rc;
+}
+
+static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     SCM_REQUIRE(d != nullptr, "conv3x3: null descriptor");
     SCM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0, "conv3x3: bad geometry B=%d H=%d W=%d", d->B, d->H, d->W);
     SCM_REQUIRE(d->x && d->w, "conv3x3: null input/weight pointer");
@@ -325,6 +339,7 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     P.add = reinterpret_cast<const __nv_bfloat16*>(d->add); P.add_cs = d->add_cs; P.add_c_off = d->add_c_off;
     P.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate); P.gate_cs = d->gate_cs; P.gate_c_off = d->gate_c_off;
     P.out_f32 = d->out_f32; P.n_valid = d->n_valid; P.sample_out = d->sample_out; P.uniforms = d->uniforms;
+    P.rng = d->rng_state;
     {
         const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? atoi(dbg) : 0;

@@ -54,8 +54,35 @@ struct IgemmParams {
     // Bernoulli head (Transition conv6): z = (u < p) in training, (p > 0.5) in eval
     float* sample_out;      // fp32 NCHW [B][n_valid][H][W] or nullptr
     const float* uniforms;  // fp32 NCHW or nullptr (nullptr => threshold at 0.5)
+    const unsigned long long* rng;  // device {seed, offset} for the in-kernel Philox stream, or nullptr
     int debug;              // profiling aid (env SCMGAN_DEBUG): bit0 skip global stores, bit1 skip TMEM loads
 };
+
+// Philox4x32-10 (Salmon et al., SC'11), the counter-based generator torch/cuRAND use.  One 128-bit counter yields four
+// uniforms; element idx of a tensor uses counter (offset + idx/4) and lane idx%4, so the stream does not depend on
+// which thread or tile produces the element.
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, unsigned long long ctr, int lane) {
+    uint32_t c0 = uint32_t(ctr), c1 = uint32_t(ctr >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const uint32_t x = lane == 0 ? c0 : (lane == 1 ? c1 : (lane == 2 ? c2 : c3));
+    return (float(x >> 8) + 0.5f) * (1.0f / 16777216.0f);  // 24 random bits, strictly inside (0, 1)
+}
+
+// Bernoulli / threshold head shared by all conv kernels: training with injected uniforms, training with the
+// in-kernel Philox stream, or evaluation (p > 0.5).
+__device__ __forceinline__ float bernoulli_head(const IgemmParams& P, size_t idx, float p) {
+    if (P.uniforms) return __ldg(P.uniforms + idx) < p ? 1.f : 0.f;
+    if (P.rng) return philox_uniform(__ldg(P.rng), __ldg(P.rng + 1) + (idx >> 2), int(idx & 3)) < p ? 1.f : 0.f;
+    return p > 0.5f ? 1.f : 0.f;
+}
 
 template <int CK>
 struct IgemmCfg {
@@ -294,11 +321,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                         if (n < P.n_valid) {
                             const size_t idx = base + size_t(n) * hw;
                             P.out_f32[idx] = v[i];
-                            if (P.sample_out) {
-                                const float thr = P.uniforms ? __ldg(P.uniforms + idx) : 0.5f;
-                                // training: z = (u < p) ; eval: z = (p > 0.5)
-                                P.sample_out[idx] = P.uniforms ? (thr < v[i] ? 1.f : 0.f) : (v[i] > 0.5f ? 1.f : 0.f);
-                            }
+                            if (P.sample_out) P.sample_out[idx] = bernoulli_head(P, idx, v[i]);
                         }
                     }
                 }

@@ -529,4 +529,7 @@ __global__ void transition_tail_kernel(const float* __restrict__ x, const float*
     }
 }
 
+// advance the device-side Philox offset after a sampling launch (keeps the whole step CUDA-graph replayable)
+__global__ void rng_advance_kernel(unsigned long long* rng, unsigned long long n) { rng[1] += n; }
+
 }  // namespace scm

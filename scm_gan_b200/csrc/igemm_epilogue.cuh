@@ -148,12 +148,7 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
                 if (n < P.n_valid) {
                     const size_t idx = base + size_t(n) * hw;
                     P.out_f32[idx] = v[i];
-                    if (P.sample_out) {
-                        // training: z = (u < p) ; eval: z = (p > 0.5)
-                        const float z = P.uniforms ? (__ldg(P.uniforms + idx) < v[i] ? 1.f : 0.f)
-                                                   : (v[i] > 0.5f ? 1.f : 0.f);
-                        P.sample_out[idx] = z;
-                    }
+                    if (P.sample_out) P.sample_out[idx] = bernoulli_head(P, idx, v[i]);
                 }
             }
         }

@@ -75,6 +75,9 @@ class Transition(nn.Module):
         self.conv5 = SpectralNorm(circ(2 * hid, hid))   # input: cat[act4, skip2]
         self.conv6 = circ(2 * hid, latent_size)         # input: cat[act5, skip1]; not spectrally normalised
         self._uniforms = None  # test hook: uniforms consumed by the next training-mode forward (U < p)
+        # Philox {seed, offset} for the in-kernel Bernoulli draw (not part of the state_dict, like torch's generator)
+        self.register_buffer("_rng_state", torch.tensor([torch.initial_seed() & 0x7FFFFFFFFFFFFFFF, 0],
+                                                        dtype=torch.int64), persistent=False)
         _to_device(self)
 
     def forward(self, s, a, return_all=False):
@@ -86,13 +89,14 @@ class Transition(nn.Module):
         if self.training:
             uniforms, self._uniforms = self._uniforms, None
             if uniforms is None:
-                uniforms = torch.rand(s.shape, dtype=torch.float32, device=s.device)
+                _ops._RNG_SOURCE.append(self._rng_state)  # sample inside the conv6 epilogue (Philox4x32-10)
         _ops._UV_SOURCE.append((u, v))
         try:
             out = torch.ops.scmgan.transition_fwd(s, a, wbar, bias, sigma, self.conv6.weight, self.conv6.bias,
                                                   uniforms, self.training)
         finally:
             _ops._UV_SOURCE.clear()
+            _ops._RNG_SOURCE.clear()
         x = out[0]
         if not self.training:
             x = x.detach()  # thresholding carries no gradient (reference models.py:112)

@@ -63,7 +63,7 @@ def spectral_norm_update(wbar, u, v):
     return sigma
 
 
-def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training):
+def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_state=None):
     """z [B,L,H,W] fp32, a [B,A] fp32.  wbar/bias: lists for conv1..conv5; sigma [5] from spectral_norm_update.
     Returns (z_next, p, saved) with saved = [zin, buf6, buf5, act3, wd...] for backward."""
     dev = z.device
@@ -104,7 +104,8 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training):
     zn = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     b6p = b6 if Lp == L else torch.nn.functional.pad(b6, (0, Lp - L))
     K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6p, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
-              uniforms=uniforms if training else None)                                              # conv6 + head
+              uniforms=uniforms if training else None,
+              rng_state=rng_state if (training and uniforms is None) else None)                     # conv6 + head
     return zn, p, [zin, buf6, buf5, act3] + wd
 
 

@@ -56,7 +56,7 @@ def packed_weight(n_pad, k_pad, device):
 
 def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, act=ACT_NONE,
             out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
-            n_valid=0, sample_out=None, uniforms=None, dgrad=False):
+            n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False):
     n = w_packed.shape[1]
     assert w_packed.shape[2] == cin and w_packed.dtype == torch.bfloat16
     d = L.ConvDesc()
@@ -76,6 +76,7 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     d.gate_c_off = gate_c_off
     d.out_f32, d.n_valid = L.ptr(out_f32), n_valid
     d.sample_out, d.uniforms = L.ptr(sample_out), L.ptr(uniforms)
+    d.rng_state = L.ptr(rng_state)  # int64 [2] = {seed, offset}; advanced by the library after the launch
     fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
     L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
 

@@ -35,13 +35,19 @@ def spectral_norm_update(wbar: Sequence[Tensor], u: Sequence[Tensor], v: Sequenc
     return E.spectral_norm_update(list(wbar), list(u), list(v))
 
 
+# Philox state {seed, offset} of the module issuing the next training-mode forward (device int64[2]).  Like the
+# power-iteration vectors it is module state that the kernels advance, so it travels beside the functional op.
+_RNG_SOURCE = []
+
+
 @torch.library.custom_op("scmgan::transition_fwd", mutates_args=())
 def transition_fwd(z: Tensor, a: Tensor, wbar: Sequence[Tensor], bias: Sequence[Tensor], sigma: Tensor,
                    w6: Tensor, b6: Tensor, uniforms: Optional[Tensor], training: bool) -> List[Tensor]:
     _require_cuda(z, a, w6)
+    rng = _RNG_SOURCE.pop() if _RNG_SOURCE else None
     zn, p, saved = E.transition_forward(z.contiguous().float(), a.contiguous().float(), list(wbar), list(bias),
                                         sigma, w6, b6,
-                                        None if uniforms is None else uniforms.contiguous().float(), training)
+                                        None if uniforms is None else uniforms.contiguous().float(), training, rng)
     return [zn, p] + saved
 
 

@@ -390,3 +390,44 @@ def test_cf_losses_and_transition_tail():
     assert torch.equal(z, (u < p).float())
     K.transition_tail(x, None, p, z)
     assert torch.equal(z, (p > 0.5).float())
+
+
+def test_in_kernel_philox_bernoulli():
+    """Bernoulli head with the in-kernel Philox4x32-10 stream: calibrated, reproducible from {seed, offset}, offset
+    advanced on the device (graph-replay safe)."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(9)
+    B, H, W, Ci, Co = 8, 32, 32, 64, 16
+    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (1.5 * Ci ** 0.5))
+    xp = make_plane(x, Ci, 0, True)
+    wp = pack_conv_weight(w, Co, Ci)
+    n = B * Co * H * W
+
+    def draw(state):
+        p = torch.empty(B, Co, H, W, device=DEV)
+        z = torch.empty(B, Co, H, W, device=DEV)
+        K.conv3x3(xp, wp, B, H, W, cin=Ci, act=2, out_f32=p, n_valid=Co, sample_out=z, rng_state=state)
+        return p, z
+
+    s1 = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    p, z1 = draw(s1)
+    assert s1.tolist() == [1234, (n + 3) // 4]
+    assert set(z1.unique().tolist()) <= {0.0, 1.0}
+    # calibration: E[z] = p.  Overall and per probability bin (4 sigma)
+    assert abs(z1.mean().item() - p.mean().item()) < 4 * 0.5 / n ** 0.5
+    for lo in (0.0, 0.2, 0.4, 0.6, 0.8):
+        sel = (p >= lo) & (p < lo + 0.2)
+        m = int(sel.sum())
+        if m > 1000:
+            assert abs(z1[sel].mean().item() - p[sel].mean().item()) < 4 * 0.5 / m ** 0.5, lo
+    _, z2 = draw(s1)                      # continues the stream: independent draw
+    agree = (z1 == z2).float().mean().item()
+    expect = (p * p + (1 - p) * (1 - p)).mean().item()
+    assert abs(agree - expect) < 0.01
+    s3 = torch.tensor([1234, 0], dtype=torch.int64, device=DEV)
+    _, z3 = draw(s3)                      # same {seed, offset}: same sample
+    assert torch.equal(z1, z3)
+    _, z4 = draw(torch.tensor([99, 0], dtype=torch.int64, device=DEV))
+    assert not torch.equal(z1, z4)
