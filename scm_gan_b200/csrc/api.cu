@@ -135,7 +135,7 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
     constexpr int CK = 64, RB = 128;
     static const char* off = getenv("SCMGAN_NO_PAIR");
     if (off && atoi(off)) return 1;
-    if (d->n != 128 || d->cin % 64 != 0) return 1;
+    if (d->n != 128 || d->cin % 64 != 0 || d->out_f32) return 1;
     const int chunks = d->cin / CK;
     const int n_half = d->n / 2;
     const bool streamed = 9 * chunks * n_half * RB > 150 * 1024;  // e.g. Cin = 256: weights ride in the stages
@@ -249,7 +249,17 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
         const int tile_bytes = 128 * RB;
         const int stage_bytes = 9 * tile_bytes;
         const int stages = std::min(6, avail / stage_bytes);
-        if (stages >= 2 && chunks <= 4) {
+        const int R = 128 + 2 * Wp + 2;
+        static const char* soft_env = getenv("SCMGAN_NO_SOFT_A");
+        if (chunks == 1 && R <= 272 && !(soft_env && atoi(soft_env))) {
+            // one software-staged super tile per 128-row tile (see the producer warp in conv_igemm_v2.cuh)
+            tpg = 9;
+            G.a_soft = 1;
+            G.loads = 0; G.box_rows = R;
+            G.a_stage_bytes = (R * RB + 1023) & ~1023;
+            G.num_stages = std::min(6, avail / G.a_stage_bytes);
+            for (int t = 0; t < 9; ++t) G.a_off16[t] = uint32_t(((t / 3) * Wp + (t % 3)) * RB) >> 4;
+        } else if (stages >= 2 && chunks <= 4) {
             tpg = 9;
             G.loads = 9; G.box_rows = 128; G.a_stage_bytes = stage_bytes; G.num_stages = stages;
             for (int t = 0; t < 9; ++t) {
@@ -267,7 +277,7 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
     {
         uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};
         uint64_t str[1] = {uint64_t(d->x_cs) * 2};
-        uint32_t box[2] = {uint32_t(CK), uint32_t(G.box_rows)};
+        uint32_t box[2] = {uint32_t(CK), uint32_t(G.a_soft ? 128 : G.box_rows)};
         int rc = encode_tmap_bf16(&ta, d->x, 2, dims, str, box, RB);
         if (rc) return rc;
     }
@@ -333,6 +343,7 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     const int CK = (d->cin % 64 == 0) ? 64 : 16;
     P.cin_chunks = d->cin / CK;
     P.a_c_off = d->x_c_off;
+    P.a = reinterpret_cast<const __nv_bfloat16*>(d->x); P.a_cs = d->x_cs;
     P.scale = d->scale; P.bias = d->bias; P.sample_bias = d->sample_bias; P.act = d->act; P.slope = d->slope;
     P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
     P.wrap = d->wrap;

@@ -33,6 +33,8 @@ struct IgemmParams {
     int n;           // UMMA N (multiple of 16, <= 256); also the packed-weight rows per tap
     int cin_chunks;  // Cin_padded / CK
     int a_c_off;     // first input channel inside the A plane
+    const __nv_bfloat16* a;  // the A plane itself (software-staged narrow-K path of conv_igemm_v2.cuh)
+    int a_cs;                // its channel stride
     // epilogue
     float scale;               // multiplies the accumulator (1/sigma folding, loss scaling)
     const float* bias;         // [n] or nullptr

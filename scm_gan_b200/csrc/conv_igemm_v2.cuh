@@ -29,6 +29,7 @@ struct IgemmV2Geom {
     uint32_t a_off16[9];  // per tap of a group: operand start inside the stage, in 16-byte units
     int a_stage_bytes;   // bytes of one pipeline stage (activation super tile [+ streamed weight tiles])
     int a_part_bytes;    // v3 streamed-weights mode: offset of the weight tiles inside a stage
+    int a_soft;          // CK = 16: the producer warp stages the super tile with LDG/STS instead of TMA
     int b_streamed;      // v3: 0 = weights resident for the whole kernel, 1 = the chunk's 9 weight tiles ride in each stage
     int b_tile_bytes;    // n_cta * row bytes
     int num_stages;
@@ -108,8 +109,53 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         __syncwarp();
         int stage = 0;
         uint32_t phase = 0;
-        const uint32_t tx = uint32_t(G.loads * G.box_rows * RB);
+        if (CK == 16 && G.a_soft) {
+            // Narrow K (Cin = 16): a plane row is 32 bytes, and a TMA box of 32-byte rows is bound by the TMA's
+            // request rate (measured: 3.7k cycles per 128-row tile for 9 x 4 KB boxes).  The producer warp instead
+            // copies ONE super tile (128 + 2*Wp + 2 rows, all nine taps) per tile with 16-byte loads, one tile ahead
+            // in registers, and writes it in the 32-byte-swizzled K-major layout (address bit 4 ^= bit 7, on the
+            // absolute shared-memory address, which is also what the row-shifted UMMA descriptors assume).
+            constexpr int kIt = 17;  // 17 x 32 lanes x 16 B >= 272 rows
+            const int nch = G.box_rows * 2;
+            uint4 buf[kIt];
+            auto fetch = [&](int tile) {
+                const int row0 = tile * 128 - P.Wp - 1;
+#pragma unroll
+                for (int it = 0; it < kIt; ++it) {
+                    const int i = it * 32 + lane;
+                    const int row = row0 + (i >> 1);
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (i < nch && row >= 0 && row < P.rows)
+                        v = __ldg(reinterpret_cast<const uint4*>(P.a + size_t(row) * P.a_cs + P.a_c_off) + (i & 1));
+                    buf[it] = v;
+                }
+            };
+            int tile = blockIdx.x;
+            if (tile < P.num_tiles) fetch(tile);
+            for (; tile < P.num_tiles; tile += G.tiles_stride) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const uint32_t sa = smem_u32(s_a + size_t(stage) * G.a_stage_bytes);
+#pragma unroll
+                for (int it = 0; it < kIt; ++it) {
+                    const int i = it * 32 + lane;
+                    if (i < nch && !(P.debug & 8)) {
+                        uint32_t ad = sa + uint32_t(i) * 16u;
+                        ad ^= (ad >> 3) & 16u;
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(buf[it].x),
+                                     "r"(buf[it].y), "r"(buf[it].z), "r"(buf[it].w)
+                                     : "memory");
+                    }
+                }
+                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                if (++stage == G.num_stages) { stage = 0; phase ^= 1; }
+                const int nt = tile + G.tiles_stride;
+                if (nt < P.num_tiles) fetch(nt);
+            }
+        } else
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+            const uint32_t tx = uint32_t(G.loads * G.box_rows * RB);
             const int m0 = tile * 128;
             for (int g = 0; g < kGroups; ++g) {
                 const int tap0 = g * TPG;
@@ -162,6 +208,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                     if (elect_one()) {
 #pragma unroll
                         for (int t = 0; t < TPG; ++t) {
+                            if (P.debug & 4) break;  // profiling: barrier traffic only
                             const uint64_t at = a_st + uint64_t(a_off[t]);
                             const uint64_t bt = b_st + uint64_t(uint32_t(t * chunks) * b_tile16);
 #pragma unroll
@@ -192,10 +239,12 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
-            if ((G.n_cta & 31) == 0)
-                igemm_epilogue_tile<32>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+            if (P.out_f32)
+                igemm_epilogue_tile<16, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+            else if ((G.n_cta & 31) == 0)
+                igemm_epilogue_tile<32, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
             else
-                igemm_epilogue_tile<16>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+                igemm_epilogue_tile<16, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);

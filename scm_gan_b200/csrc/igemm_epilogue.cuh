@@ -20,6 +20,14 @@ __device__ __forceinline__ void st_global_256(void* p, const uint32_t (&o)[8]) {
                  : "memory");
 }
 
+// Compiler-only fence: ties 16 accumulator registers to a point after tcgen05.wait::ld so that no arithmetic on them
+// can be scheduled above the wait (the asynchronous tcgen05.ld has only then delivered them).
+__device__ __forceinline__ void epi_reg_fence16(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]),
+                      "+f"(v[8]), "+f"(v[9]), "+f"(v[10]), "+f"(v[11]), "+f"(v[12]), "+f"(v[13]), "+f"(v[14]),
+                      "+f"(v[15]));
+}
+
 struct EpiRow {
     int p, b, hp, wp;
     bool valid, interior;
@@ -42,7 +50,9 @@ __device__ __forceinline__ EpiRow epi_decode_row(const IgemmParams& P, int p) {
 }
 
 // GROUP: columns per pass (32, or 16 when the CTA's N slice is not a multiple of 32 / shared memory is tight).
-template <int GROUP>
+// F32: the fp32 NCHW / Bernoulli-head output is compiled in (only the narrow N = 16 heads use it; keeping it out of
+// the wide instantiations keeps the hot loop small enough for the instruction cache).
+template <int GROUP, bool F32>
 __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_total, int n0, int ncols_cta, int p,
                                                     int half, int lane, uint32_t taddr, const float* s_bias) {
     constexpr int CH = GROUP / 8;       // 16-byte chunks per row segment
@@ -61,20 +71,28 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
     }
     const float* sbp = (P.sample_bias && R.valid) ? P.sample_bias + size_t(R.b) * n_total + n0 : nullptr;
     const size_t hw = size_t(P.H) * P.W;
+    const uint32_t s_bias_u32 = smem_u32(s_bias);
+    __nv_bfloat16* const ob = P.out + (P.out_c_off + n0);
+    __nv_bfloat16* const ob0 = ob + size_t(d0 < 0 ? 0 : d0) * P.out_cs;
+    const bool any_wrap = (d1 >= 0) || (d2 >= 0);
 
-    for (int c0 = half * GROUP; c0 < ncols_cta; c0 += 2 * GROUP) {
-        float v[GROUP];
-        if (!(P.debug & 2)) {
-            tmem_ld16(taddr + uint32_t(c0), v);
-            if (GROUP == 32) tmem_ld16(taddr + uint32_t(c0 + 16), v + (GROUP == 32 ? 16 : 0));
-            tmem_ld_wait();
-        }
-        if (P.debug & 1) continue;
+    // TMEM reads are double-buffered: the tcgen05.ld of the warp's next column group is in flight while the current
+    // group goes through the arithmetic and the stores (the epilogue is latency-bound, not issue-bound).
+    auto load = [&](float (&v)[GROUP], int c0) {
+        tmem_ld16(taddr + uint32_t(c0), v);
+        if (GROUP == 32) tmem_ld16(taddr + uint32_t(c0 + 16), v + (GROUP == 32 ? 16 : 0));
+    };
+    auto process = [&](float (&v)[GROUP], int c0) {
+        epi_reg_fence16(v);
+        if (GROUP == 32) epi_reg_fence16(v + (GROUP == 32 ? 16 : 0));
+        if (P.debug & 1) return;
         {
-            const float4* bp = reinterpret_cast<const float4*>(s_bias + c0);
 #pragma unroll
             for (int j = 0; j < GROUP / 4; ++j) {
-                const float4 b4 = bp[j];
+                float4 b4;
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
+                             : "r"(s_bias_u32 + uint32_t(c0 + 4 * j) * 4u));
                 v[4 * j] = fmaf(v[4 * j], P.scale, b4.x);
                 v[4 * j + 1] = fmaf(v[4 * j + 1], P.scale, b4.y);
                 v[4 * j + 2] = fmaf(v[4 * j + 2], P.scale, b4.z);
@@ -131,16 +149,18 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
 #pragma unroll
                     for (int i = 0; i < 8; ++i) o[i] = 0u;
                 }
-                __nv_bfloat16* ob = P.out + (P.out_c_off + n0 + c0 + j * 16);
+                const int co = c0 + j * 16;
                 if (!(P.debug & 64)) {
-                    if (d0 >= 0) st_global_256(ob + size_t(d0) * P.out_cs, o);
-                    if (d1 >= 0) st_global_256(ob + size_t(d1) * P.out_cs, o);
-                    if (d2 >= 0) st_global_256(ob + size_t(d2) * P.out_cs, o);
-                    if (d3 >= 0) st_global_256(ob + size_t(d3) * P.out_cs, o);
+                    if (d0 >= 0) st_global_256(ob0 + co, o);
+                    if (any_wrap) {  // border rows only (divergent, rare)
+                        if (d1 >= 0) st_global_256(ob + size_t(d1) * P.out_cs + co, o);
+                        if (d2 >= 0) st_global_256(ob + size_t(d2) * P.out_cs + co, o);
+                        if (d3 >= 0) st_global_256(ob + size_t(d3) * P.out_cs + co, o);
+                    }
                 }
             }
         }
-        if (P.out_f32 && R.interior) {
+        if (F32 && P.out_f32 && R.interior) {
             const size_t base = (size_t(R.b) * P.n_valid) * hw + size_t(R.hp - 1) * P.W + (R.wp - 1);
 #pragma unroll
             for (int i = 0; i < GROUP; ++i) {
@@ -152,6 +172,20 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
                 }
             }
         }
+    };
+    float va[GROUP], vb[GROUP];
+    int c0 = half * GROUP;
+    if (c0 < ncols_cta) load(va, c0);
+    while (c0 < ncols_cta) {
+        tmem_ld_wait();
+        const int c1 = c0 + 2 * GROUP;
+        if (c1 < ncols_cta) load(vb, c1);
+        process(va, c0);
+        if (c1 >= ncols_cta) break;
+        tmem_ld_wait();
+        c0 = c1 + 2 * GROUP;
+        if (c0 < ncols_cta) load(va, c0);
+        process(vb, c1);
     }
 }
 
