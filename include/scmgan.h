@@ -114,7 +114,8 @@ typedef struct {
     void* workspace; /* optional split-K scratch (scmgan_wgrad_workspace_bytes()); with it the reduction is a second,
                         deterministic kernel instead of fp32 atomics */
     long long workspace_bytes;
-    float* db; /* optional bias gradient: db[co] += sum over interior pixels of dy[p][co] (co < cout) */
+    float* db; /* optional bias gradient: db[co] += sum over interior pixels of dy[p][co]; written for
+                  co < co_valid rounded up to a multiple of 8 (the buffer must hold that many floats) */
 } scmgan_wgrad_desc;
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* desc_host, scmgan_stream_t stream);
 long long scmgan_wgrad_workspace_bytes(void);
@@ -137,7 +138,9 @@ typedef struct {
 } scmgan_sn_layer;
 int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers_host, scmgan_stream_t stream);
 
-/* dWbar = G/sigma - (<G,Wbar>/sigma^2) u v^T  (autograd of `w / sigma.expand_as(w)`, sigma = u.(W v)). */
+/* dWbar = G/sigma - (<G,Wbar>/sigma^2) u v^T  (autograd of `w / sigma.expand_as(w)`, sigma = u.(W v)).
+ * accumulate != 0: out += dWbar (what autograd's AccumulateGrad does for a weight shared by the unrolled steps of
+ * main.py:162-215), else out = dWbar. */
 typedef struct {
     const float* g;
     const float* wbar;
@@ -147,6 +150,7 @@ typedef struct {
     float* dot; /* [1] scratch, zeroed by caller */
     float* out;
     int rows, cols;
+    int accumulate;
 } scmgan_sn_bwd_layer;
 int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers_host, scmgan_stream_t stream);
 

@@ -50,7 +50,7 @@ class SnLayer(C.Structure):
 class SnBwdLayer(C.Structure):
     _fields_ = [("g", C.c_void_p), ("wbar", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
                 ("sigma", C.c_void_p), ("dot", C.c_void_p), ("out", C.c_void_p),
-                ("rows", C.c_int), ("cols", C.c_int)]
+                ("rows", C.c_int), ("cols", C.c_int), ("accumulate", C.c_int)]
 
 
 class AdamChunk(C.Structure):

@@ -624,7 +624,7 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     // bias gradient (optional): folded into the first v2 launch of every 128-channel output block, otherwise a
     // separate interior column sum over the gradient plane
     auto bias_fallback = [&](int m0, int mcount) -> int {
-        const int n8 = (mcount + 7) & ~7;
+        const int n8 = (std::min(mcount, d->co_valid - m0) + 7) & ~7;  // db holds co_valid (rounded up to 8) floats
         return scmgan_plane_colsum(d->dy, d->dy_cs, d->dy_c_off + m0, n8, d->B, d->H, d->W, nullptr, d->db + m0, stream);
     };
     if (d->cout % 128 == 0) {
@@ -730,7 +730,7 @@ int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmga
     for (int i = 0; i < count; ++i) {
         const scmgan_sn_bwd_layer& s = layers[i];
         SCM_REQUIRE(s.g && s.wbar && s.u && s.v && s.sigma && s.dot && s.out, "spectral_norm_bwd: bad layer %d", i);
-        L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols};
+        L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols, s.accumulate};
     }
     sn_bwd_dot_kernel<<<dim3(32, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());

@@ -190,6 +190,7 @@ struct SnBwdLayer {
     float* dot;   // [1] scratch, zeroed by the caller
     float* out;   // [rows][cols]
     int rows, cols;
+    int accumulate;  // out += result instead of out = result
 };
 struct SnBwdLayers {
     SnBwdLayer layer[kMaxSnLayers];
@@ -217,7 +218,8 @@ __global__ void sn_bwd_apply_kernel(const __grid_constant__ SnBwdLayers L) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int n = int(i / Y.cols), k = int(i - (long long)n * Y.cols);
-        Y.out[i] = __ldg(Y.g + i) * inv - coef * __ldg(Y.u + n) * __ldg(Y.v + k);
+        const float r = __ldg(Y.g + i) * inv - coef * __ldg(Y.u + n) * __ldg(Y.v + k);
+        Y.out[i] = Y.accumulate ? Y.out[i] + r : r;
     }
 }
 

@@ -38,6 +38,8 @@ class BucketedGradSync:
         self._armed = False
         trainer.sync = self
         trainer.world_size = self.world_size
+        if hasattr(trainer, "register_sinks"):
+            trainer.register_sinks()
 
     def zero(self):
         for b in self.buckets:

@@ -109,9 +109,12 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     return zn, p, [zin, buf6, buf5, act3] + wd
 
 
-def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6):
+def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     """Backward of transition_forward.  dz_next: gradient w.r.t. the sampled state (straight-through => w.r.t. p,
-    reference models.py:38-40).  Returns (dz, [dWbar1..5], [db1..5], dW6, db6)."""
+    reference models.py:38-40).  Returns (dz, [dWbar1..5], [db1..5], dW6, db6).
+    sink = [gWbar1..5, gb1..5, gW6, gb6] (entries may be None): the kernels ADD that parameter's gradient into the
+    given buffer (the parameter's .grad) and None is returned in its place; the weights are shared by every unrolled
+    step, so this replaces one AccumulateGrad add per parameter and step."""
     zin, buf6, buf5, act3 = saved[:4]
     wd = saved[4:]
     dev = dz_next.device
@@ -133,6 +136,13 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6):
     S1 = flat[off: off + B * HID].view(B, HID)
     off += B * HID
     dots = flat[off: off + 8]
+    sink = list(sink) if sink is not None else [None] * 12
+    gw, gb, gw6, gb6 = sink[0:5], sink[5:10], sink[10], sink[11]
+    if gw6 is not None:
+        G[5] = gw6
+    db = [db[i] if gb[i] is None else gb[i] for i in range(5)]
+    if gb6 is not None and Lp == L:
+        db6 = gb6
 
     # d pre-activation of conv6: dz * p * (1 - p)
     d6 = K.new_plane(B, H, W, Lp, dev)
@@ -166,9 +176,13 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6):
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
     # spectral norm backward with the u, v currently held by the module (= last forward call)
-    dwbar = [torch.empty_like(w) for w in wbar]
-    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1], dwbar[i]) for i in range(5)])
-    return dz, dwbar, [d.clone() for d in db], G[5].clone(), db6[:L].clone()
+    dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
+    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
+                          dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(5)])
+    if gb6 is not None and Lp != L:
+        gb6 += db6[:L]
+    return (dz, dwbar, [db[i].clone() if gb[i] is None else None for i in range(5)],
+            G[5].clone() if gw6 is None else None, db6[:L].clone() if gb6 is None else None)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -200,7 +214,8 @@ def encoder_forward(x, wbar, bias, sigma, w4, b4):
     return z, [xin, a1, a2, a3] + wd
 
 
-def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4):
+def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
+    """sink = [gWbar1..3, gb1..3, gW4, gb4] (entries may be None): see transition_backward."""
     xin, a1, a2, a3 = saved[:4]
     wd = saved[4:]
     dev = dz.device
@@ -217,6 +232,13 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4):
     db = [flat[off + i * HID: off + (i + 1) * HID] for i in range(3)]
     db4 = flat[off + 3 * HID: off + 3 * HID + Lp]
     dots = flat[off + 3 * HID + Lp:]
+    sink = list(sink) if sink is not None else [None] * 8
+    gw, gb, gw4, gb4 = sink[0:3], sink[3:6], sink[6], sink[7]
+    if gw4 is not None:
+        G[3] = gw4
+    db = [db[i] if gb[i] is None else gb[i] for i in range(3)]
+    if gb4 is not None and Lp == L:
+        db4 = gb4
     d4 = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(dz, d4, wrap=False, sig=z)
     K.wgrad(d4, a3, G[3], B, H, W, cout=Lp, cin=HID, g_s_co=HID * 9, g_s_ci=9, co_valid=L)
@@ -228,9 +250,13 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4):
     K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
     K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
     K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0])
-    dwbar = [torch.empty_like(w) for w in wbar]
-    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1], dwbar[i]) for i in range(3)])
-    return dwbar, [d.clone() for d in db], G[3].clone(), db4[:L].clone()
+    dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
+    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
+                          dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(3)])
+    if gb4 is not None and Lp != L:
+        gb4 += db4[:L]
+    return (dwbar, [db[i].clone() if gb[i] is None else None for i in range(3)],
+            G[3].clone() if gw4 is None else None, db4[:L].clone() if gb4 is None else None)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -247,24 +273,26 @@ def decoder_forward(z, w1, b1, w2, b2):
     co = w2.shape[1]
     cop = _r16(co)
     assert hid % 64 == 0 and hid <= HID
-    wf1 = K.packed_weight(HID, Lp, dev)      # hidden padded to 128 channels (upper ones are exactly zero)
+    # the hidden plane is 128 channels wide (wgrad wants a 128-channel operand) but only `hid` are computed: the
+    # unwritten upper channels only ever reach wgrad outputs beyond co_valid / ci_valid, which are discarded
+    wf1 = K.packed_weight(hid, Lp, dev)
     wf2 = K.packed_weight(cop, hid, dev)
     wd1 = K.packed_weight(Lp, hid, dev)
-    wd2 = K.packed_weight(HID, cop, dev)
+    wd2 = K.packed_weight(hid, cop, dev)
     K.pack_weights([_convT_fwd_job(w1, wf1), _convT_fwd_job(w2, wf2), _convT_dgrad_job(w1, wd1),
                     _convT_dgrad_job(w2, wd2)])
     zin = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=False)
     hidp = K.new_plane(B, H, W, HID, dev)
-    b1p = b1 if hid == HID else torch.nn.functional.pad(b1, (0, HID - hid))
-    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1p, act=ACT_LRELU, out=hidp)
+    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     logits = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
     b2p = b2 if cop == co else torch.nn.functional.pad(b2, (0, cop - co))
     K.conv3x3(hidp, wf2, B, H, W, cin=hid, bias=b2p, act=ACT_NONE, out_f32=logits, n_valid=co)
     return logits, [zin, hidp, wd1, wd2]
 
 
-def decoder_backward(dlogits, saved, w1, w2):
+def decoder_backward(dlogits, saved, w1, w2, sink=None):
+    """sink = [gW1, gb1, gW2, gb2] (entries may be None): see transition_backward."""
     zin, hidp, wd1, wd2 = saved
     dev = dlogits.device
     B, co, H, W = dlogits.shape
@@ -276,6 +304,15 @@ def decoder_backward(dlogits, saved, w1, w2):
     g2 = flat[w1.numel(): w1.numel() + w2.numel()].view(w2.shape)
     db1 = flat[w1.numel() + w2.numel(): w1.numel() + w2.numel() + HID]
     db2 = flat[w1.numel() + w2.numel() + HID:]
+    sink = list(sink) if sink is not None else [None] * 4
+    if sink[0] is not None:
+        g1 = sink[0]
+    if sink[1] is not None and hid % 8 == 0:   # wgrad writes the valid channels rounded up to 8
+        db1 = sink[1]
+    if sink[2] is not None:
+        g2 = sink[2]
+    if sink[3] is not None and cop == co:
+        db2 = sink[3]
     d2 = K.new_plane(B, H, W, cop, dev)
     K.pack_nchw(dlogits, d2, wrap=False)
     # ConvTranspose weight layout [Cin][Cout][3][3], taps flipped relative to the equivalent correlation
@@ -287,7 +324,12 @@ def decoder_backward(dlogits, saved, w1, w2):
             db=db1)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True)
-    return dz, g1.clone(), db1[:hid].clone(), g2.clone(), db2[:co].clone()
+    if sink[1] is not None and db1 is not sink[1]:
+        sink[1].add_(db1[:hid])
+    if sink[3] is not None and db2 is not sink[3]:
+        sink[3].add_(db2[:co])
+    return (dz, g1.clone() if sink[0] is None else None, db1[:hid].clone() if sink[1] is None else None,
+            g2.clone() if sink[2] is None else None, db2[:co].clone() if sink[3] is None else None)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -306,16 +348,17 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     co = w2.shape[0]
     R = co // 3
     assert w1.shape[0] == RHID and co <= 16
-    wf1 = K.packed_weight(HID, Lp, dev)   # hidden padded to 128 channels (zero rows beyond 32)
+    # hidden plane 128 channels wide for wgrad, only RHID computed (see decoder_forward)
+    wf1 = K.packed_weight(RHID, Lp, dev)
     wf2 = K.packed_weight(16, RHID, dev)
     wd1 = K.packed_weight(Lp, RHID, dev)
-    wd2 = K.packed_weight(HID, 16, dev)
+    wd2 = K.packed_weight(RHID, 16, dev)
     K.pack_weights([_conv2d_fwd_job(w1, wf1), _conv2d_fwd_job(w2, wf2),
                     _conv2d_dgrad_job(w1, wd1), _conv2d_dgrad_job(w2, wd2)])
     zin = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=False)
     hidp = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=torch.nn.functional.pad(b1, (0, HID - RHID)), act=ACT_LRELU, out=hidp)
+    K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     y2 = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(hidp, wf2, B, H, W, cin=RHID, bias=torch.nn.functional.pad(b2, (0, 16 - co)), act=ACT_NONE,
               out_f32=y2, n_valid=co)
@@ -326,7 +369,8 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     return r, rmap, [zin, hidp, y2, wd1, wd2]
 
 
-def reward_backward(dr, saved, w1, w2):
+def reward_backward(dr, saved, w1, w2, sink=None):
+    """sink = [gW1, gb1, gW2, gb2] (entries may be None): see transition_backward."""
     zin, hidp, y2, wd1, wd2 = saved
     dev = dr.device
     B, co, H, W = y2.shape
@@ -337,6 +381,13 @@ def reward_backward(dr, saved, w1, w2):
     flat = torch.zeros(n1 + n2 + HID + 16, dtype=torch.float32, device=dev)
     g1, g2 = flat[:n1].view(w1.shape), flat[n1:n1 + n2].view(w2.shape)
     db1, db2 = flat[n1 + n2:n1 + n2 + HID], flat[n1 + n2 + HID:]
+    sink = list(sink) if sink is not None else [None] * 4
+    if sink[0] is not None:
+        g1 = sink[0]
+    if sink[1] is not None:   # RHID = 32 valid channels are written
+        db1 = sink[1]
+    if sink[2] is not None:
+        g2 = sink[2]
     d2 = K.new_plane(B, H, W, 16, dev)
     K.reward_head_bwd(y2, dr, R, d2)
     K.wgrad(d2, hidp, g2, B, H, W, cout=16, cin=HID, g_s_co=RHID * 9, g_s_ci=9, co_valid=co, ci_valid=RHID)
@@ -346,4 +397,7 @@ def reward_backward(dr, saved, w1, w2):
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True)
-    return dz, g1.clone(), db1[:RHID].clone(), g2.clone(), db2[:co].clone()
+    if sink[3] is not None:
+        sink[3].add_(db2[:co])
+    return (dz, g1.clone() if sink[0] is None else None, db1[:RHID].clone() if sink[1] is None else None,
+            g2.clone() if sink[2] is None else None, db2[:co].clone() if sink[3] is None else None)

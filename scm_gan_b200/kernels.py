@@ -128,12 +128,13 @@ def spectral_norm_fwd(layers):
 
 
 def spectral_norm_bwd(layers):
-    """layers: list of (g, wbar, u, v, sigma, dot, out)."""
+    """layers: list of (g, wbar, u, v, sigma, dot, out[, accumulate])."""
     arr = (L.SnBwdLayer * len(layers))()
-    for i, (g, w, u, v, s, dot, out) in enumerate(layers):
+    for i, lay in enumerate(layers):
+        g, w, u, v, s, dot, out = lay[:7]
         rows = w.shape[0]
         arr[i] = L.SnBwdLayer(g.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), s.data_ptr(), dot.data_ptr(),
-                              out.data_ptr(), rows, w.numel() // rows)
+                              out.data_ptr(), rows, w.numel() // rows, int(bool(lay[7])) if len(lay) > 7 else 0)
     L.check(L.lib().scmgan_spectral_norm_bwd(len(layers), arr, _stream()), "scmgan_spectral_norm_bwd")
 
 

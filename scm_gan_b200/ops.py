@@ -3,6 +3,7 @@
 One forward op and one backward op per network; the bodies only sequence hand-written kernels
 (scm_gan_b200.engine).  There is no eager/CPU fallback: calling any op with non-CUDA tensors raises.
 """
+import weakref
 from typing import List, Optional, Sequence
 
 import torch
@@ -16,6 +17,56 @@ from . import kernels as K
 # The power-iteration vectors are module state read at *backward* time (reference semantics), so they travel
 # beside the op instead of through its functional signature.
 _UV_SOURCE = []
+
+
+# Gradient sinks: parameter storage address -> (gradient buffer, callback, parameter).  When a parameter of a differentiable scmgan op has
+# a sink, the backward kernels ADD its gradient straight into the buffer (normally the parameter's .grad), autograd
+# receives None for it, and `callback(parameter)` runs in place of the post-accumulate-grad hook.  The weights of
+# the world model are shared by every unrolled step (reference main.py:162-215), so without sinks autograd launches
+# one elementwise add per parameter and step.  Registered by scm_gan_b200.train_step.Trainer; off by default.
+_GRAD_SINK = {}
+
+
+def register_grad_sink(param, grad, callback=None):
+    assert grad.shape == param.shape and grad.dtype == torch.float32 and grad.is_contiguous()
+    _GRAD_SINK[param.data_ptr()] = (grad, callback, weakref.ref(param))
+
+
+def clear_grad_sinks():
+    _GRAD_SINK.clear()
+
+
+def _sinks_of(params):
+    """-> (present sink buffers, bit mask over `params`)."""
+    bufs, mask = [], 0
+    for i, p in enumerate(params):
+        s = _GRAD_SINK.get(p.data_ptr()) if _GRAD_SINK else None
+        if s is not None and s[2]() is None:   # the registering parameter died: its address may have been reused
+            del _GRAD_SINK[p.data_ptr()]
+            s = None
+        if s is not None and s[0].shape == p.shape:
+            bufs.append(s[0])
+            mask |= 1 << i
+    return bufs, mask
+
+
+def _expand_sinks(sinks, mask, n):
+    it = iter(sinks)
+    return [next(it) if (mask >> i) & 1 else None for i in range(n)]
+
+
+def _merge(outs, mask, n):
+    """Re-insert None for the sunk slots into the op's compacted output list."""
+    it = iter(outs)
+    return [None if (mask >> i) & 1 else next(it) for i in range(n)]
+
+
+def _notify(params, mask):
+    for i, p in enumerate(params):
+        if (mask >> i) & 1:
+            _, cb, ref = _GRAD_SINK[p.data_ptr()]
+            if cb is not None:
+                cb(ref())
 
 
 def _require_cuda(*ts):
@@ -51,13 +102,18 @@ def transition_fwd(z: Tensor, a: Tensor, wbar: Sequence[Tensor], bias: Sequence[
     return [zn, p] + saved
 
 
-@torch.library.custom_op("scmgan::transition_bwd", mutates_args=())
+@torch.library.custom_op("scmgan::transition_bwd", mutates_args=("sinks",))
 def transition_bwd(dz_next: Tensor, p: Tensor, a: Tensor, saved: Sequence[Tensor], wbar: Sequence[Tensor],
-                   sigma: Tensor, u: Sequence[Tensor], v: Sequence[Tensor], w6: Tensor) -> List[Tensor]:
+                   sigma: Tensor, u: Sequence[Tensor], v: Sequence[Tensor], w6: Tensor, sinks: Sequence[Tensor],
+                   sink_mask: int) -> List[Tensor]:
+    """Returns [dz] + the parameter gradients (dWbar1..5, db1..5, dW6, db6) whose bit in sink_mask is clear; the
+    others are added into `sinks`."""
     _require_cuda(dz_next)
+    n = len(wbar)
     dz, dwbar, db, dw6, db6 = E.transition_backward(dz_next.contiguous().float(), p, a.contiguous().float(),
-                                                    list(saved), list(wbar), sigma, list(u), list(v), w6)
-    return [dz] + dwbar + db + [dw6, db6]
+                                                    list(saved), list(wbar), sigma, list(u), list(v), w6,
+                                                    _expand_sinks(sinks, sink_mask, 2 * n + 2))
+    return [dz] + [t for t in dwbar + db + [dw6, db6] if t is not None]
 
 
 def _transition_setup(ctx, inputs, output):
@@ -66,6 +122,7 @@ def _transition_setup(ctx, inputs, output):
     ctx.training = training
     ctx.a, ctx.sigma = a, sigma
     ctx.wbar, ctx.w6 = list(wbar), w6
+    ctx.bias, ctx.b6 = list(bias), b6
     ctx.nw = len(wbar)
     # u, v are attached by the calling module (ctx.uv_source) and deliberately NOT saved with version tracking:
     # the reference's backward reads whatever u, v the module holds at backward time.
@@ -81,12 +138,14 @@ def _transition_backward(ctx, grads):
     if dz_next is None or not ctx.training:
         return (None,) * 9
     u, v = ctx.uv
-    out = torch.ops.scmgan.transition_bwd(dz_next, p, ctx.a, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w6)
+    params = ctx.wbar + ctx.bias + [ctx.w6, ctx.b6]
+    sinks, mask = _sinks_of(params)
+    out = torch.ops.scmgan.transition_bwd(dz_next, p, ctx.a, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w6,
+                                          sinks, mask)
     dz = out[0]
-    dwbar = list(out[1:1 + n])
-    db = list(out[1 + n:1 + 2 * n])
-    dw6, db6 = out[1 + 2 * n], out[2 + 2 * n]
-    return dz, None, dwbar, db, None, dw6, db6, None, None
+    g = _merge(out[1:], mask, 2 * n + 2)
+    _notify(params, mask)
+    return dz, None, g[:n], g[n:2 * n], None, g[2 * n], g[2 * n + 1], None, None
 
 
 transition_fwd.register_autograd(_transition_backward, setup_context=_transition_setup)
@@ -106,19 +165,23 @@ def encoder_fwd(x: Tensor, wbar: Sequence[Tensor], bias: Sequence[Tensor], sigma
     return [z] + saved
 
 
-@torch.library.custom_op("scmgan::encoder_bwd", mutates_args=())
+@torch.library.custom_op("scmgan::encoder_bwd", mutates_args=("sinks",))
 def encoder_bwd(dz: Tensor, z: Tensor, saved: Sequence[Tensor], wbar: Sequence[Tensor], sigma: Tensor,
-                u: Sequence[Tensor], v: Sequence[Tensor], w4: Tensor) -> List[Tensor]:
+                u: Sequence[Tensor], v: Sequence[Tensor], w4: Tensor, sinks: Sequence[Tensor],
+                sink_mask: int) -> List[Tensor]:
+    """Returns the parameter gradients (dWbar1..3, db1..3, dW4, db4) whose bit in sink_mask is clear."""
     _require_cuda(dz)
+    n = len(wbar)
     dwbar, db, dw4, db4 = E.encoder_backward(dz.contiguous().float(), z, list(saved), list(wbar), sigma, list(u),
-                                             list(v), w4)
-    return dwbar + db + [dw4, db4]
+                                             list(v), w4, _expand_sinks(sinks, sink_mask, 2 * n + 2))
+    return [t for t in dwbar + db + [dw4, db4] if t is not None]
 
 
 def _encoder_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     x, wbar, bias, sigma, w4, b4 = inputs
     ctx.wbar, ctx.sigma, ctx.w4 = list(wbar), sigma, w4
+    ctx.bias, ctx.b4 = list(bias), b4
     ctx.nw = len(wbar)
     ctx.uv = _UV_SOURCE.pop()
     ctx.save_for_backward(*output)
@@ -131,8 +194,12 @@ def _encoder_backward(ctx, grads):
         return (None,) * 6
     n = ctx.nw
     u, v = ctx.uv
-    out = torch.ops.scmgan.encoder_bwd(grads[0], z, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w4)
-    return None, list(out[:n]), list(out[n:2 * n]), None, out[2 * n], out[2 * n + 1]
+    params = ctx.wbar + ctx.bias + [ctx.w4, ctx.b4]
+    sinks, mask = _sinks_of(params)
+    out = torch.ops.scmgan.encoder_bwd(grads[0], z, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w4, sinks, mask)
+    g = _merge(out, mask, 2 * n + 2)
+    _notify(params, mask)
+    return None, g[:n], g[n:2 * n], None, g[2 * n], g[2 * n + 1]
 
 
 encoder_fwd.register_autograd(_encoder_backward, setup_context=_encoder_setup)
@@ -148,24 +215,32 @@ def decoder_fwd(z: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Li
     return [logits] + saved
 
 
-@torch.library.custom_op("scmgan::decoder_bwd", mutates_args=())
-def decoder_bwd(dlogits: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor) -> List[Tensor]:
+@torch.library.custom_op("scmgan::decoder_bwd", mutates_args=("sinks",))
+def decoder_bwd(dlogits: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor, sinks: Sequence[Tensor],
+                sink_mask: int) -> List[Tensor]:
+    """Returns [dz] + the parameter gradients (dW1, db1, dW2, db2) whose bit in sink_mask is clear."""
     _require_cuda(dlogits)
-    return list(E.decoder_backward(dlogits.contiguous().float(), list(saved), w1, w2.contiguous()))
+    out = E.decoder_backward(dlogits.contiguous().float(), list(saved), w1, w2.contiguous(),
+                             _expand_sinks(sinks, sink_mask, 4))
+    return [t for t in out if t is not None]
 
 
 def _decoder_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     z, w1, b1, w2, b2 = inputs
     ctx.w1, ctx.w2 = w1, w2
+    ctx.params = [w1, b1, w2, b2]
     ctx.save_for_backward(*output[1:])
 
 
 def _decoder_backward(ctx, grads):
     if grads[0] is None:
         return (None,) * 5
-    dz, g1, db1, g2, db2 = torch.ops.scmgan.decoder_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2)
-    return dz, g1, db1, g2, db2
+    sinks, mask = _sinks_of(ctx.params)
+    out = torch.ops.scmgan.decoder_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2, sinks, mask)
+    g = _merge(out[1:], mask, 4)
+    _notify(ctx.params, mask)
+    return (out[0], *g)
 
 
 decoder_fwd.register_autograd(_decoder_backward, setup_context=_decoder_setup)
@@ -211,24 +286,31 @@ def reward_fwd(z: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor) -> Lis
     return [r, rmap] + saved
 
 
-@torch.library.custom_op("scmgan::reward_bwd", mutates_args=())
-def reward_bwd(dr: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor) -> List[Tensor]:
+@torch.library.custom_op("scmgan::reward_bwd", mutates_args=("sinks",))
+def reward_bwd(dr: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor, sinks: Sequence[Tensor],
+               sink_mask: int) -> List[Tensor]:
+    """Returns [dz] + the parameter gradients (dW1, db1, dW2, db2) whose bit in sink_mask is clear."""
     _require_cuda(dr)
-    return list(E.reward_backward(dr.contiguous().float(), list(saved), w1, w2))
+    out = E.reward_backward(dr.contiguous().float(), list(saved), w1, w2, _expand_sinks(sinks, sink_mask, 4))
+    return [t for t in out if t is not None]
 
 
 def _reward_setup(ctx, inputs, output):
     ctx.set_materialize_grads(False)  # the saved bf16 planes are outputs too: never build zero grads for them
     z, w1, b1, w2, b2 = inputs
     ctx.w1, ctx.w2 = w1, w2
+    ctx.params = [w1, b1, w2, b2]
     ctx.save_for_backward(*output[2:])
 
 
 def _reward_backward(ctx, grads):
     if grads[0] is None:
         return (None,) * 5
-    dz, g1, db1, g2, db2 = torch.ops.scmgan.reward_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2)
-    return dz, g1, db1, g2, db2
+    sinks, mask = _sinks_of(ctx.params)
+    out = torch.ops.scmgan.reward_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2, sinks, mask)
+    g = _merge(out[1:], mask, 4)
+    _notify(ctx.params, mask)
+    return (out[0], *g)
 
 
 reward_fwd.register_autograd(_reward_backward, setup_context=_reward_setup)

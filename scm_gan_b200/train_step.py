@@ -158,9 +158,15 @@ class Trainer:
         # torch.optim.Adam counts steps per parameter and skips parameters without a gradient; gradients appear
         # per network (e.g. Transition gets none at horizon 3), so one counter per network reproduces it.
         self.step_dev = torch.zeros(len(self.NET_ORDER), dtype=torch.float32, device=dev)
+        # all gradients are views into one flat buffer (one memset per iteration); the backward kernels add into
+        # them directly (ops.register_grad_sink), autograd's own accumulation remains for whatever they do not cover
+        self.flat_grad = torch.zeros(sum(p.numel() for p, _ in self.groups), dtype=torch.float32, device=dev)
+        off = 0
         for p, _ in self.groups:
-            p.grad = torch.zeros_like(p)
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
             p.register_post_accumulate_grad_hook(self._on_grad)
+        self.register_sinks()
         try:  # gradients are accumulated on whichever stream runs backward (side stream during graph warm-up)
             torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
         except AttributeError:
@@ -176,6 +182,12 @@ class Trainer:
     def params(self):
         return [p for p, _ in self.groups]
 
+    def register_sinks(self):
+        """(Re-)point the backward kernels at the current .grad buffers (dp.BucketedGradSync re-homes them)."""
+        from . import ops
+        for p, _ in self.groups:
+            ops.register_grad_sink(p, p.grad, self._on_grad)
+
     def _on_grad(self, p):
         if self._counting:
             self._counts[id(p)] = self._counts.get(id(p), 0) + 1
@@ -186,8 +198,7 @@ class Trainer:
         if self.sync is not None:
             self.sync.zero()
             return
-        for p, _ in self.groups:
-            p.grad.zero_()
+        self.flat_grad.zero_()
 
     def _loss(self, batch, theta, cf_now):
         loss, _ = rollout_loss(self.nets, batch["states"], batch["rewards"], batch["dones"], batch["actions"],
