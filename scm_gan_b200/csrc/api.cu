@@ -715,6 +715,35 @@ int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_st
         L.layer[i] = SnLayer{s.w, s.u, s.v, s.sigma, s.u_save, s.v_save, s.rows, s.cols};
         max_smem = std::max(max_smem, int((s.rows + s.cols + 64) * sizeof(float)));
     }
+    // cluster kernel when every layer's column slice fits one 1024-thread pass
+    {
+        SnClusterGeom Gm;
+        memset(&Gm, 0, sizeof(Gm));
+        bool ok = true;
+        static const char* off = getenv("SCMGAN_SN_SINGLE_CTA");
+        if (off && atoi(off)) ok = false;
+        int gmax = 1;
+        for (int i = 0; i < count && ok; ++i) {
+            const int cpc = (layers[i].cols + kSnCluster - 1) / kSnCluster;
+            const int cpcp = (cpc + 31) & ~31;
+            if (cpcp > 1024 || layers[i].rows > 1024) { ok = false; break; }
+            Gm.cpc[i] = cpc;
+            Gm.groups[i] = std::max(1, std::min(std::min(16, layers[i].rows), 1024 / cpcp));
+            gmax = std::max(gmax, Gm.groups[i]);
+            Gm.cpc_max = std::max(Gm.cpc_max, cpc);
+            Gm.rows_max = std::max(Gm.rows_max, layers[i].rows);
+        }
+        if (ok) {
+            const int smem = int(sizeof(float)) * (Gm.rows_max * (2 + kSnCluster) + Gm.cpc_max * (1 + gmax) +
+                                                   kSnCluster + 33);
+            if (smem <= 48 * 1024) {
+                sn_power_iter_cluster_kernel<<<count * kSnCluster, 1024, smem, (cudaStream_t)stream>>>(L, Gm);
+                SCM_CUDA(cudaGetLastError());
+                ++g_launches;
+                return SCM_OK;
+            }
+        }
+    }
     SCM_REQUIRE(max_smem <= 48 * 1024, "spectral_norm_fwd: layer too large");
     sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
