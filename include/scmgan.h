@@ -97,6 +97,13 @@ typedef struct {
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 
+/* out[i] = uniform in (0,1) number i of the Philox4x32-10 stream {seed, offset} held in rng_state (element i uses
+ * counter offset + i/4, lane i%4: the very numbers the in-kernel Bernoulli head of scmgan_conv3x3_fwd draws for
+ * element i), then offset += ceil(n/4).  Feeds `uniforms` of the Transition's last conv: generating the stream in
+ * its own pass (all four outputs of every Philox block used, full-chip parallelism) is ~10x cheaper than inside the
+ * conv epilogue.  Replaces torch.rand_like of DifferentiableBernoulliSampler, reference models.py:27-31. */
+int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream);
+
 /* Weight gradient: g[co*g_s_co + ci*g_s_ci + tap'*g_s_tap] += scale * sum_interior dy[p][co] * x[p+tap][ci],
  * tap' = flip ? 8-tap : tap.  g is fp32 and must be pre-initialised (atomically accumulated into).
  * Replaces cuDNN wgrad under loss.backward() (reference main.py:285). */

@@ -29,3 +29,13 @@ n = sum(e.count for e in rows)
 print(f"total device time {tot / 1e3:.3f} ms over {n} kernels/memops")
 for e in rows[:40]:
     print(f"{e.device_time_total / 1e3:8.3f} ms {100 * e.device_time_total / tot:5.1f}% n={e.count:4d} avg={e.device_time_total / e.count:7.1f} us  {e.key[:100]}")
+
+if "--seq" in sys.argv:
+    # per-launch durations in launch order (our kernels only), to tell forward / dgrad / wgrad instances apart
+    evs = [e for e in prof.events() if e.device_type.name == "CUDA" and "scm::" in e.name]
+    evs.sort(key=lambda e: e.time_range.start)
+    line = []
+    for e in evs:
+        short = e.name.split("scm::")[1].split("(")[0].replace("conv3x3_", "").replace("_kernel", "")
+        line.append(f"{short}:{e.device_time:.0f}")
+    print(" ".join(line))

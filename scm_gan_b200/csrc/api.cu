@@ -871,6 +871,18 @@ int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, 
     return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss_scratch, dx, stream);
 }
 
+int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream) {
+    SCM_REQUIRE(out && rng_state && n > 0, "philox_uniform: bad arguments");
+    const long long blocks4 = (n + 3) / 4;
+    philox_fill_kernel<<<unsigned((blocks4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rng_state);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state, (unsigned long long)blocks4);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float beta1, float beta2, float eps,
                      int step, const float* step_dev, float gscale, scmgan_stream_t stream) {
     SCM_REQUIRE(count >= 0 && (count == 0 || chunks), "clip_adam: bad arguments");

@@ -239,7 +239,9 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             mbar_wait(&acc_full[acc], acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
-            if (P.out_f32)
+            if (P.out_f32 && !P.out && G.n_cta == 16)
+                igemm_epilogue_tile<8, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+            else if (P.out_f32)
                 igemm_epilogue_tile<16, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
             else if ((G.n_cta & 31) == 0)
                 igemm_epilogue_tile<32, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);

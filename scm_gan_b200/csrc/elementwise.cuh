@@ -638,6 +638,33 @@ __global__ void transition_tail_kernel(const float* __restrict__ x, const float*
     }
 }
 
+// uniforms of the Philox stream as a tensor: thread t evaluates block (offset + t) once and writes its four outputs
+__global__ void philox_fill_kernel(float* __restrict__ out, long long n, const unsigned long long* __restrict__ rng) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long i0 = t * 4;
+    if (i0 >= n) return;
+    const unsigned long long seed = __ldg(rng), ctr = __ldg(rng + 1) + (unsigned long long)t;
+    uint32_t c0 = uint32_t(ctr), c1 = uint32_t(ctr >> 32), c2 = 0u, c3 = 0u;
+    uint32_t k0 = uint32_t(seed), k1 = uint32_t(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    const float s = 1.0f / 16777216.0f;
+    const float4 u = make_float4((float(c0 >> 8) + 0.5f) * s, (float(c1 >> 8) + 0.5f) * s,
+                                 (float(c2 >> 8) + 0.5f) * s, (float(c3 >> 8) + 0.5f) * s);
+    if (i0 + 3 < n && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        reinterpret_cast<float4*>(out)[t] = u;
+    } else {
+        const float v[4] = {u.x, u.y, u.z, u.w};
+        for (int j = 0; j < 4 && i0 + j < n; ++j) out[i0 + j] = v[j];
+    }
+}
+
 // advance the device-side Philox offset after a sampling launch (keeps the whole step CUDA-graph replayable)
 __global__ void rng_advance_kernel(unsigned long long* rng, unsigned long long n) { rng[1] += n; }
 

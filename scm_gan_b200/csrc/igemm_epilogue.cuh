@@ -28,6 +28,10 @@ __device__ __forceinline__ void epi_reg_fence16(float* v) {
                       "+f"(v[15]));
 }
 
+__device__ __forceinline__ void epi_reg_fence8(float* v) {
+    asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
+}
+
 struct EpiRow {
     int p, b, hp, wp;
     bool valid, interior;
@@ -49,12 +53,14 @@ __device__ __forceinline__ EpiRow epi_decode_row(const IgemmParams& P, int p) {
     return r;
 }
 
-// GROUP: columns per pass (32, or 16 when the CTA's N slice is not a multiple of 32 / shared memory is tight).
+// GROUP: columns per pass (32; 16 when the CTA's N slice is not a multiple of 32; 8 for the 16-column fp32 heads so
+// that both warps of a lane quarter have work - only without a bf16 plane output, whose stores are 16 columns wide).
 // F32: the fp32 NCHW / Bernoulli-head output is compiled in (only the narrow N = 16 heads use it; keeping it out of
 // the wide instantiations keeps the hot loop small enough for the instruction cache).
 template <int GROUP, bool F32>
 __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_total, int n0, int ncols_cta, int p,
                                                     int half, int lane, uint32_t taddr, const float* s_bias) {
+    static_assert(GROUP == 8 || GROUP == 16 || GROUP == 32, "unsupported column group");
     constexpr int CH = GROUP / 8;       // 16-byte chunks per row segment
     const EpiRow R = epi_decode_row(P, p);
     const int plane = P.Hp * P.Wp;
@@ -79,12 +85,20 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
     // TMEM reads are double-buffered: the tcgen05.ld of the warp's next column group is in flight while the current
     // group goes through the arithmetic and the stores (the epilogue is latency-bound, not issue-bound).
     auto load = [&](float (&v)[GROUP], int c0) {
-        tmem_ld16(taddr + uint32_t(c0), v);
-        if (GROUP == 32) tmem_ld16(taddr + uint32_t(c0 + 16), v + (GROUP == 32 ? 16 : 0));
+        if constexpr (GROUP == 8) {
+            tmem_ld8(taddr + uint32_t(c0), v);
+        } else {
+            tmem_ld16(taddr + uint32_t(c0), v);
+            if constexpr (GROUP == 32) tmem_ld16(taddr + uint32_t(c0 + 16), v + 16);
+        }
     };
     auto process = [&](float (&v)[GROUP], int c0) {
-        epi_reg_fence16(v);
-        if (GROUP == 32) epi_reg_fence16(v + (GROUP == 32 ? 16 : 0));
+        if constexpr (GROUP == 8) {
+            epi_reg_fence8(v);
+        } else {
+            epi_reg_fence16(v);
+            if constexpr (GROUP == 32) epi_reg_fence16(v + 16);
+        }
         if (P.debug & 1) return;
         {
 #pragma unroll

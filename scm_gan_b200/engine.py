@@ -103,9 +103,13 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     p = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     zn = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     b6p = b6 if Lp == L else torch.nn.functional.pad(b6, (0, Lp - L))
+    if training and uniforms is None and rng_state is not None:
+        # the module's Philox stream, generated in its own pass (same numbers as the in-kernel head would draw,
+        # ~10x cheaper than evaluating Philox inside the conv epilogue)
+        uniforms = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
+        K.philox_uniform(uniforms, rng_state)
     K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6p, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
-              uniforms=uniforms if training else None,
-              rng_state=rng_state if (training and uniforms is None) else None)                     # conv6 + head
+              uniforms=uniforms if training else None)                                              # conv6 + head
     return zn, p, [zin, buf6, buf5, act3] + wd
 
 

@@ -138,6 +138,12 @@ def spectral_norm_bwd(layers):
     L.check(L.lib().scmgan_spectral_norm_bwd(len(layers), arr, _stream()), "scmgan_spectral_norm_bwd")
 
 
+def philox_uniform(out, rng_state):
+    """out (fp32, contiguous) <- the next out.numel() uniforms of the device Philox stream rng_state (int64 [2])."""
+    L.check(L.lib().scmgan_philox_uniform(out.data_ptr(), out.numel(), rng_state.data_ptr(), _stream()),
+            "scmgan_philox_uniform")
+
+
 def action_bias(wbar, sigma, bias, act, latent, out):
     B, A = act.shape
     cout = wbar.shape[0]

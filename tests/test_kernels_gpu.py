@@ -431,3 +431,33 @@ def test_in_kernel_philox_bernoulli():
     assert torch.equal(z1, z3)
     _, z4 = draw(torch.tensor([99, 0], dtype=torch.int64, device=DEV))
     assert not torch.equal(z1, z4)
+
+
+def test_philox_uniform_stream_matches_in_kernel_head():
+    """scmgan_philox_uniform writes the very uniforms the in-kernel Bernoulli head draws: sampling with the filled
+    tensor passed as `uniforms` is bit-identical to sampling with `rng_state`, and the offsets advance alike."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    torch.manual_seed(10)
+    B, H, W, Ci, Co = 4, 16, 16, 64, 16
+    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (1.5 * Ci ** 0.5))
+    xp = make_plane(x, Ci, 0, True)
+    wp = pack_conv_weight(w, Co, Ci)
+    s_a = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
+    s_b = s_a.clone()
+    p1, z1 = torch.empty(B, Co, H, W, device=DEV), torch.empty(B, Co, H, W, device=DEV)
+    K.conv3x3(xp, wp, B, H, W, cin=Ci, act=2, out_f32=p1, n_valid=Co, sample_out=z1, rng_state=s_a)
+    u = torch.empty(B, Co, H, W, device=DEV)
+    K.philox_uniform(u, s_b)
+    assert s_a.tolist() == s_b.tolist()
+    assert 0.0 < u.min().item() and u.max().item() < 1.0
+    assert abs(u.mean().item() - 0.5) < 4 * (1 / 12) ** 0.5 / u.numel() ** 0.5
+    p2, z2 = torch.empty_like(p1), torch.empty_like(z1)
+    K.conv3x3(xp, wp, B, H, W, cin=Ci, act=2, out_f32=p2, n_valid=Co, sample_out=z2, uniforms=u)
+    assert torch.equal(p1, p2) and torch.equal(z1, z2)
+    # odd length: the tail of the last Philox block is dropped, the offset still advances by whole blocks
+    v = torch.empty(10, device=DEV)
+    s_c = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
+    K.philox_uniform(v, s_c)
+    assert torch.equal(v, u.flatten()[:10]) and s_c.tolist() == [77, 8]
