@@ -51,7 +51,10 @@ int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int 
 
 /* Weight packing fp32 parameter -> bf16 [9][n_pad][k_pad] GEMM operand, optionally divided by *sigma
  * (the `w / sigma` of reference spectral_normalization.py:35).
- *   out[tap][n][k] = w[n*s_n + (k+k_src_off)*s_k + (flip ? 8-tap : tap)] / sigma */
+ *   out[tap][n][k] = w[n*s_n + (k+k_src_off)*s_k + (flip ? 8-tap : tap)] / sigma
+ * out_ld (elements, 0 = k_pad) is the row pitch of `out`: with out_ld > k_pad the job fills a K window of a wider
+ * operand [9][n_pad][out_ld], so that the gradients of two convolutions reading the same activation (the skip
+ * connections of reference models.py:95,101) become ONE dgrad GEMM over concatenated K. */
 typedef struct {
     const float* w;
     void* out;
@@ -60,6 +63,7 @@ typedef struct {
     long long s_n, s_k;
     int k_src_off;
     int flip;
+    int out_ld;
 } scmgan_pack_job;
 int scmgan_pack_weights(int count, const scmgan_pack_job* jobs_host, scmgan_stream_t stream);
 

@@ -17,7 +17,8 @@ c_f32p = C.c_void_p  # device pointers travel as integers
 class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("sigma", C.c_void_p),
                 ("n_pad", C.c_int), ("k_pad", C.c_int), ("n_valid", C.c_int), ("k_valid", C.c_int),
-                ("s_n", C.c_longlong), ("s_k", C.c_longlong), ("k_src_off", C.c_int), ("flip", C.c_int)]
+                ("s_n", C.c_longlong), ("s_k", C.c_longlong), ("k_src_off", C.c_int), ("flip", C.c_int),
+                ("out_ld", C.c_int)]
 
 
 class ConvDesc(C.Structure):

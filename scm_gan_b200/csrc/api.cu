@@ -597,6 +597,8 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t 
             d.w = s.w; d.out = reinterpret_cast<__nv_bfloat16*>(s.out); d.sigma = s.sigma;
             d.n_pad = s.n_pad; d.k_pad = s.k_pad; d.n_valid = s.n_valid; d.k_valid = s.k_valid;
             d.s_n = s.s_n; d.s_k = s.s_k; d.k_src_off = s.k_src_off; d.flip = s.flip;
+            SCM_REQUIRE(s.out_ld == 0 || s.out_ld >= s.k_pad, "pack_weights: job %d: out_ld < k_pad", base + i);
+            d.out_ld = s.out_ld ? s.out_ld : s.k_pad;
             max_total = std::max(max_total, 9LL * s.n_pad * s.k_pad);
         }
         const int threads = 256;

@@ -65,6 +65,7 @@ struct PackJob {
     long long s_n, s_k;
     int k_src_off;  // first source k (e.g. skip nothing: 0)
     int flip;
+    int out_ld;     // row pitch of out in elements (>= k_pad)
 };
 constexpr int kMaxPackJobs = 16;
 struct PackJobs {
@@ -85,7 +86,7 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
         float x = 0.f;
         if (n < J.n_valid && k < J.k_valid)
             x = __ldg(J.w + n * J.s_n + (long long)(k + J.k_src_off) * J.s_k + (J.flip ? 8 - tap : tap)) * inv;
-        J.out[i] = __float2bfloat16_rn(x);
+        J.out[r * J.out_ld + k] = __float2bfloat16_rn(x);
     }
 }
 

@@ -74,16 +74,24 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     # packed operands: forward [9][Cout][Cin] and dgrad [9][Cin][Cout] (1/sigma folded in)
     wf = [K.packed_weight(HID, Lp, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
           K.packed_weight(HID, HID, dev), K.packed_weight(HID, 2 * HID, dev), K.packed_weight(Lp, 2 * HID, dev)]
-    wd = [K.packed_weight(Lp, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
-          K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
-          K.packed_weight(HID, Lp, dev), K.packed_weight(HID, Lp, dev)]
+    # dgrad operands.  The two gradients that meet at a skip connection are one GEMM over concatenated K:
+    #   d act2 = [d pre3 | d pre5] x [Wd3 ; Wd5(skip half)]     (K = 128 + 128)
+    #   d act1 = [d pre2 | d pre6] x [Wd2 ; Wd6(skip half)]     (K = 128 + 64, the 16 latent gradients zero-padded)
+    LS = 64  # channel slot of d pre6 inside the [d pre2 | d pre6] plane
+    assert Lp <= LS
+    wd = [K.packed_weight(Lp, HID, dev), K.packed_weight(HID, HID + LS, dev), K.packed_weight(HID, 2 * HID, dev),
+          K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, Lp, dev)]
     jobs = [_conv2d_fwd_job(wbar[0], wf[0], sigma[0:1], k_valid=L)]
     jobs += [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(1, 5)]
     jobs += [_conv2d_fwd_job(w6, wf[5])]
     jobs += [_conv2d_dgrad_job(wbar[0], wd[0], sigma[0:1], 0, L)]
-    jobs += [_conv2d_dgrad_job(wbar[i], wd[i], sigma[i:i + 1]) for i in range(1, 4)]
-    jobs += [_conv2d_dgrad_job(wbar[4], wd[4], sigma[4:5], 0, HID), _conv2d_dgrad_job(wbar[4], wd[5], sigma[4:5], HID, HID)]
-    jobs += [_conv2d_dgrad_job(w6, wd[6], None, 0, HID, co_valid=L), _conv2d_dgrad_job(w6, wd[7], None, HID, HID, co_valid=L)]
+    jobs += [_conv2d_dgrad_job(wbar[1], wd[1][:, :, :HID], sigma[1:2]),                       # conv2
+             _conv2d_dgrad_job(w6, wd[1][:, :, HID:], None, HID, HID, co_valid=L)]              # conv6, skip half
+    jobs += [_conv2d_dgrad_job(wbar[2], wd[2][:, :, :HID], sigma[2:3]),                       # conv3
+             _conv2d_dgrad_job(wbar[4], wd[2][:, :, HID:], sigma[4:5], HID, HID)]               # conv5, skip half
+    jobs += [_conv2d_dgrad_job(wbar[3], wd[3], sigma[3:4])]                                   # conv4
+    jobs += [_conv2d_dgrad_job(wbar[4], wd[4], sigma[4:5], 0, HID)]                           # conv5, act4 half
+    jobs += [_conv2d_dgrad_job(w6, wd[5], None, 0, HID, co_valid=L)]                          # conv6, act5 half
     K.pack_weights(jobs)
 
     sbias = torch.empty((B, HID), dtype=torch.float32, device=dev)
@@ -148,31 +156,29 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     if gb6 is not None and Lp == L:
         db6 = gb6
 
+    # Gradient planes.  DB = [d pre2 | d pre6 (Lp channels, zero-padded to LS)], DA = [d pre3 | d pre5]: each pair is
+    # the K-concatenated input of one dgrad GEMM (see transition_forward), so the partial sums of the skip
+    # connections never go through memory.
+    LS = wd[1].shape[2] - HID
+    DB = K.new_plane(B, H, W, HID + LS, dev)
+    DA = K.new_plane(B, H, W, 2 * HID, dev)
     # d pre-activation of conv6: dz * p * (1 - p)
-    d6 = K.new_plane(B, H, W, Lp, dev)
-    K.pack_nchw(dz_next, d6, wrap=True, sig=p)
+    K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
-    K.wgrad(d6, buf6, G[5], B, H, W, cout=Lp, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L)
-    K.plane_colsum(d6, 0, Lp, B, H, W, db=db6)
+    K.wgrad(DB, buf6, G[5], B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L)
+    K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
-    d5 = K.new_plane(B, H, W, HID, dev)
-    d1part = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(d6, wd[6], B, H, W, cin=Lp, out=d5, gate=buf6, gate_c_off=0, **dg)        # d act5 -> d pre5
-    K.conv3x3(d6, wd[7], B, H, W, cin=Lp, out=d1part, **dg)                             # d skip1 (partial)
-    K.wgrad(d5, buf5, G[4], B, H, W, cout=HID, cin=cin6, g_s_co=cin6 * 9, g_s_ci=9, db=db[4])
+    K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0, **dg)  # d pre5
+    K.wgrad(DA, buf5, G[4], B, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, db=db[4])
     d4 = K.new_plane(B, H, W, HID, dev)
-    d2part = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(d5, wd[4], B, H, W, cin=HID, out=d4, gate=buf5, gate_c_off=0, **dg)       # d act4 -> d pre4
-    K.conv3x3(d5, wd[5], B, H, W, cin=HID, out=d2part, **dg)                            # d skip2 (partial)
+    K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, **dg)              # d pre4
     K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[3])
-    d3 = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=d3, gate=act3, **dg)
-    K.wgrad(d3, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
-    d2 = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(d3, wd[2], B, H, W, cin=HID, out=d2, add=d2part, gate=buf5, gate_c_off=HID, **dg)
-    K.wgrad(d2, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
+    K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, **dg)                            # d pre3
+    K.wgrad(DA, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
+    K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, **dg)        # d pre2
+    K.wgrad(DB, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
     d1 = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(d2, wd[1], B, H, W, cin=HID, out=d1, add=d1part, gate=buf6, gate_c_off=HID, **dg)
+    K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, **dg)                    # d pre1
     c1 = L + A
     K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L)
     K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])

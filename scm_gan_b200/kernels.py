@@ -42,11 +42,15 @@ def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False, sig=None):
 
 
 def pack_weights(jobs):
-    """jobs: list of dicts(w, out, sigma, n_pad, k_pad, n_valid, k_valid, s_n, s_k, k_src_off, flip)."""
+    """jobs: list of dicts(w, out, sigma, n_pad, k_pad, n_valid, k_valid, s_n, s_k, k_src_off, flip); `out` may be a
+    K window (a [:, :, a:b] view) of a wider packed operand."""
     arr = (L.PackJob * len(jobs))()
     for i, j in enumerate(jobs):
-        arr[i] = L.PackJob(j["w"].data_ptr(), j["out"].data_ptr(), L.ptr(j.get("sigma")), j["n_pad"], j["k_pad"],
-                           j["n_valid"], j["k_valid"], j["s_n"], j["s_k"], j.get("k_src_off", 0), j.get("flip", 0))
+        out = j["out"]
+        assert out.stride(2) == 1 and out.stride(0) == out.shape[1] * out.stride(1)
+        arr[i] = L.PackJob(j["w"].data_ptr(), out.data_ptr(), L.ptr(j.get("sigma")), j["n_pad"], j["k_pad"],
+                           j["n_valid"], j["k_valid"], j["s_n"], j["s_k"], j.get("k_src_off", 0), j.get("flip", 0),
+                           out.stride(1))
     L.check(L.lib().scmgan_pack_weights(len(jobs), arr, _stream()), "scmgan_pack_weights")
 
 
