@@ -6,6 +6,7 @@
 #include "conv_igemm_v3.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_wgrad_v2.cuh"
+#include "conv_wgrad_narrow.cuh"
 #include "elementwise.cuh"
 #include "host_util.cuh"
 
@@ -448,12 +449,99 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     const int total = 9 * n * 32;
-    wgrad_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
-                                                                   n_valid, scale);
+    if (n <= 32)
+        wgrad_reduce_kernel<32><<<(total + 31) / 32 + (db ? 1 : 0), dim3(32, 32), 0, st>>>(
+            ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db);
+    else
+        wgrad_reduce_kernel<8><<<(total + 31) / 32 + (db ? 1 : 0), dim3(32, 8), 0, st>>>(
+            ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    if (db) {
-        wgrad_bias_reduce_kernel<<<1, 128, 0, st>>>(P.ws_bias, splits, db, m_valid, 1.0f);
+    return SCM_OK;
+}
+
+// 16-channel-on-one-side layers (conv_wgrad_narrow.cuh): all 128-channel blocks of the wide side in one launch.
+//   x_is_wide = true : cout = 16; M = X (padded view), N = dY (interior view at -tap); g[m=ci][n=co]
+//   x_is_wide = false: cin  = 16; M = dY (interior view), N = X (padded view at +tap);  g[m=co][n=ci]; db optional
+// g is indexed g[m*g_sm + n*g_sn + tap*g_st].  Returns 1 when the shape does not qualify.
+static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* xp, int x_cs, int x_c_off,
+                               const void* dyp, int dy_cs, int dy_c_off, int m_blocks, int flip, float scale, float* g,
+                               long long g_sm, long long g_sn, long long g_st, int m_valid, int n_valid, float* ws,
+                               long long ws_bytes, float* db, cudaStream_t st) {
+    static const char* off = getenv("SCMGAN_WGRAD_NO_NARROW");
+    if (off && atoi(off)) return 1;
+    if (!ws) return 1;
+    const int Hp = H + 2, Wp = W + 2;
+    const int rows_k = x_is_wide ? Hp : H;            // image rows the K dimension runs over (the M operand's view)
+    const int kw = ((x_is_wide ? Wp : W) + 15) & ~15;  // pixels per image-row box
+    if (kw > 256) return 1;
+    int BH = 0, stage_bytes = 0;
+    for (int cand : {4, 2, 1}) {
+        const int sb = (cand * kw * (256 + 10 * 32) + 1023) & ~1023;
+        if (2 * sb + 2048 <= kSmemMax) { BH = cand; stage_bytes = sb; break; }
+    }
+    if (!BH) return 1;
+    const int stages = std::min(4, (kSmemMax - 2048) / stage_bytes);
+    WgradNarrowParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = B; P.Hp = Hp; P.BH = BH; P.kw = kw;
+    P.nrb = (rows_k + BH - 1) / BH;
+    P.num_kblocks = B * P.nrb;
+    int splits = std::max(1, std::min(P.num_kblocks / 2, std::max(1, num_sms() / m_blocks)));
+    P.kb_per_cta = (P.num_kblocks + splits - 1) / splits;
+    splits = (P.num_kblocks + P.kb_per_cta - 1) / P.kb_per_cta;
+    const long long per_block = (long long)splits * 9 * kNarrowCo * 128;
+    const long long main_floats = per_block * m_blocks;
+    const bool with_ones = db != nullptr && !x_is_wide;
+    if ((main_floats + (with_ones ? (long long)m_blocks * splits * 128 : 0)) * 4 > ws_bytes) return 1;
+    P.x_c_off = x_is_wide ? x_c_off : dy_c_off;
+    P.dy_c_off = x_is_wide ? dy_c_off : x_c_off;
+    P.n_sign = x_is_wide ? -1 : +1;
+    P.with_ones = with_ones ? 1 : 0;
+    P.ws = ws;
+    P.ws_bias = with_ones ? ws + main_floats : nullptr;
+    {
+        static const char* dbg = getenv("SCMGAN_DEBUG");
+        P.debug = dbg ? (atoi(dbg) & 16) : 0;
+    }
+    // tensor maps: padded view of X, interior view of dY; the wide one is the M operand (64-channel boxes, 128B
+    // swizzle), the 16-channel one the N operand (32B swizzle)
+    CUtensorMap tx, tdy;
+    {
+        uint64_t dims[4] = {uint64_t(x_cs), uint64_t(Wp), uint64_t(Hp), uint64_t(B)};
+        uint64_t str[3] = {uint64_t(x_cs) * 2, uint64_t(Wp) * x_cs * 2, uint64_t(Hp) * Wp * x_cs * 2};
+        uint32_t box[4] = {uint32_t(x_is_wide ? 64 : kNarrowCo), uint32_t(kw), uint32_t(BH), 1};
+        int rc = encode_tmap_bf16(&tx, xp, 4, dims, str, box, x_is_wide ? 128 : 32);
+        if (rc) return rc;
+    }
+    {
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(dyp) + (size_t(Wp) + 1) * dy_cs;
+        uint64_t dims[4] = {uint64_t(dy_cs), uint64_t(W), uint64_t(H), uint64_t(B)};
+        uint64_t str[3] = {uint64_t(dy_cs) * 2, uint64_t(Wp) * dy_cs * 2, uint64_t(Hp) * Wp * dy_cs * 2};
+        uint32_t box[4] = {uint32_t(x_is_wide ? kNarrowCo : 64), uint32_t(kw), uint32_t(BH), 1};
+        int rc = encode_tmap_bf16(&tdy, bp, 4, dims, str, box, x_is_wide ? 32 : 128);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      kSmemMax));
+        attr_set = true;
+    }
+    const int smem = stages * stage_bytes + 1024 + 1024;
+    if (x_is_wide)
+        conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tx, tdy, P, stages);
+    else
+        conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tdy, tx, P, stages);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    const int total = 9 * kNarrowCo * 32;
+    for (int mb = 0; mb < m_blocks; ++mb) {
+        const int mv = std::min(128, m_valid - mb * 128);
+        if (mv <= 0) break;
+        wgrad_reduce_kernel<32><<<(total + 31) / 32 + (with_ones ? 1 : 0), dim3(32, 32), 0, st>>>(
+            ws + mb * per_block, splits, kNarrowCo, g + mb * 128 * g_sm, g_sm, g_sn, g_st, flip, mv, n_valid, scale,
+            with_ones ? P.ws_bias + (long long)mb * splits * 128 : nullptr, with_ones ? db + mb * 128 : nullptr);
         SCM_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -547,8 +635,8 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     ++g_launches;
     if (P.ws) {
         const int total = 9 * n * 32;
-        wgrad_reduce_kernel<<<(total + 31) / 32, dim3(32, 8), 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid,
-                                                                  n_valid, scale);
+        wgrad_reduce_kernel<8><<<(total + 31) / 32, dim3(32, 8), 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip,
+                                                                          m_valid, n_valid, scale, nullptr, nullptr);
         SCM_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -629,6 +717,14 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
         const int n8 = (std::min(mcount, d->co_valid - m0) + 7) & ~7;  // db holds co_valid (rounded up to 8) floats
         return scmgan_plane_colsum(d->dy, d->dy_cs, d->dy_c_off + m0, n8, d->B, d->H, d->W, nullptr, d->db + m0, stream);
     };
+    if (d->cout % 128 == 0 && d->cin == kNarrowCo) {
+        const int blocks = std::min(d->cout / 128, (d->co_valid + 127) / 128);
+        const int rc = wgrad_launch_narrow(false, d->B, d->H, d->W, d->x, d->x_cs, d->x_c_off, d->dy, d->dy_cs,
+                                           d->dy_c_off, blocks, d->flip, d->scale, d->g, d->g_s_co, d->g_s_ci,
+                                           d->g_s_tap, d->co_valid, d->ci_valid, (float*)d->workspace,
+                                           d->workspace_bytes, d->db, st);
+        if (rc <= 0) return rc;
+    }
     if (d->cout % 128 == 0) {
         for (int m0 = 0; m0 < d->cout; m0 += 128) {
             if (m0 >= d->co_valid) break;
@@ -662,6 +758,18 @@ int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
         return SCM_OK;
     }
     if (d->cin % 128 == 0 && d->cout <= 256) {
+        if (d->cout == kNarrowCo) {
+            const int blocks = std::min(d->cin / 128, (d->ci_valid + 127) / 128);
+            const int rc = wgrad_launch_narrow(true, d->B, d->H, d->W, d->x, d->x_cs, d->x_c_off, d->dy, d->dy_cs,
+                                               d->dy_c_off, blocks, d->flip, d->scale, d->g, d->g_s_ci, d->g_s_co,
+                                               d->g_s_tap, d->ci_valid, d->co_valid, (float*)d->workspace,
+                                               d->workspace_bytes, nullptr, st);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                if (d->db) return bias_fallback(0, d->cout);
+                return SCM_OK;
+            }
+        }
         for (int c0 = 0; c0 < d->cin; c0 += 128) {
             const int mv = std::min(128, d->ci_valid - c0);
             if (mv <= 0) break;

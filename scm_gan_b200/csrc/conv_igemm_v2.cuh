@@ -236,17 +236,19 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
             const int p = tile * 128 + q * 32 + lane;
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
             if (P.out_f32 && !P.out && G.n_cta == 16)
-                igemm_epilogue_tile<8, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+                igemm_epilogue_tile<8, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else if (P.out_f32)
-                igemm_epilogue_tile<16, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+                igemm_epilogue_tile<16, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else if ((G.n_cta & 31) == 0)
-                igemm_epilogue_tile<32, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+                igemm_epilogue_tile<32, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else
-                igemm_epilogue_tile<16, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias);
+                igemm_epilogue_tile<16, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);

@@ -187,10 +187,9 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const uint32_t acc_empty_L1 = mapa_shared(smem_u32(&acc_empty[1]), 0);
         for (int tile = pair; tile < P.num_tiles; tile += G.tiles_stride) {
             const int p = tile * 256 + int(rank) * 128 + q * 32 + lane;
-            mbar_wait(&acc_full[acc], acc_phase);
-            tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
-            igemm_epilogue_tile<32, false>(P, n_full, 0, n_full, p, half, lane, taddr, s_bias);
+            igemm_epilogue_tile<32, false>(P, n_full, 0, n_full, p, half, lane, taddr, s_bias, &acc_full[acc],
+                                           acc_phase, p + G.tiles_stride * 256);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(acc ? acc_empty_L1 : acc_empty_L0);

@@ -189,20 +189,34 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
 
 // Sum the split-K partials and scatter into the caller's gradient layout:
 //   g[m*g_sm + n*g_sn + tap'*g_st] += scale * sum_split ws[split][tap][n][m]
-// Block = 32 float4 columns (512 contiguous bytes of one split row) x 8 split lanes: every split lane sums the
-// splits congruent to it, the eight partial sums are combined through shared memory in a fixed order.
-__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n,
+// Block = 32 float4 columns (512 contiguous bytes of one split row) x LANES split lanes (8, or 32 when the
+// output is small and the grid would otherwise leave most SMs idle): every split lane sums the splits congruent to
+// it, the partial sums are combined through shared memory in a fixed order.
+// One extra block (blockIdx.x == ceil(total4 / 32)) sums the bias-gradient partials of conv_wgrad_v2.cuh when given:
+//   db[m] += sum_split ws_bias[split][m]
+template <int LANES>
+__global__ void __launch_bounds__(32 * LANES) wgrad_reduce_kernel(const float* __restrict__ ws, int splits, int n,
                                                             float* __restrict__ g, long long g_sm, long long g_sn,
                                                             long long g_st, int flip, int m_valid, int n_valid,
-                                                            float scale) {
-    __shared__ float4 part[8][32];
+                                                            float scale, const float* __restrict__ ws_bias,
+                                                            float* __restrict__ db) {
+    __shared__ float4 part[LANES][32];
+    constexpr int lanes = LANES;
     const int total4 = 9 * n * 32;  // float4 groups per split
+    if (int(blockIdx.x) * 32 >= total4) {  // the bias block
+        const int m = threadIdx.y * 32 + threadIdx.x;
+        if (ws_bias == nullptr || m >= 128 || m >= m_valid) return;
+        float acc = 0.f;
+        for (int s = 0; s < splits; ++s) acc += __ldg(ws_bias + size_t(s) * 128 + m);
+        db[m] += acc;
+        return;
+    }
     const int i4 = blockIdx.x * 32 + threadIdx.x;
     const int lane_s = threadIdx.y;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (i4 < total4) {
         const float4* src = reinterpret_cast<const float4*>(ws) + i4;
-        for (int s = lane_s; s < splits; s += 8) {
+        for (int s = lane_s; s < splits; s += lanes) {
             const float4 a = __ldg(src + size_t(s) * total4);
             acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
         }
@@ -211,7 +225,7 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restri
     __syncthreads();
     if (lane_s != 0 || i4 >= total4) return;
 #pragma unroll
-    for (int j = 1; j < 8; ++j) {
+    for (int j = 1; j < lanes; ++j) {
         const float4 a = part[j][threadIdx.x];
         acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
     }

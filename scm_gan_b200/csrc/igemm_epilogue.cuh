@@ -57,9 +57,14 @@ __device__ __forceinline__ EpiRow epi_decode_row(const IgemmParams& P, int p) {
 // that both warps of a lane quarter have work - only without a bf16 plane output, whose stores are 16 columns wide).
 // F32: the fp32 NCHW / Bernoulli-head output is compiled in (only the narrow N = 16 heads use it; keeping it out of
 // the wide instantiations keeps the hot loop small enough for the instruction cache).
+// The warp's tile is final when `acc_bar` completes phase `acc_phase`; everything that does not need the accumulator
+// (row decode, and the LeakyReLU-derivative gate of dgrad: the sign bits of this row's slice of the gate plane, 128
+// columns per warp at most -> four registers) is fetched BEFORE that wait, so that the global-memory latency of the
+// gate plane (a saved forward activation, usually in HBM) overlaps the MMAs instead of stalling every column group.
 template <int GROUP, bool F32>
 __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_total, int n0, int ncols_cta, int p,
-                                                    int half, int lane, uint32_t taddr, const float* s_bias) {
+                                                    int half, int lane, uint32_t taddr, const float* s_bias,
+                                                    uint64_t* acc_bar, uint32_t acc_phase, int p_next) {
     static_assert(GROUP == 8 || GROUP == 16 || GROUP == 32, "unsupported column group");
     constexpr int CH = GROUP / 8;       // 16-byte chunks per row segment
     const EpiRow R = epi_decode_row(P, p);
@@ -75,6 +80,59 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
         if (wp2 >= 0) d2 = R.b * plane + R.hp * P.Wp + wp2;
         if (hp2 >= 0 && wp2 >= 0) d3 = R.b * plane + hp2 * P.Wp + wp2;
     }
+    if (P.gate && p_next >= 0 && p_next < P.rows) {
+        // pull the NEXT tile's gate row into L2 while this tile is processed (the plane is a saved forward
+        // activation that normally sits in HBM); costs no registers
+        const char* gn = reinterpret_cast<const char*>(P.gate + size_t(p_next) * P.gate_cs + P.gate_c_off + n0);
+        const int bytes = ncols_cta * 2;
+        for (int o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(gn + o));
+    }
+    uint32_t gb[4] = {0u, 0u, 0u, 0u};  // bit (k*GROUP + i): gate of column i of this warp's k-th group is "positive"
+    if (P.gate && R.interior) {
+        // phase 1: every load of the tile in flight at once (the accumulator registers are dead here); 256-bit loads
+        // because each lane reads its own row: a request costs one L1 wavefront per lane whatever its width
+        constexpr int NG = 128 / GROUP;      // column groups per warp at most
+        constexpr int WPG = GROUP / 2;       // 32-bit words per group
+        uint32_t raw[NG * WPG];
+        const __nv_bfloat16* grow = P.gate + size_t(p) * P.gate_cs + P.gate_c_off + n0;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            const int c0 = half * GROUP + k * 2 * GROUP;
+            if (c0 < ncols_cta) {
+                if constexpr (GROUP >= 16) {
+#pragma unroll
+                    for (int j = 0; j < GROUP / 16; ++j) {
+                        uint32_t* w = raw + k * WPG + 8 * j;
+                        asm("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                            : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]),
+                              "=r"(w[7])
+                            : "l"(grow + c0 + 16 * j));
+                    }
+                } else {
+                    const uint4 r = __ldg(reinterpret_cast<const uint4*>(grow + c0));
+                    raw[k * WPG] = r.x; raw[k * WPG + 1] = r.y; raw[k * WPG + 2] = r.z; raw[k * WPG + 3] = r.w;
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < WPG; ++q) raw[k * WPG + q] = 0u;
+            }
+        }
+        // phase 2: per bf16 half, bit <- (value > 0), i.e. magnitude != 0 and sign clear
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+            uint32_t m = 0u;
+#pragma unroll
+            for (int q = 0; q < WPG; ++q) {
+                const uint32_t w = raw[k * WPG + q];
+                const uint32_t pos = ((w & 0x7FFF7FFFu) + 0x7FFF7FFFu) & ~w & 0x80008000u;
+                m |= ((pos >> 15) & 1u) << (2 * q);
+                m |= (pos >> 31) << (2 * q + 1);
+            }
+            gb[(k * GROUP) >> 5] |= m << ((k * GROUP) & 31);
+        }
+    }
+    mbar_wait(acc_bar, acc_phase);
+    tc_fence_after();
     const float* sbp = (P.sample_bias && R.valid) ? P.sample_bias + size_t(R.b) * n_total + n0 : nullptr;
     const size_t hw = size_t(P.H) * P.W;
     const uint32_t s_bias_u32 = smem_u32(s_bias);
@@ -138,14 +196,12 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             for (int i = 0; i < GROUP; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
         }
         if (R.interior && P.gate) {
-            const uint4* gp = reinterpret_cast<const uint4*>(P.gate + size_t(p) * P.gate_cs + P.gate_c_off + n0 + c0);
+            const int bit0 = ((c0 - half * GROUP) / (2 * GROUP)) * GROUP;  // this group's first bit in gb
+            const int wi = bit0 >> 5;
+            const uint32_t word = wi == 0 ? gb[0] : (wi == 1 ? gb[1] : (wi == 2 ? gb[2] : gb[3]));
+            const uint32_t m = word >> (bit0 & 31);
 #pragma unroll
-            for (int j = 0; j < CH; ++j) {
-                const uint4 r = __ldg(gp + j);
-                const __nv_bfloat16* h = reinterpret_cast<const __nv_bfloat16*>(&r);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) v[8 * j + i] *= (__bfloat162float(h[i]) > 0.f) ? 1.f : P.slope;
-            }
+            for (int i = 0; i < GROUP; ++i) v[i] *= ((m >> i) & 1u) ? 1.f : P.slope;
         }
         if (P.out) {
             // direct path: every lane writes its own row with 256-bit stores (one full 32-byte sector per 16

@@ -200,6 +200,9 @@ WGRAD_CASES = [
     (2, 16, 16, 16, 128, False),
     (2, 12, 32, 256, 128, True),
     (3, 10, 48, 64, 128, True),
+    # 16 output channels at the bench plane size: nine taps folded into N (conv_wgrad_narrow.cuh)
+    (2, 64, 64, 256, 16, True),
+    (1, 33, 70, 128, 16, False),
 ]
 
 
