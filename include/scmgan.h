@@ -171,6 +171,15 @@ int scmgan_action_bias(const float* wbar, const float* sigma, const float* bias,
 int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L, int A, float* g,
                         scmgan_stream_t stream);
 
+/* Reward regression term of the rollout loss (reference main.py:182-186):
+ *   loss[0] = scale * mean_b( mask[b] * mean_r (pred[b][r] - target[b][r])^2 ),  dpred = d loss / d pred.
+ * target rows are target_bstride elements apart (a time slice of the [B][Hn][R] reward tensor), mask elements
+ * mask_stride apart (a time slice of the [B][Hn-1] active mask).  One launch instead of six elementwise / reduction
+ * kernels forward and as many backward. */
+int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
+                      long long mask_stride, int B, int R, float scale, float* loss, float* dpred,
+                      scmgan_stream_t stream);
+
 /* loss[0] += mean_b( mask[b] * mean_chw BCE(sigmoid(x), y) ); dx (optional) = d loss / d x.
  * Fuses torch.sigmoid + F.binary_cross_entropy + means (reference main.py:188-197, 310-312). */
 int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,

@@ -95,6 +95,8 @@ SIGNATURES = {
     "scmgan_cf_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_philox_uniform": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "scmgan_clip_adam": (C.c_int, [C.c_int, C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_float, C.c_void_p]),

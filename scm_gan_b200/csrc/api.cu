@@ -126,7 +126,7 @@ static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const Ig
                                       kSmemMax));
         attr_set = true;
     }
-    conv3x3_igemm_v2_kernel<CK, TPG><<<dim3(gx, nsplit), kV2Threads, smem, st>>>(ta, tb, P, G);
+    conv3x3_igemm_v2_kernel<CK, TPG><<<dim3(gx, nsplit), v2_threads<CK>(), smem, st>>>(ta, tb, P, G);
     SCM_CUDA(cudaGetLastError());
     return SCM_OK;
 }
@@ -896,6 +896,17 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
     SCM_REQUIRE(S && act && g && B > 0 && Cout > 0 && A > 0, "action_wgrad: bad arguments");
     const int total = Cout * A;
     action_wgrad_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, act, B, Cout, L, A, g);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
+                      long long mask_stride, int B, int R, float scale, float* loss, float* dpred,
+                      scmgan_stream_t stream) {
+    SCM_REQUIRE(pred && target && loss && B > 0 && R > 0, "masked_mse: bad arguments");
+    masked_mse_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, target_bstride, mask, mask_stride, B, R, scale,
+                                                          loss, dpred);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;

@@ -40,10 +40,14 @@ struct IgemmV2Geom {
 // bottleneck (measured); eight epilogue warps = two per TMEM lane quarter, interleaving the 32-column groups.
 constexpr int kV2EpiWarps = 8;
 constexpr int kV2Threads = 64 + 32 * kV2EpiWarps;
+// The narrow-K instantiation (CK = 16: nine MMAs per tile) is pure epilogue - measured 26 us for a 16->128 layer whose
+// output takes 6 us to write - so it runs sixteen epilogue warps, four per lane quarter.
+template <int CK> struct V2Epi { static constexpr int kWarps = (CK == 16) ? 16 : 8; };
+template <int CK> constexpr int v2_threads() { return 64 + 32 * V2Epi<CK>::kWarps; }
 
 // CK: channels per K chunk (64 -> 128B swizzle, 16 -> 32B swizzle).  TPG: filter taps served by one stage.
 template <int CK, int TPG>
-__global__ void __launch_bounds__(kV2Threads, 1)
+__global__ void __launch_bounds__(v2_threads<CK>(), 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ IgemmParams P, const __grid_constant__ IgemmV2Geom G) {
     using Cfg = IgemmCfg<CK>;
@@ -67,6 +71,8 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const int lane = threadIdx.x & 31;
     const int n0 = blockIdx.y * G.n_cta;  // first output channel of this CTA's slice
     constexpr int kGroups = 9 / TPG;
+    constexpr int kEpiWarps = V2Epi<CK>::kWarps;
+    constexpr int kShare = kEpiWarps / 4;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -77,7 +83,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         }
         for (int s = 0; s < 2; ++s) {
             mbar_init(&acc_full[s], 1);
-            mbar_init(&acc_empty[s], kV2EpiWarps);
+            mbar_init(&acc_empty[s], kEpiWarps);
         }
         mbar_init(b_full, 1);
         fence_barrier_init();
@@ -87,7 +93,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_relinquish();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kV2EpiWarps) s_bias[i] = P.bias ? P.bias[n0 + i] : 0.f;
+        for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kEpiWarps) s_bias[i] = P.bias ? P.bias[n0 + i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();
@@ -231,23 +237,23 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         // ------------------------------ epilogue (igemm_epilogue.cuh) ------------------------------
         const int q = warp & 3;  // TMEM lane quarter this warp may access
         const int ew = warp - 2;
-        const int half = ew >> 2;  // which of the two warps sharing this lane quarter
+        const int half = ew >> 2;  // which of the kShare warps sharing this lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
             const int p = tile * 128 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
             if (P.out_f32 && !P.out && G.n_cta == 16)
-                igemm_epilogue_tile<8, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                igemm_epilogue_tile<8, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else if (P.out_f32)
-                igemm_epilogue_tile<16, true>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                igemm_epilogue_tile<16, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else if ((G.n_cta & 31) == 0)
-                igemm_epilogue_tile<32, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                igemm_epilogue_tile<32, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else
-                igemm_epilogue_tile<16, false>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                igemm_epilogue_tile<16, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             tc_fence_before();
             __syncwarp();

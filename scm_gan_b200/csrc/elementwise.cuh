@@ -436,6 +436,27 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ----------------------------------------------------------------------------------------------
+// Masked mean-squared error of the reward predictions (reference main.py:182-186), forward and gradient in one
+// single-block launch:  loss = scale/(B*R) * sum_b mask[b] * sum_r (pred - target)^2
+// ----------------------------------------------------------------------------------------------
+__global__ void masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
+                                  long long t_bstride, const float* __restrict__ mask, long long m_stride, int B, int R,
+                                  float scale, float* __restrict__ loss, float* __restrict__ dpred) {
+    __shared__ float red[33];
+    const float k = scale / (float(B) * float(R));
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < B * R; i += blockDim.x) {
+        const int b = i / R, r = i - b * R;
+        const float m = mask ? __ldg(mask + (long long)b * m_stride) : 1.f;
+        const float d = pred[i] - __ldg(target + (long long)b * t_bstride + r);
+        acc = fmaf(m * d, d, acc);
+        if (dpred) dpred[i] = 2.f * k * m * d;
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) *loss = acc * k;
+}
+
+// ----------------------------------------------------------------------------------------------
 // Fused clip_grad_value_ + Adam (reference main.py:287-296; torch.optim.Adam defaults, no weight decay).
 // Multi-tensor: one launch updates every parameter of every network.
 // ----------------------------------------------------------------------------------------------

@@ -61,7 +61,9 @@ __device__ __forceinline__ EpiRow epi_decode_row(const IgemmParams& P, int p) {
 // (row decode, and the LeakyReLU-derivative gate of dgrad: the sign bits of this row's slice of the gate plane, 128
 // columns per warp at most -> four registers) is fetched BEFORE that wait, so that the global-memory latency of the
 // gate plane (a saved forward activation, usually in HBM) overlaps the MMAs instead of stalling every column group.
-template <int GROUP, bool F32>
+// SHARE: epilogue warps per TMEM lane quarter (2, or 4 in the narrow-K kernel whose short main loop leaves the
+// epilogue exposed); the warps of a quarter interleave the column groups.
+template <int GROUP, bool F32, int SHARE = 2>
 __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_total, int n0, int ncols_cta, int p,
                                                     int half, int lane, uint32_t taddr, const float* s_bias,
                                                     uint64_t* acc_bar, uint32_t acc_phase, int p_next) {
@@ -91,13 +93,13 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
     if (P.gate && R.interior) {
         // phase 1: every load of the tile in flight at once (the accumulator registers are dead here); 256-bit loads
         // because each lane reads its own row: a request costs one L1 wavefront per lane whatever its width
-        constexpr int NG = 128 / GROUP;      // column groups per warp at most
+        constexpr int NG = 256 / (SHARE * GROUP);  // column groups per warp at most
         constexpr int WPG = GROUP / 2;       // 32-bit words per group
         uint32_t raw[NG * WPG];
         const __nv_bfloat16* grow = P.gate + size_t(p) * P.gate_cs + P.gate_c_off + n0;
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-            const int c0 = half * GROUP + k * 2 * GROUP;
+            const int c0 = half * GROUP + k * SHARE * GROUP;
             if (c0 < ncols_cta) {
                 if constexpr (GROUP >= 16) {
 #pragma unroll
@@ -196,7 +198,7 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             for (int i = 0; i < GROUP; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
         }
         if (R.interior && P.gate) {
-            const int bit0 = ((c0 - half * GROUP) / (2 * GROUP)) * GROUP;  // this group's first bit in gb
+            const int bit0 = ((c0 - half * GROUP) / (SHARE * GROUP)) * GROUP;  // this group's first bit in gb
             const int wi = bit0 >> 5;
             const uint32_t word = wi == 0 ? gb[0] : (wi == 1 ? gb[1] : (wi == 2 ? gb[2] : gb[3]));
             const uint32_t m = word >> (bit0 & 31);
@@ -243,19 +245,30 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             }
         }
     };
-    float va[GROUP], vb[GROUP];
-    int c0 = half * GROUP;
-    if (c0 < ncols_cta) load(va, c0);
-    while (c0 < ncols_cta) {
-        tmem_ld_wait();
-        const int c1 = c0 + 2 * GROUP;
-        if (c1 < ncols_cta) load(vb, c1);
-        process(va, c0);
-        if (c1 >= ncols_cta) break;
-        tmem_ld_wait();
-        c0 = c1 + 2 * GROUP;
+    if constexpr (SHARE > 2) {
+        // four warps per quarter: a warp rarely owns more than one group, a second register buffer would only cost
+        // occupancy headroom
+        float va[GROUP];
+        for (int c0 = half * GROUP; c0 < ncols_cta; c0 += SHARE * GROUP) {
+            load(va, c0);
+            tmem_ld_wait();
+            process(va, c0);
+        }
+    } else {
+        float va[GROUP], vb[GROUP];
+        int c0 = half * GROUP;
         if (c0 < ncols_cta) load(va, c0);
-        process(vb, c1);
+        while (c0 < ncols_cta) {
+            tmem_ld_wait();
+            const int c1 = c0 + SHARE * GROUP;
+            if (c1 < ncols_cta) load(vb, c1);
+            process(va, c0);
+            if (c1 >= ncols_cta) break;
+            tmem_ld_wait();
+            c0 = c1 + SHARE * GROUP;
+            if (c0 < ncols_cta) load(va, c0);
+            process(vb, c1);
+        }
     }
 }
 

@@ -171,6 +171,15 @@ def bce_logits(x, y, mask, loss, dx=None):
                                       L.ptr(dx), _stream()), "scmgan_bce_logits")
 
 
+def masked_mse(pred, target, mask, scale, loss, dpred=None):
+    """pred [B,R] contiguous; target [B,R] with unit inner stride; mask [B] (any stride) or None."""
+    B, R = pred.shape
+    assert pred.is_contiguous() and target.shape == pred.shape and (R == 1 or target.stride(1) == 1)
+    L.check(L.lib().scmgan_masked_mse(pred.data_ptr(), target.data_ptr(), target.stride(0), L.ptr(mask),
+                                      mask.stride(0) if mask is not None else 0, B, R, float(scale), loss.data_ptr(),
+                                      L.ptr(dpred), _stream()), "scmgan_masked_mse")
+
+
 def reward_head_fwd(y2, R, r, rmap=None):
     B, _, H, W = y2.shape
     L.check(L.lib().scmgan_reward_head_fwd(y2.data_ptr(), B, R, H, W, r.data_ptr(), L.ptr(rmap), _stream()),

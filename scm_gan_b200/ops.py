@@ -277,6 +277,37 @@ bce_logits.register_autograd(_bce_backward, setup_context=_bce_setup)
 
 
 # ------------------------------------------------------------------------------------------------------------
+# Masked reward MSE (reference main.py:182-186), one kernel for value and gradient
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::masked_mse", mutates_args=())
+def masked_mse(pred: Tensor, target: Tensor, mask: Tensor, scale: float) -> List[Tensor]:
+    _require_cuda(pred, target, mask)
+    pred = pred.contiguous().float()
+    if not (target.dtype == torch.float32 and (target.shape[1] == 1 or target.stride(1) == 1)):
+        target = target.contiguous().float()
+    if mask.dtype != torch.float32:
+        mask = mask.float()
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pred)
+    K.masked_mse(pred, target, mask, scale, loss, dpred)
+    return [loss.view(()), dpred]
+
+
+def _mse_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(output[1])
+
+
+def _mse_backward(ctx, grads):
+    (dpred,) = ctx.saved_tensors
+    g = grads[0]
+    return (None if g is None else dpred * g), None, None, None
+
+
+masked_mse.register_autograd(_mse_backward, setup_context=_mse_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # RewardPredictor
 # ------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("scmgan::reward_fwd", mutates_args=())

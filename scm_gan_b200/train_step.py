@@ -75,14 +75,14 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     for t in range(1, Hn - 1):
         mask = masks[:, t - 1]
         expected = rew(z)
-        rd = torch.mean(torch.mean((expected - rewards[:, t]) ** 2, dim=1) * mask)
-        loss = loss + (theta * reward_coef) * rd
+        rd_scaled = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, theta * reward_coef)[0]
+        loss = loss + rd_scaled
         rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
         if truncate_bptt and t > 1:
             z = z.detach()
         loss = loss + rec
         if collect is not None:
-            collect[f"Rd Loss t={t}"] = rd
+            collect[f"Rd Loss t={t}"] = torch.mean(torch.mean((expected.detach() - rewards[:, t]) ** 2, dim=1) * mask)
             collect[f"Reconstruction t={t}"] = rec
         z = step(z, actions[:, t])
 

@@ -464,3 +464,20 @@ def test_philox_uniform_stream_matches_in_kernel_head():
     s_c = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
     K.philox_uniform(v, s_c)
     assert torch.equal(v, u.flatten()[:10]) and s_c.tolist() == [77, 8]
+
+
+def test_masked_mse():
+    """Reward regression term (reference main.py:182-186): value and gradient of the fused kernel vs torch."""
+    _setup()
+    torch.manual_seed(12)
+    B, Hn, R = 32, 10, 3
+    rewards = torch.randn(B, Hn, R, device=DEV)
+    masks = (torch.rand(B, Hn - 1, device=DEV) > 0.3).float()
+    pred = torch.randn(B, R, device=DEV, requires_grad=True)
+    ref = 0.37 * torch.mean(torch.mean((pred - rewards[:, 4]) ** 2, dim=1) * masks[:, 3])
+    (gref,) = torch.autograd.grad(ref, pred)
+    p2 = pred.detach().clone().requires_grad_(True)
+    got = torch.ops.scmgan.masked_mse(p2, rewards[:, 4], masks[:, 3], 0.37)[0]
+    (ggot,) = torch.autograd.grad(got * 2.0, p2)
+    assert report("masked mse", got, ref, 1e-6)
+    assert report("masked mse grad", ggot, 2.0 * gref, 1e-6)
