@@ -144,7 +144,33 @@ class Decoder(nn.Module):
         self.color_channels = color_channels
         self.conv1 = nn.ConvTranspose2d(latent_size, latent_size * 4, (3, 3), stride=1, padding=1)
         self.conv2 = nn.ConvTranspose2d(latent_size * 4, latent_size * color_channels, (3, 3), stride=1, padding=1)
+        self._fold = None  # (key, folded weight, folded bias) shared by the decoder calls of one iteration
         _to_device(self)
+
+    def _folded_last_layer(self):
+        """conv2 with the sum over latent groups folded into its weights.  Every unrolled step of an iteration decodes
+        with the same weights, so the fold (and its backward) is done once per autograd graph: the cached tensors are
+        dropped when their gradient arrives, or when the parameters change version (load_state_dict, optimizer)."""
+        w2, b2 = self.conv2.weight, self.conv2.bias
+        key = (w2._version, b2._version, w2.data_ptr(), torch.is_grad_enabled())
+        if self._fold is not None and self._fold[0] == key:
+            return self._fold[1], self._fold[2]
+        hid = w2.shape[0]
+        w2f = w2.view(hid, self.latent_size, self.color_channels, 3, 3).sum(1)
+        b2f = b2.view(self.latent_size, self.color_channels).sum(0)
+        if w2f.requires_grad:
+            w2f.register_hook(self._drop_fold)
+            self._fold = (key, w2f, b2f)
+        return w2f, b2f
+
+    def _drop_fold(self, grad):
+        self._fold = None
+        return grad
+
+    def __getstate__(self):  # the cache holds non-leaf tensors: never copied or pickled with the module
+        state = self.__dict__.copy()
+        state["_fold"] = None
+        return state
 
     def forward(self, z_map, visualize=False):
         batch_size, latent_size, height, width = z_map.shape
@@ -156,9 +182,7 @@ class Decoder(nn.Module):
             return torch.sum(x, dim=1), x[0]
         # sum over the latent groups commutes with the (linear) last layer: fold it into the weights, exactly
         # (up to fp reassociation).  Autograd broadcasts the folded gradient back to all groups.
-        hid = w2.shape[0]
-        w2f = w2.view(hid, latent_size, self.color_channels, 3, 3).sum(1)
-        b2f = b2.view(latent_size, self.color_channels).sum(0)
+        w2f, b2f = self._folded_last_layer()
         return torch.ops.scmgan.decoder_fwd(z_map, self.conv1.weight, self.conv1.bias, w2f, b2f)[0]
 
 
