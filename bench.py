@@ -158,7 +158,8 @@ def cpu_reference_run(workload, horizon, sample_batch, steps, warmup, threads=No
 
 def time_dominant_kernel(B, H, W, iters=30):
     """Average duration of the dominant kernel (3x3 conv 128->128 implicit GEMM, wrap padding, bias+LeakyReLU
-    epilogue) at the workload's shape, CUDA events on the launching stream, rotating over > L2 worth of planes."""
+    epilogue) at the workload's shape, rotating over > L2 worth of planes.  Launched the way the training step
+    launches it - as nodes of a replayed CUDA graph - and timed with CUDA events on the replaying stream."""
     import torch
     from scm_gan_b200 import kernels as K
     dev = "cuda"
@@ -171,10 +172,17 @@ def time_dominant_kernel(B, H, W, iters=30):
     for i in range(3):
         K.conv3x3(xs[i % nbuf], w, B, H, W, cin=128, bias=bias, act=K.ACT_LRELU, out=ys[i % nbuf], wrap=True)
     torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(graph, stream=side):
+            for i in range(iters):
+                K.conv3x3(xs[i % nbuf], w, B, H, W, cin=128, bias=bias, act=K.ACT_LRELU, out=ys[i % nbuf], wrap=True)
+    graph.replay()
+    torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for i in range(iters):
-        K.conv3x3(xs[i % nbuf], w, B, H, W, cin=128, bias=bias, act=K.ACT_LRELU, out=ys[i % nbuf], wrap=True)
+    graph.replay()
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
