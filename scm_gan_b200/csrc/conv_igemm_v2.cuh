@@ -249,7 +249,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
             else if (P.out_f32)
                 igemm_epilogue_tile<16, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
-            else if ((G.n_cta & 31) == 0)
+            else if ((G.n_cta & 31) == 0 && G.n_cta >= 32 * kShare)  // else 16-column groups keep more warps busy
                 igemm_epilogue_tile<32, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
                                               &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
             else
