@@ -30,7 +30,7 @@ def smooth(x, w):
     return (c[w:] - c[:-w]) / w
 
 
-def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print):
+def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_seed=None):
     from oracle import restated as R
     from scm_gan_b200.synthetic import MovingDots
     from scm_gan_b200.train_step import Trainer, build_nets
@@ -51,6 +51,9 @@ def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print):
     opt = torch.optim.Adam(oparams_clip + oparams_free, lr=1e-4)
     kw = dict(enable_disentanglement=True, enable_action_control=True, counterfactual_horizon=cf_h)
     trainer = Trainer(nets, loss_kwargs=kw)
+    if rng_seed is not None:  # vary only the Bernoulli streams (ours: Philox seed; oracle: torch generator)
+        nets["transition"]._rng_state[0] = int(rng_seed)
+        torch.manual_seed(int(rng_seed))
     src_a, src_b = MovingDots(C, H, W, A, Rw, seed=11), MovingDots(C, H, W, A, Rw, seed=11)
     g = torch.Generator().manual_seed(5)
     ours, oracle = [], []
@@ -117,8 +120,10 @@ if __name__ == "__main__":
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--horizon", type=int, default=5)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "curve_parity.json"))
+    ap.add_argument("--rng-seed", type=int, default=None, help="seed of the Bernoulli streams only (same init/data)")
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
-    res = run(args.steps, args.batch, args.horizon)
+    res = run(args.steps, args.batch, args.horizon, rng_seed=args.rng_seed, use_graph=not args.no_graph)
     res["summary"] = summarize(res)
     print(json.dumps(res["summary"], indent=1))
     print(f"time: ours {res['seconds_ours']:.1f}s, oracle (torch fp32 on the same GPU) {res['seconds_oracle']:.1f}s")
