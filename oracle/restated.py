@@ -386,6 +386,40 @@ def measure_prediction_mse(nets, states, rewards, dones, actions, *, num_actions
     return mse, mse_std, rew, rew_std
 
 
+def compute_rollout_reward(nets, z, num_actions, *, training=False, lookahead=2, rollout_depth=12,
+                           negative_positive_tradeoff=10.0, uniform_source=None):
+    """reference main.py:455-489 with rollout_policy='noop': best plan score of the A^2 beam started at z [1,L,H,W].
+    uniform_source(shape) supplies the Bernoulli uniforms in train mode (None: torch.rand)."""
+    assert lookahead == 2
+    width = num_actions ** lookahead
+    eye = torch.eye(num_actions, dtype=z.dtype, device=z.device)
+    plans = torch.as_tensor([[i, j] + [0] * (rollout_depth - lookahead)
+                             for i in range(num_actions) for j in range(num_actions)], device=z.device)
+    with torch.no_grad():
+        z = z.repeat(width, 1, 1, 1)
+        cumulative = reward_forward(nets["reward_predictor"], z).clone()
+        for t in range(rollout_depth):
+            u = uniform_source(tuple(z.shape)) if (training and uniform_source is not None) else None
+            z = transition_forward(nets["transition"], z, eye[plans[:, t]], training=training, uniforms=u)
+            cumulative += reward_forward(nets["reward_predictor"], z)
+        cumulative[:, 0] *= negative_positive_tradeoff
+        return cumulative.sum(dim=1).max(dim=0)[0]
+
+
+def choose_action(nets, z, num_actions, *, training=False, rollout_depth=12, uniform_source=None):
+    """One decision of play(), reference main.py:356-368: (argmax action, per-action scores [A])."""
+    eye = torch.eye(num_actions, dtype=z.dtype, device=z.device)
+    scores = []
+    with torch.no_grad():
+        for a in range(num_actions):
+            u = uniform_source(tuple(z.shape)) if (training and uniform_source is not None) else None
+            z_a = transition_forward(nets["transition"], z, eye[a:a + 1], training=training, uniforms=u)
+            scores.append(compute_rollout_reward(nets, z_a, num_actions, training=training,
+                                                 rollout_depth=rollout_depth, uniform_source=uniform_source))
+    scores = torch.stack(scores)
+    return int(torch.argmax(scores)), scores
+
+
 # --------------------------------------------------------------------------------------------------------------
 # parameter initialisation in the reference's construction order (so seeded weights match bit for bit)
 # --------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,128 @@
+"""Model-predictive control on the learned world model: host-side mirror of the reference's `play()` /
+`compute_rollout_reward()` (main.py:327-400, 455-489) on the drop-in modules.
+
+The decision rule is the reference's: for every candidate action a, advance the latent state one step with a, then
+score it with the best of a beam of A^lookahead plans (every [i, j] action pair followed by a fixed roll-out policy)
+simulated `rollout_depth` steps with Transition + RewardPredictor; take argmax over a.  Nothing is decoded.
+
+Everything stays on the device; the only device->host transfer per decision is the vector of A scores (the reference
+reads `max()`/`argmax` of python floats, i.e. one transfer per candidate).  Call order and batch shapes follow the
+reference exactly by default, because every Transition call advances the spectral-norm power iteration
+(spectral_normalization.py:28-31) and, in train mode, draws Bernoulli noise.  `fold_actions=True` simulates the A
+candidates as one batch of A * A^lookahead trajectories (A x fewer Transition calls of A x the batch - the shape the
+tcgen05 kernels like); it performs fewer power iterations per decision, so it matches the sequential planner only up
+to the (converged) spectral-norm state.
+"""
+import numpy as np
+import torch
+
+
+def onehot(a_idx, num_actions, device):
+    """reference main.py:447-452: int -> [1, A]; LongTensor [B] -> [B, A]."""
+    eye = torch.eye(num_actions, dtype=torch.float32, device=device)
+    if isinstance(a_idx, int):
+        return eye[a_idx].unsqueeze(0)
+    return eye[a_idx]
+
+
+def beam_actions(num_actions, lookahead=2, rollout_depth=12, rollout_policy="noop", rng=None):
+    """[A^lookahead, rollout_depth] int64 plan table of compute_rollout_reward (main.py:463-473; lookahead is 2 there)."""
+    assert lookahead == 2, "the reference enumerates action pairs"
+    rows = []
+    for i in range(num_actions):
+        for j in range(num_actions):
+            if rollout_policy == "noop":
+                tail = [0] * (rollout_depth - lookahead)
+            elif rollout_policy == "random":
+                rng = rng or np.random
+                tail = [int(rng.randint(num_actions)) for _ in range(rollout_depth - lookahead)]
+            else:
+                raise ValueError(rollout_policy)
+            rows.append([i, j] + tail)
+    return torch.as_tensor(np.asarray(rows, dtype=np.int64))
+
+
+@torch.no_grad()
+def rollout_scores(z, transition, reward_predictor, num_actions, lookahead=2, rollout_depth=12,
+                   rollout_policy="noop", negative_positive_tradeoff=10.0, actions=None):
+    """Score of every plan of the beam started at each row of z: [Bz * A^lookahead] (plans of one start state are
+    contiguous).  With Bz = 1 this is the `cumulative_reward.sum(dim=1)` of main.py:476-486."""
+    width = num_actions ** lookahead
+    if actions is None:
+        actions = beam_actions(num_actions, lookahead, rollout_depth, rollout_policy)
+    actions = actions.to(z.device)
+    bz = z.shape[0]
+    z = z.repeat_interleave(width, dim=0) if bz > 1 else z.repeat(width, 1, 1, 1)
+    plan = actions.repeat(bz, 1)
+    cumulative = reward_predictor(z).clone()
+    for t in range(rollout_depth):
+        z = transition(z.detach(), onehot(plan[:, t], num_actions, z.device))
+        cumulative += reward_predictor(z)
+    cumulative[:, 0] *= negative_positive_tradeoff  # "caution" about the first (negative) reward channel
+    return cumulative.sum(dim=1)
+
+
+@torch.no_grad()
+def compute_rollout_reward(z, transition, reward_predictor, num_actions, selected_action=None, lookahead=2,
+                           rollout_depth=12, rollout_policy="noop", negative_positive_tradeoff=10.0):
+    """Reference signature (main.py:455-489): best achievable plan score from latent state z [1, L, H, W]
+    (a 0-dim device tensor)."""
+    return rollout_scores(z, transition, reward_predictor, num_actions, lookahead, rollout_depth, rollout_policy,
+                          negative_positive_tradeoff).max(dim=0)[0]
+
+
+@torch.no_grad()
+def choose_action(z, transition, reward_predictor, num_actions, rollout_depth=12, rollout_policy="noop",
+                  fold_actions=False):
+    """One decision of play() (main.py:356-368).  Returns (best action, [score of every action] as a CPU tensor)."""
+    dev = z.device
+    if fold_actions:
+        z_all = transition(z.repeat(num_actions, 1, 1, 1),
+                           onehot(torch.arange(num_actions, device=dev), num_actions, dev))
+        scores = rollout_scores(z_all, transition, reward_predictor, num_actions, 2, rollout_depth, rollout_policy)
+        rewards = scores.view(num_actions, -1).max(dim=1)[0]
+    else:
+        per_action = []
+        for a in range(num_actions):
+            z_a = transition(z, onehot(a, num_actions, dev))
+            per_action.append(compute_rollout_reward(z_a, transition, reward_predictor, num_actions, a,
+                                                     rollout_depth=rollout_depth, rollout_policy=rollout_policy))
+        rewards = torch.stack(per_action)
+    rewards = rewards.cpu()  # the decision itself is taken on the host, like the reference's np.argmax
+    return int(torch.argmax(rewards)), rewards
+
+
+@torch.no_grad()
+def play(env, convert_frame, nets, num_actions, no_op=3, max_steps=300, fold_actions=False, on_step=None):
+    """The agent loop of main.py:327-400 without the video/file output: env must offer reset() -> state and
+    step(a) -> (state, reward, done, info); convert_frame(state) -> (network frame [C,H,W], rgb frame).
+    Returns (cumulative reward, list of chosen actions)."""
+    enc, tr, rew = nets["encoder"], nets["transition"], nets["reward_predictor"]
+    dev = next(enc.parameters()).device
+    no_op = min(no_op, num_actions - 1)
+
+    def frames_to_z(frames, action):
+        x = torch.as_tensor(np.asarray(frames, dtype=np.float32), device=dev).unsqueeze(0)
+        return tr(enc(x), onehot(action, num_actions, dev))
+
+    state = env.reset()
+    frames = [convert_frame(state)[0]]
+    done = False
+    for _ in range(2):  # no-op through the first frames for the initial state estimate (main.py:333-345)
+        state, _, done, _ = env.step(no_op)
+        frames.append(convert_frame(state)[0])
+    z = frames_to_z(frames, no_op)
+    total, chosen, t = 0.0, [], 2
+    while not done:
+        a, scores = choose_action(z.detach(), tr, rew, num_actions, fold_actions=fold_actions)
+        state, r, done, info = env.step(a)
+        total += float(r)
+        chosen.append(a)
+        if on_step is not None:
+            on_step(t, a, scores, r, info)
+        frames = frames[1:] + [convert_frame(state)[0]]
+        z = frames_to_z(frames, a)  # re-estimate the state from the real frames (main.py:389-391)
+        t += 1
+        if t > max_steps:
+            break
+    return total, chosen

@@ -22,11 +22,15 @@ class MovingDots:
         self.rng = np.random.RandomState(seed)
         self.p_done = p_done
 
-    def make_env(self):
-        raise NotImplementedError("synthetic source: trajectories only")
+    def make_env(self, **kwargs):
+        """A gym-style environment with the same dynamics (reset() / step(a)), for the MPC loop of main.py:327-400."""
+        return MovingDotsEnv(self.conv_input_channels, self.height, self.width, self.binary_input_channels,
+                             self.scalar_output_channels, seed=int(self.rng.randint(1 << 30)))
 
     def convert_frame(self, state, **kwargs):
-        return state
+        """-> (network frame [C,H,W] float32, rgb frame [H,W,3] uint8), as datasource.convert_frame does."""
+        rgb = (np.transpose(state[:3], (1, 2, 0)) * 255).astype(np.uint8)
+        return state.astype(np.float32), rgb
 
     def get_trajectories(self, batch_size=32, timesteps=10, random_start=True, training=True):
         C, H, W = self.conv_input_channels, self.height, self.width
@@ -60,3 +64,44 @@ class MovingDots:
                     done = True
                 dones[b, t] = done
         return states, rewards, dones, actions
+
+
+class MovingDotsEnv:
+    """One interactive episode of the MovingDots dynamics: reset() -> frame, step(a) -> (frame, reward, done, info).
+    reward is the sum of the reward channels; info carries them separately, like the reference's environments."""
+
+    def __init__(self, channels=3, height=15, width=19, num_actions=5, num_rewards=2, seed=0, episode_length=40):
+        self.C, self.H, self.W, self.A, self.R = channels, height, width, num_actions, num_rewards
+        self.rng = np.random.RandomState(seed)
+        self.episode_length = episode_length
+        self.reset()
+
+    def _frame(self):
+        f = np.zeros((self.C, self.H, self.W), dtype=np.float32)
+        f[0, self.agent[0], self.agent[1]] = 1.0
+        f[1 % self.C][self.food] = 1.0
+        f[2 % self.C, self.ghost[0], self.ghost[1]] = 1.0
+        return f
+
+    def reset(self):
+        rng, H, W = self.rng, self.H, self.W
+        self.agent = np.array([rng.randint(H), rng.randint(W)])
+        self.ghost = np.array([rng.randint(H), rng.randint(W)])
+        self.gdir = np.array(MOVES[1 + rng.randint(4)])
+        self.food = rng.rand(H, W) < 0.08
+        self.t = 0
+        return self._frame()
+
+    def step(self, action):
+        H, W = self.H, self.W
+        self.agent = (self.agent + np.array(MOVES[int(action) % len(MOVES)])) % (H, W)
+        self.ghost = (self.ghost + self.gdir) % (H, W)
+        info = {}
+        if self.food[self.agent[0], self.agent[1]]:
+            self.food[self.agent[0], self.agent[1]] = False
+            info["food"] = 1.0
+        if self.R > 1 and (self.agent == self.ghost).all():
+            info["ghost"] = -1.0
+        self.t += 1
+        done = self.t >= self.episode_length or not self.food.any()
+        return self._frame(), float(sum(info.values())), done, info

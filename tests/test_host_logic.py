@@ -151,3 +151,22 @@ def test_bucketed_grad_sync_gloo_world2():
     for p in procs:
         p.join(timeout=60)
     assert res == [(0, True), (1, True)]
+
+
+def test_synthetic_env_contract():
+    """MovingDots.make_env(): gym-style reset()/step() with the trajectory source's dynamics (for planner.play)."""
+    import numpy as np
+    from scm_gan_b200.synthetic import MovingDots
+    src = MovingDots(3, 15, 19, 5, 2, seed=1)
+    env = src.make_env()
+    f = env.reset()
+    assert f.shape == (3, 15, 19) and f.dtype == np.float32 and f[0].sum() == 1.0
+    total, done, steps = 0.0, False, 0
+    while not done:
+        f, r, done, info = env.step(steps % 5)
+        assert f.shape == (3, 15, 19) and r == sum(info.values())
+        total += r
+        steps += 1
+    assert steps <= env.episode_length
+    net_frame, rgb = src.convert_frame(f)
+    assert net_frame.shape == (3, 15, 19) and rgb.shape == (15, 19, 3) and rgb.dtype == np.uint8

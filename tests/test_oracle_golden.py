@@ -105,3 +105,18 @@ def test_layers_coordconv_csrn():
     cs = g["csrn"]
     y = R.csrn_forward(cs["state"], cs["x"])
     torch.testing.assert_close(y, cs["y"], rtol=1e-4, atol=1e-3)
+
+
+def test_mpc_planner_matches_reference_play_loop():
+    """oracle.restated.choose_action / compute_rollout_reward against the unmodified reference's
+    `compute_rollout_reward` driven as in `play()` (main.py:356-368, 455-489; oracle/make_golden_planner.py)."""
+    g = load("planner")
+    nets = fresh_nets(g["config"])
+    for k, v in g["sn_before"].items():
+        assert torch.equal(nets["transition"][k], v), k
+    best, scores = R.choose_action(nets, g["z0"], g["config"]["A"], training=False)
+    ref = g["scores"]
+    assert best == g["best_action"]
+    assert torch.allclose(scores, ref, rtol=1e-4, atol=1e-3), (scores, ref)
+    for k, v in g["sn_after"].items():  # 65 Transition calls advanced the power iteration identically
+        assert torch.allclose(nets["transition"][k], v, rtol=1e-4, atol=1e-5), k
