@@ -314,9 +314,23 @@ def main():
     loss_host = torch.zeros((), dtype=torch.float32).pin_memory()
     sync_all()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # public API for host-resident data: scm_gan_b200.data.InputPipeline (double-buffered pinned-host -> device
+    # copies on a copy stream).  Every step's inputs cross PCIe inside the timed region; the copy of step i+1 is in
+    # flight while step i computes.
+    from scm_gan_b200.data import InputPipeline
+    pipe = InputPipeline(trainer, host, depth=2, device=dev)
+    if not use_graph:
+        pipe = None
     f0.record()
+    if pipe is not None:
+        pipe.submit(host)
     for i in range(args.steps):
-        loss = run_step(i, from_host=True)
+        if pipe is not None:
+            if i + 1 < args.steps:
+                pipe.submit(host)
+            loss = pipe.step(theta, cf_now=((i + args.cf_phase) % CF_RATE == 0), use_graph=True)
+        else:
+            loss = run_step(i, from_host=True)
         loss_host.copy_(loss.detach(), non_blocking=True)
         torch.cuda.current_stream().synchronize()  # the caller reads the loss every step
     f1.record()
