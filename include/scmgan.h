@@ -101,6 +101,33 @@ typedef struct {
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 
+/* One directional sweep of CSRN (reference spatial_recurrent.py:61-114; interface-only layer: imported by models.py:14,
+ * never instantiated by main.py).  Lines are visited in order (or reversed); per line: single-step bias-free GRU on the
+ * line's n pixels with the hidden state handed over from the previous line, context = GRU output, next hidden state =
+ * tanh(Conv1d_k3,p1(output) + b).  x, ctx, dx and dctx share the strides xs_* (element units) over [B][C][line][pixel]:
+ * a row sweep of a dense [B,C,H,W] tensor uses xs_line = W, xs_pix = 1, L = H, n = W; a column sweep xs_line = 1,
+ * xs_pix = W, L = W, n = H.  `states` [B][L][n][C] receives the hidden state entering every line (needed by bwd).
+ * bwd: dctx and ctx (the forward output) in, dx out, and per-sample parameter-gradient partials
+ * dparams [B][3C*C (dW_ih) + 3C*C (dW_hh) + 3C*C (dconv_w, [C][C][3]) + C (dconv_b)] which the caller zeroes
+ * beforehand and sums over B afterwards (deterministic).  Limits: 12*n*C*4 bytes of shared memory (<= 227 KB). */
+typedef struct {
+    const float* x;
+    long long xs_b, xs_c, xs_line, xs_pix;
+    int B, C, L, n;
+    int reverse;
+    const float* w_ih;   /* [3C][C] GRU weight_ih_l0 (gates r, z, n) */
+    const float* w_hh;   /* [3C][C] GRU weight_hh_l0 */
+    const float* conv_w; /* [C][C][3] */
+    const float* conv_b; /* [C] */
+    float* ctx;          /* fwd: output.  bwd: forward output (read) */
+    float* states;       /* [B][L][n][C] */
+    const float* dctx;   /* bwd */
+    float* dx;           /* bwd */
+    float* dparams;      /* bwd */
+} scmgan_csrn_sweep_desc;
+int scmgan_gru_conv_sweep_fwd(const scmgan_csrn_sweep_desc* desc_host, scmgan_stream_t stream);
+int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* desc_host, scmgan_stream_t stream);
+
 /* out[i] = uniform in (0,1) number i of the Philox4x32-10 stream {seed, offset} held in rng_state (element i uses
  * counter offset + i/4, lane i%4: the very numbers the in-kernel Bernoulli head of scmgan_conv3x3_fwd draws for
  * element i), then offset += ceil(n/4).  Feeds `uniforms` of the Transition's last conv: generating the stream in

@@ -54,6 +54,14 @@ class SnBwdLayer(C.Structure):
                 ("rows", C.c_int), ("cols", C.c_int), ("accumulate", C.c_int)]
 
 
+class CsrnSweepDesc(C.Structure):
+    _fields_ = [("x", C.c_void_p), ("xs_b", C.c_longlong), ("xs_c", C.c_longlong), ("xs_line", C.c_longlong),
+                ("xs_pix", C.c_longlong), ("B", C.c_int), ("C", C.c_int), ("L", C.c_int), ("n", C.c_int),
+                ("reverse", C.c_int), ("w_ih", C.c_void_p), ("w_hh", C.c_void_p), ("conv_w", C.c_void_p),
+                ("conv_b", C.c_void_p), ("ctx", C.c_void_p), ("states", C.c_void_p), ("dctx", C.c_void_p),
+                ("dx", C.c_void_p), ("dparams", C.c_void_p)]
+
+
 class AdamChunk(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
                 ("n", C.c_int), ("clip", C.c_float), ("step", C.c_void_p)]
@@ -97,6 +105,8 @@ SIGNATURES = {
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_gru_conv_sweep_fwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
+    "scmgan_gru_conv_sweep_bwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_philox_uniform": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
     "scmgan_clip_adam": (C.c_int, [C.c_int, C.POINTER(AdamChunk), C.c_float, C.c_float, C.c_float, C.c_float,
                                    C.c_int, C.c_void_p, C.c_float, C.c_void_p]),

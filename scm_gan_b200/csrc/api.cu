@@ -7,6 +7,7 @@
 #include "conv_wgrad.cuh"
 #include "conv_wgrad_v2.cuh"
 #include "conv_wgrad_narrow.cuh"
+#include "csrn_sweep.cuh"
 #include "elementwise.cuh"
 #include "host_util.cuh"
 
@@ -990,6 +991,64 @@ int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, 
                            long long per, float* loss_scratch, float* dx, scmgan_stream_t stream) {
     SCM_REQUIRE(dx != nullptr && loss_scratch != nullptr, "decoder_bce_bwd: dx and a scratch scalar are required");
     return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss_scratch, dx, stream);
+}
+
+static int csrn_fill(const scmgan_csrn_sweep_desc* d, CsrnSweepParams& P, bool bwd) {
+    SCM_REQUIRE(d != nullptr, "gru_conv_sweep: null descriptor");
+    SCM_REQUIRE(d->x && d->w_ih && d->w_hh && d->conv_w && d->conv_b && d->ctx, "gru_conv_sweep: null pointer");
+    SCM_REQUIRE(d->B > 0 && d->C > 0 && d->L > 0 && d->n > 0, "gru_conv_sweep: bad geometry");
+    SCM_REQUIRE(!bwd || (d->states && d->dctx && d->dx && d->dparams), "gru_conv_sweep_bwd: null pointer");
+    memset(&P, 0, sizeof(P));
+    P.x = d->x; P.xs_b = d->xs_b; P.xs_c = d->xs_c; P.xs_line = d->xs_line; P.xs_pix = d->xs_pix;
+    P.B = d->B; P.C = d->C; P.L = d->L; P.n = d->n; P.reverse = d->reverse;
+    P.w_ih = d->w_ih; P.w_hh = d->w_hh; P.conv_w = d->conv_w; P.conv_b = d->conv_b;
+    P.states = d->states;
+    if (bwd) {
+        P.ctx = const_cast<float*>(d->dctx); P.ctx_fwd = d->ctx; P.dx = d->dx; P.dparams = d->dparams;
+    } else {
+        P.ctx = d->ctx;
+    }
+    return SCM_OK;
+}
+
+int scmgan_gru_conv_sweep_fwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t stream) {
+    CsrnSweepParams P;
+    int rc = csrn_fill(d, P, false);
+    if (rc) return rc;
+    const size_t smem = size_t(3) * P.n * P.C * sizeof(float);
+    if (smem > size_t(kSmemMax)) {
+        set_error("gru_conv_sweep_fwd: line of %d x %d does not fit shared memory", P.n, P.C);
+        return SCM_EUNSUPPORTED;
+    }
+    static bool attr = false;
+    if (!attr) {
+        SCM_CUDA(cudaFuncSetAttribute(csrn_sweep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr = true;
+    }
+    csrn_sweep_fwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t stream) {
+    CsrnSweepParams P;
+    int rc = csrn_fill(d, P, true);
+    if (rc) return rc;
+    const size_t smem = size_t(12) * P.n * P.C * sizeof(float);
+    if (smem > size_t(kSmemMax)) {
+        set_error("gru_conv_sweep_bwd: line of %d x %d does not fit shared memory", P.n, P.C);
+        return SCM_EUNSUPPORTED;
+    }
+    static bool attr = false;
+    if (!attr) {
+        SCM_CUDA(cudaFuncSetAttribute(csrn_sweep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
+        attr = true;
+    }
+    csrn_sweep_bwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
 }
 
 int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream) {

@@ -12,6 +12,8 @@ import torch
 from torch import nn
 from torch.nn import functional as F
 
+from scm_gan_b200 import ops as _ops  # noqa: F401  (registers torch.ops.scmgan.*)
+
 
 def _explode_init(t, channels):
     # deliberately huge N(0, channels) init: "the RNN gradient should explode, not vanish" (spatial_recurrent.py:9-18)
@@ -61,9 +63,22 @@ class CSRN(nn.Module):
                 context[:, :, :, i] = out
             state = torch.tanh(conv(out)).permute(0, 2, 1).reshape(b * n, c)
 
+    def _native_sweep(self, x, direction, along_rows, reverse):
+        """One sweep through the hand-written kernels (scmgan::csrn_sweep -> scmgan_gru_conv_sweep_fwd/bwd)."""
+        gru, conv = getattr(self, "rnn_" + direction), getattr(self, "conv_" + direction)
+        return torch.ops.scmgan.csrn_sweep(x, gru.weight_ih_l0, gru.weight_hh_l0, conv.weight, conv.bias,
+                                           along_rows, reverse)[0]
+
     def forward(self, x):
         b, c, h, w = x.shape
         assert c == self.channels
+        if x.is_cuda and 12 * max(h, w) * c * 4 <= 227 * 1024:
+            above = self._native_sweep(x, "down", True, False)
+            below = self._native_sweep(x, "up", True, True)
+            # sic (reference line 110): the right-to-left sweep is stored as the LEFT context, overwriting every
+            # column of the left-to-right sweep (whose result is therefore never used), and the right context is zero
+            left = self._native_sweep(x, "right", False, True)
+            return self.conv_combine(torch.cat((above, below, left, torch.zeros_like(x)), dim=1))
         above, below, left, right = (x.new_zeros(b, c, h, w) for _ in range(4))
         self._sweep(x, "down", above, range(h), True)
         self._sweep(x, "up", below, reversed(range(h)), True)

@@ -142,6 +142,35 @@ def spectral_norm_bwd(layers):
     L.check(L.lib().scmgan_spectral_norm_bwd(len(layers), arr, _stream()), "scmgan_spectral_norm_bwd")
 
 
+def _csrn_desc(x, along_rows, reverse, w_ih, w_hh, conv_w, conv_b, ctx, states):
+    B, Cc, H, W = x.shape
+    assert x.is_contiguous() and ctx.is_contiguous() and x.dtype == torch.float32
+    d = L.CsrnSweepDesc()
+    d.x, d.xs_b, d.xs_c = x.data_ptr(), Cc * H * W, H * W
+    if along_rows:   # lines are image rows
+        d.xs_line, d.xs_pix, d.L, d.n = W, 1, H, W
+    else:            # lines are image columns
+        d.xs_line, d.xs_pix, d.L, d.n = 1, W, W, H
+    d.B, d.C, d.reverse = B, Cc, int(reverse)
+    d.w_ih, d.w_hh = w_ih.data_ptr(), w_hh.data_ptr()
+    d.conv_w, d.conv_b = conv_w.data_ptr(), conv_b.data_ptr()
+    d.ctx, d.states = ctx.data_ptr(), L.ptr(states)
+    return d
+
+
+def csrn_sweep_fwd(x, along_rows, reverse, w_ih, w_hh, conv_w, conv_b, ctx, states=None):
+    """One CSRN sweep (see include/scmgan.h): x, ctx [B,C,H,W] dense fp32; states [B, L, n, C] or None."""
+    d = _csrn_desc(x, along_rows, reverse, w_ih, w_hh, conv_w, conv_b, ctx, states)
+    L.check(L.lib().scmgan_gru_conv_sweep_fwd(C.byref(d), _stream()), "scmgan_gru_conv_sweep_fwd")
+
+
+def csrn_sweep_bwd(x, along_rows, reverse, w_ih, w_hh, conv_w, conv_b, ctx, states, dctx, dx, dparams):
+    d = _csrn_desc(x, along_rows, reverse, w_ih, w_hh, conv_w, conv_b, ctx, states)
+    assert dctx.is_contiguous() and dx.is_contiguous() and dparams.is_contiguous()
+    d.dctx, d.dx, d.dparams = dctx.data_ptr(), dx.data_ptr(), dparams.data_ptr()
+    L.check(L.lib().scmgan_gru_conv_sweep_bwd(C.byref(d), _stream()), "scmgan_gru_conv_sweep_bwd")
+
+
 def philox_uniform(out, rng_state):
     """out (fp32, contiguous) <- the next out.numel() uniforms of the device Philox stream rng_state (int64 [2])."""
     L.check(L.lib().scmgan_philox_uniform(out.data_ptr(), out.numel(), rng_state.data_ptr(), _stream()),

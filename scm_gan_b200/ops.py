@@ -389,3 +389,59 @@ def _cf_backward(ctx, grads):
 
 
 cf_loss.register_autograd(_cf_backward, setup_context=_cf_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CSRN directional sweep (reference spatial_recurrent.py:61-114; interface-only layer)
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::csrn_sweep", mutates_args=())
+def csrn_sweep(x: Tensor, w_ih: Tensor, w_hh: Tensor, conv_w: Tensor, conv_b: Tensor, along_rows: bool,
+               reverse: bool) -> List[Tensor]:
+    """-> [context map (same shape as x), hidden state entering every line [B, L, n, C]]."""
+    _require_cuda(x, w_ih, w_hh, conv_w, conv_b)
+    x = x.contiguous().float()
+    B, Cc, H, W = x.shape
+    lines, n = (H, W) if along_rows else (W, H)
+    ctx = torch.empty_like(x)
+    states = torch.empty((B, lines, n, Cc), dtype=torch.float32, device=x.device)
+    K.csrn_sweep_fwd(x, along_rows, reverse, w_ih.contiguous().float(), w_hh.contiguous().float(),
+                     conv_w.contiguous().float(), conv_b.contiguous().float(), ctx, states)
+    return [ctx, states]
+
+
+@torch.library.custom_op("scmgan::csrn_sweep_bwd", mutates_args=())
+def csrn_sweep_bwd(dctx: Tensor, x: Tensor, ctx: Tensor, states: Tensor, w_ih: Tensor, w_hh: Tensor, conv_w: Tensor,
+                   conv_b: Tensor, along_rows: bool, reverse: bool) -> List[Tensor]:
+    """-> [dx, dW_ih, dW_hh, dconv_w, dconv_b]."""
+    _require_cuda(dctx, x)
+    x = x.contiguous().float()
+    B, Cc = x.shape[0], x.shape[1]
+    dx = torch.empty_like(x)
+    per = 9 * Cc * Cc + Cc
+    dparams = torch.zeros((B, per), dtype=torch.float32, device=x.device)
+    K.csrn_sweep_bwd(x, along_rows, reverse, w_ih.contiguous().float(), w_hh.contiguous().float(),
+                     conv_w.contiguous().float(), conv_b.contiguous().float(), ctx, states,
+                     dctx.contiguous().float(), dx, dparams)
+    tot = dparams.sum(0)  # fixed-order sum over the per-sample partials
+    cc3 = 3 * Cc * Cc
+    return [dx, tot[:cc3].view(3 * Cc, Cc).clone(), tot[cc3:2 * cc3].view(3 * Cc, Cc).clone(),
+            tot[2 * cc3:3 * cc3].view(Cc, Cc, 3).clone(), tot[3 * cc3:].clone()]
+
+
+def _csrn_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    x, w_ih, w_hh, conv_w, conv_b, along_rows, reverse = inputs
+    ctx.flags = (along_rows, reverse)
+    ctx.save_for_backward(x, w_ih, w_hh, conv_w, conv_b, output[0], output[1])
+
+
+def _csrn_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 7
+    x, w_ih, w_hh, conv_w, conv_b, out, states = ctx.saved_tensors
+    dx, dwi, dwh, dcw, dcb = torch.ops.scmgan.csrn_sweep_bwd(grads[0], x, out, states, w_ih, w_hh, conv_w, conv_b,
+                                                            ctx.flags[0], ctx.flags[1])
+    return dx, dwi, dwh, dcw, dcb, None, None
+
+
+csrn_sweep.register_autograd(_csrn_backward, setup_context=_csrn_setup)

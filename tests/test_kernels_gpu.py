@@ -481,3 +481,39 @@ def test_masked_mse():
     (ggot,) = torch.autograd.grad(got * 2.0, p2)
     assert report("masked mse", got, ref, 1e-6)
     assert report("masked mse grad", ggot, 2.0 * gref, 1e-6)
+
+
+@pytest.mark.parametrize("shape", [(2, 8, 6, 7), (3, 16, 12, 9), (2, 32, 16, 16)])
+def test_csrn_native_sweeps_vs_oracle(shape):
+    """scmgan_gru_conv_sweep_fwd/bwd (interface-only layer CSRN, reference spatial_recurrent.py:61-114): output and
+    every gradient of the drop-in module on CUDA (hand-written sweep kernels) against the fp32 oracle restatement
+    differentiated by torch autograd."""
+    _setup()
+    import sys
+    from oracle import restated as R
+    from scm_gan_b200.train_step import import_dropin_models
+    import_dropin_models()
+    CSRN = sys.modules["spatial_recurrent"].CSRN
+    B, C, H, W = shape
+    torch.manual_seed(3)
+    net = CSRN(C).to(DEV)
+    with torch.no_grad():  # the reference's N(0, channels) init saturates every gate; use a scale with live gradients
+        for n_, p in net.named_parameters():
+            if "combine" not in n_:
+                p.normal_(0, 0.5 / C ** 0.5)
+    x = (torch.randn(B, C, H, W, device=DEV) * 0.7).requires_grad_(True)
+    y = net(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    sd = {k: v.detach().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+    x2 = x.detach().clone().requires_grad_(True)
+    yr = R.csrn_forward(sd, x2)
+    yr.backward(gy)
+    assert report(f"csrn fwd {shape}", y, yr, 1e-5)
+    assert report(f"csrn dx {shape}", x.grad, x2.grad, 1e-4)
+    for k, p in net.named_parameters():
+        ref = sd[k].grad
+        if ref is None or ref.abs().max().item() == 0:   # rnn_left / conv_left: overwritten by the reference quirk
+            assert p.grad is None or p.grad.abs().max().item() == 0, k
+            continue
+        assert report(f"csrn d{k} {shape}", p.grad, ref, 1e-4)
