@@ -49,6 +49,11 @@ long long scmgan_launch_count(void);
 int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
                      int c_off, int c_pad, int wrap, const float* sig, scmgan_stream_t stream);
 
+/* CoordConv coordinate channels (reference coordconv.py:10-14; interface-only layer): plane channel c_off of interior
+ * pixel (h, w) <- -1 + 2w/W and channel c_off+1 <- -1 + 2h/H, for every sample.  Run after scmgan_pack_nchw has
+ * filled (zeroed) the channel window; replaces the arange/repeat/cat of the reference. */
+int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, scmgan_stream_t stream);
+
 /* Weight packing fp32 parameter -> bf16 [9][n_pad][k_pad] GEMM operand, optionally divided by *sigma
  * (the `w / sigma` of reference spectral_normalization.py:35).
  *   out[tap][n][k] = w[n*s_n + (k+k_src_off)*s_k + (flip ? 8-tap : tap)] / sigma

@@ -105,6 +105,7 @@ SIGNATURES = {
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_pack_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scmgan_gru_conv_sweep_fwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_gru_conv_sweep_bwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_philox_uniform": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),

@@ -671,6 +671,17 @@ int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int 
     return SCM_OK;
 }
 
+int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, scmgan_stream_t stream) {
+    SCM_REQUIRE(dst_plane && B > 0 && H > 0 && W > 0, "pack_coords: bad arguments");
+    SCM_REQUIRE(c_off % 2 == 0 && c_off + 2 <= Cs, "pack_coords: bad channel window (Cs=%d off=%d)", Cs, c_off);
+    const long long total = (long long)B * H * W;
+    pack_coords_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, B, H, W);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t stream) {
     SCM_REQUIRE(count >= 0 && (count == 0 || jobs), "pack_weights: bad arguments");
     for (int base = 0; base < count; base += kMaxPackJobs) {

@@ -52,6 +52,17 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
     }
 }
 
+// CoordConv coordinate channels: x coordinate -1 + 2w/W at channel c_off, y coordinate -1 + 2h/H at c_off + 1 of every
+// interior pixel (reference coordconv.py:10-14).
+__global__ void pack_coords_kernel(__nv_bfloat16* __restrict__ dst, int Cs, int c_off, int B, int H, int W) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * H * W) return;
+    const int w = int(i % W), h = int((i / W) % H), b = int(i / ((long long)W * H));
+    const long long p = ((long long)b * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
+    const __nv_bfloat162 v = __floats2bfloat162_rn(-1.f + 2.f * float(w) / float(W), -1.f + 2.f * float(h) / float(H));
+    *reinterpret_cast<__nv_bfloat162*>(dst + p * Cs + c_off) = v;
+}
+
 // ----------------------------------------------------------------------------------------------
 // Weight packing: fp32 parameter tensor -> bf16 [9][n_pad][k_pad] (K-major B operand of the implicit GEMM).
 //   out[tap][n][k] = W[n*s_n + k*s_k + (flip ? 8-tap : tap)] / sigma      (zero outside n_valid x k_valid)

@@ -9,6 +9,8 @@ with the reference on square inputs.
 import torch
 from torch import nn
 
+from scm_gan_b200 import ops as _ops  # noqa: F401  (registers torch.ops.scmgan.*)
+
 
 class CoordConv2d(nn.Module):
     def __init__(self, *args, **kwargs):
@@ -21,7 +23,17 @@ class CoordConv2d(nn.Module):
         ys = -1.0 + 2.0 * torch.arange(height, device=device, dtype=dtype) / height
         return xs.view(1, 1, 1, width).expand(1, 1, height, width), ys.view(1, 1, height, 1).expand(1, 1, height, width)
 
+    def _native_ok(self, x):
+        c = self.conv
+        return (x.is_cuda and c.kernel_size == (3, 3) and c.stride == (1, 1) and c.padding == (1, 1)
+                and c.dilation == (1, 1) and c.groups == 1 and c.padding_mode == "zeros" and x.shape[1] % 2 == 0
+                and c.out_channels <= 128)
+
     def forward(self, x):
+        if self._native_ok(x):
+            # 3x3 / stride 1 / pad 1: hand-written path - coordinates synthesised into the bf16 input plane, tcgen05
+            # implicit-GEMM conv (bf16 operands, fp32 accumulation), dgrad/wgrad kernels behind autograd
+            return torch.ops.scmgan.coordconv3x3(x, self.conv.weight, self.conv.bias)[0]
         batch_size, _, height, width = x.shape
         cx, cy = self.coordinates(height, width, x.device, x.dtype)
         x = torch.cat([x, cx.expand(batch_size, -1, -1, -1), cy.expand(batch_size, -1, -1, -1)], dim=1)

@@ -411,3 +411,49 @@ def reward_backward(dr, saved, w1, w2, sink=None):
         sink[3].add_(db2[:co])
     return (dz, g1.clone() if sink[0] is None else None, db1[:RHID].clone() if sink[1] is None else None,
             g2.clone() if sink[2] is None else None, db2[:co].clone() if sink[3] is None else None)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CoordConv2d with a 3x3 / stride 1 / zero-pad 1 convolution (reference coordconv.py:5-15; interface-only layer)
+# ------------------------------------------------------------------------------------------------------------
+def coordconv_forward(x, w, b):
+    """x [B,C,H,W] fp32; w [Co, C+2, 3, 3]; b [Co] or None.  The two coordinate channels are synthesised straight
+    into the bf16 input plane (never concatenated in fp32).  Returns (y [B,Co,H,W], saved)."""
+    dev = x.device
+    B, Cc, H, W = x.shape
+    co, cin = w.shape[0], w.shape[1]
+    assert cin == Cc + 2 and Cc % 2 == 0, "CoordConv2d expects in_channels + 2 (even number of data channels)"
+    Cp, Np = _r16(cin), _r16(co)
+    wf = K.packed_weight(Np, Cp, dev)
+    wd = K.packed_weight(_r16(Cc), HID if Np <= HID else Np, dev)  # dgrad reads the 128-wide gradient plane
+    K.pack_weights([_conv2d_fwd_job(w, wf), _conv2d_dgrad_job(w, wd, None, 0, Cc)])
+    xin = K.new_plane(B, H, W, Cp, dev)
+    K.pack_nchw(x, xin, c_pad=Cp, wrap=False)
+    K.pack_coords(xin, Cc)
+    y = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
+    bp = None
+    if b is not None:
+        bp = b if Np == co else torch.nn.functional.pad(b, (0, Np - co))
+    K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=bp, act=ACT_NONE, out_f32=y, n_valid=co)
+    return y, [xin, wd]
+
+
+def coordconv_backward(dy, saved, w):
+    """-> (dx [B,C,H,W], dW [Co,C+2,3,3], db [Co]).  The gradient plane is 128 channels wide (zero beyond Co) because
+    the weight-gradient kernels want a 128-channel operand."""
+    xin, wd = saved
+    dev = dy.device
+    B, co, H, W = dy.shape
+    cin = w.shape[1]
+    Cc = cin - 2
+    Cp = xin.shape[3]
+    Gp = wd.shape[2]
+    assert co <= Gp
+    dyp = K.new_plane(B, H, W, Gp, dev)
+    K.pack_nchw(dy, dyp, c_pad=Gp, wrap=False)
+    g = torch.zeros_like(w)
+    db = torch.zeros(Gp, dtype=torch.float32, device=dev)
+    K.wgrad(dyp, xin, g, B, H, W, cout=Gp, cin=Cp, g_s_co=cin * 9, g_s_ci=9, co_valid=co, ci_valid=cin, db=db)
+    dx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=dev)
+    K.conv3x3(dyp, wd, B, H, W, cin=Gp, out_f32=dx, n_valid=Cc, dgrad=True)
+    return dx, g, db[:co].clone()

@@ -41,6 +41,13 @@ def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False, sig=None):
                                      c_pad, int(wrap), L.ptr(sig), _stream()), "scmgan_pack_nchw")
 
 
+def pack_coords(dst_plane, c_off):
+    """CoordConv coordinate channels into plane channels c_off (x) and c_off + 1 (y)."""
+    B, Hp, Wp, Cs = dst_plane.shape
+    L.check(L.lib().scmgan_pack_coords(dst_plane.data_ptr(), Cs, c_off, B, Hp - 2, Wp - 2, _stream()),
+            "scmgan_pack_coords")
+
+
 def pack_weights(jobs):
     """jobs: list of dicts(w, out, sigma, n_pad, k_pad, n_valid, k_valid, s_n, s_k, k_src_off, flip); `out` may be a
     K window (a [:, :, a:b] view) of a wider packed operand."""

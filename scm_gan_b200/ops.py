@@ -445,3 +445,37 @@ def _csrn_backward(ctx, grads):
 
 
 csrn_sweep.register_autograd(_csrn_backward, setup_context=_csrn_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CoordConv2d (3x3, stride 1, zero padding 1) on the tcgen05 conv kernels (reference coordconv.py; interface only)
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::coordconv3x3", mutates_args=())
+def coordconv3x3(x: Tensor, w: Tensor, b: Optional[Tensor]) -> List[Tensor]:
+    _require_cuda(x, w)
+    y, saved = E.coordconv_forward(x.contiguous().float(), w.contiguous().float(),
+                                   None if b is None else b.contiguous().float())
+    return [y] + saved
+
+
+@torch.library.custom_op("scmgan::coordconv3x3_bwd", mutates_args=())
+def coordconv3x3_bwd(dy: Tensor, saved: Sequence[Tensor], w: Tensor) -> List[Tensor]:
+    _require_cuda(dy)
+    return list(E.coordconv_backward(dy.contiguous().float(), list(saved), w.contiguous().float()))
+
+
+def _coordconv_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    x, w, b = inputs
+    ctx.w, ctx.has_bias = w, b is not None
+    ctx.save_for_backward(*output[1:])
+
+
+def _coordconv_backward(ctx, grads):
+    if grads[0] is None:
+        return None, None, None
+    dx, dw, db = torch.ops.scmgan.coordconv3x3_bwd(grads[0], list(ctx.saved_tensors), ctx.w)
+    return dx, dw, (db if ctx.has_bias else None)
+
+
+coordconv3x3.register_autograd(_coordconv_backward, setup_context=_coordconv_setup)

@@ -4,6 +4,8 @@ The tensor-core kernels take bf16 operands; the references below are fed the *sa
 (TF32 off), so the only differences are fp32 summation order and the bf16 rounding of stored outputs.
 Tolerances are written next to each check.
 """
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -517,3 +519,40 @@ def test_csrn_native_sweeps_vs_oracle(shape):
             assert p.grad is None or p.grad.abs().max().item() == 0, k
             continue
         assert report(f"csrn d{k} {shape}", p.grad, ref, 1e-4)
+
+
+@pytest.mark.parametrize("shape", [(2, 6, 12, 12, 16), (3, 14, 16, 16, 32), (2, 30, 10, 13, 24)])
+def test_coordconv_native_vs_torch(shape):
+    """CoordConv2d 3x3/s1/p1 on the hand-written path (scmgan_pack_coords + tcgen05 conv, dgrad, wgrad) against the
+    same layer evaluated by torch in fp32 (coordinates concatenated as in reference coordconv.py:10-15).  bf16
+    operands: 1e-2 relative."""
+    _setup()
+    import sys
+    from scm_gan_b200.train_step import import_dropin_models
+    import_dropin_models()
+    CoordConv2d = sys.modules["coordconv"].CoordConv2d
+    B, C, H, W, Co = shape
+    torch.manual_seed(4)
+    net = CoordConv2d(C + 2, Co, 3, padding=1).to(DEV)
+    x = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
+    assert net._native_ok(x)
+    y = net(x)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    x2 = x.detach().clone().requires_grad_(True)
+    cx, cy = net.coordinates(H, W, DEV, torch.float32)
+    xin = torch.cat([x2, cx.expand(B, -1, -1, -1), cy.expand(B, -1, -1, -1)], dim=1)
+    w2 = net.conv.weight.detach().clone().requires_grad_(True)
+    b2 = net.conv.bias.detach().clone().requires_grad_(True)
+    yr = torch.nn.functional.conv2d(xin, w2, b2, padding=1)
+    yr.backward(gy)
+    assert report(f"coordconv fwd {shape}", y, yr, 1e-2)
+    assert report(f"coordconv dx {shape}", x.grad, x2.grad, 1e-2)
+    assert report(f"coordconv dW {shape}", net.conv.weight.grad, w2.grad, 1e-2)
+    assert report(f"coordconv db {shape}", net.conv.bias.grad, b2.grad, 1e-2)
+    if shape == (2, 6, 12, 12, 16):  # the layer recorded from the unmodified reference (tests/golden/layers.pt)
+        g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "layers.pt"), weights_only=False)["coordconv"]
+        ref = CoordConv2d(6 + 2, 16, 3, padding=1).to(DEV)
+        ref.load_state_dict(g["state"])
+        with torch.no_grad():
+            assert report("coordconv vs reference golden", ref(g["x"].to(DEV)), g["y"].to(DEV), 1e-2)
