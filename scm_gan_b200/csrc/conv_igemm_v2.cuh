@@ -78,7 +78,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         prefetch_tmap(&tmap_a);
         prefetch_tmap(&tmap_b);
         for (int s = 0; s < G.num_stages; ++s) {
-            mbar_init(&full_bar[s], 1);
+            mbar_init(&full_bar[s], (CK == 16 && G.a_soft) ? 32 : 1);  // software staging: one arrival per producer lane
             mbar_init(&empty_bar[s], 1);
         }
         for (int s = 0; s < 2; ++s) {
@@ -118,46 +118,35 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         if (CK == 16 && G.a_soft) {
             // Narrow K (Cin = 16): a plane row is 32 bytes, and a TMA box of 32-byte rows is bound by the TMA's
             // request rate (measured: 3.7k cycles per 128-row tile for 9 x 4 KB boxes).  The producer warp instead
-            // copies ONE super tile (128 + 2*Wp + 2 rows, all nine taps) per tile with 16-byte loads, one tile ahead
-            // in registers, and writes it in the 32-byte-swizzled K-major layout (address bit 4 ^= bit 7, on the
-            // absolute shared-memory address, which is also what the row-shifted UMMA descriptors assume).
+            // copies ONE super tile (128 + 2*Wp + 2 rows, all nine taps) per tile with 16-byte cp.async, writing the
+            // 32-byte-swizzled K-major layout itself (address bit 4 ^= bit 7 on the absolute shared-memory address,
+            // which is also what the row-shifted UMMA descriptors assume; rows outside the tensor are zero-filled).
+            // Completion is signalled by cp.async.mbarrier.arrive, so the producer runs num_stages tiles ahead and
+            // no global-memory latency sits between two tiles.
             constexpr int kIt = 17;  // 17 x 32 lanes x 16 B >= 272 rows
             const int nch = G.box_rows * 2;
-            uint4 buf[kIt];
-            auto fetch = [&](int tile) {
+            for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+                mbar_wait(&empty_bar[stage], phase ^ 1);
+                const uint32_t sa = smem_u32(s_a + size_t(stage) * G.a_stage_bytes);
                 const int row0 = tile * 128 - P.Wp - 1;
 #pragma unroll
                 for (int it = 0; it < kIt; ++it) {
                     const int i = it * 32 + lane;
-                    const int row = row0 + (i >> 1);
-                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                    if (i < nch && row >= 0 && row < P.rows)
-                        v = __ldg(reinterpret_cast<const uint4*>(P.a + size_t(row) * P.a_cs + P.a_c_off) + (i & 1));
-                    buf[it] = v;
-                }
-            };
-            int tile = blockIdx.x;
-            if (tile < P.num_tiles) fetch(tile);
-            for (; tile < P.num_tiles; tile += G.tiles_stride) {
-                mbar_wait(&empty_bar[stage], phase ^ 1);
-                const uint32_t sa = smem_u32(s_a + size_t(stage) * G.a_stage_bytes);
-#pragma unroll
-                for (int it = 0; it < kIt; ++it) {
-                    const int i = it * 32 + lane;
                     if (i < nch && !(P.debug & 8)) {
+                        const int row = row0 + (i >> 1);
+                        const bool ok = row >= 0 && row < P.rows;
+                        const __nv_bfloat16* src = P.a + (ok ? size_t(row) * P.a_cs + P.a_c_off + (i & 1) * 8 : 0);
                         uint32_t ad = sa + uint32_t(i) * 16u;
                         ad ^= (ad >> 3) & 16u;
-                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(buf[it].x),
-                                     "r"(buf[it].y), "r"(buf[it].z), "r"(buf[it].w)
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ad), "l"(src),
+                                     "r"(ok ? 16u : 0u)
                                      : "memory");
                     }
                 }
-                fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async proxy
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&full_bar[stage]);
+                // every lane: one (non-incrementing) arrival on the stage's full barrier once its copies have landed
+                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage]))
+                             : "memory");
                 if (++stage == G.num_stages) { stage = 0; phase ^= 1; }
-                const int nt = tile + G.tiles_stride;
-                if (nt < P.num_tiles) fetch(nt);
             }
         } else
         for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
@@ -208,6 +197,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
 #pragma unroll 1
                 for (int c = 0; c < chunks; ++c) {
                     mbar_wait(&full_bar[stage], phase);
+                    if (CK == 16 && G.a_soft) fence_proxy_async_smem();  // cp.async (generic proxy) -> tensor core
                     tc_fence_after();
                     const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * a_stage16);
                     const uint64_t b_st = bdesc0 + uint64_t(uint32_t(g * TPG * chunks + c) * b_tile16);
