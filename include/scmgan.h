@@ -102,6 +102,8 @@ typedef struct {
     const float* uniforms; /* [B][n_valid][H][W] or NULL */
     unsigned long long* rng_state; /* device {seed, offset}: with sample_out and uniforms == NULL the Bernoulli draw uses an
                                       in-kernel Philox4x32-10 stream and the offset is advanced; NULL => threshold 0.5 */
+    int bias_n; /* number of valid entries of `bias` (channels beyond it get 0); 0 = n.  Lets a layer with 3 or 12
+                   real output channels pass its own bias vector although n is padded to 16. */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);

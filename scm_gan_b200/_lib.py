@@ -31,7 +31,8 @@ class ConvDesc(C.Structure):
                 ("add", C.c_void_p), ("add_cs", C.c_int), ("add_c_off", C.c_int),
                 ("gate", C.c_void_p), ("gate_cs", C.c_int), ("gate_c_off", C.c_int),
                 ("out_f32", C.c_void_p), ("n_valid", C.c_int),
-                ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p)]
+                ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p),
+                ("bias_n", C.c_int)]
 
 
 class WgradDesc(C.Structure):

@@ -346,6 +346,7 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     P.cin_chunks = d->cin / CK;
     P.a_c_off = d->x_c_off;
     P.a = reinterpret_cast<const __nv_bfloat16*>(d->x); P.a_cs = d->x_cs;
+    P.bias_n = d->bias_n > 0 ? std::min(d->bias_n, d->n) : d->n;
     P.scale = d->scale; P.bias = d->bias; P.sample_bias = d->sample_bias; P.act = d->act; P.slope = d->slope;
     P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
     P.wrap = d->wrap;

@@ -37,7 +37,8 @@ struct IgemmParams {
     int a_cs;                // its channel stride
     // epilogue
     float scale;               // multiplies the accumulator (1/sigma folding, loss scaling)
-    const float* bias;         // [n] or nullptr
+    const float* bias;         // [bias_n] or nullptr
+    int bias_n;                // valid entries of bias (channels >= bias_n get 0)
     const float* sample_bias;  // [B][n] per-sample bias (folded action channels) or nullptr
     int act;                   // ACT_*
     float slope;               // LeakyReLU negative slope
@@ -241,7 +242,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     float x = v[i] * P.scale;
-                    if (P.bias) x += __ldg(P.bias + n0 + i);
+                    if (P.bias && n0 + i < P.bias_n) x += __ldg(P.bias + n0 + i);
                     if (P.sample_bias) x += __ldg(P.sample_bias + size_t(b) * P.n + n0 + i);
                     v[i] = x;
                 }

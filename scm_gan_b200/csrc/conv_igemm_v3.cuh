@@ -66,7 +66,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_relinquish_pair();
     }
     if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < n_full; i += 32 * kV2EpiWarps) s_bias[i] = P.bias ? P.bias[i] : 0.f;
+        for (int i = threadIdx.x - 64; i < n_full; i += 32 * kV2EpiWarps) s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
     }
     tc_fence_before();
     __syncthreads();

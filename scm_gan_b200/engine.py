@@ -110,13 +110,12 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     K.conv3x3(buf5, wf[4], B, H, W, cin=2 * HID, bias=bias[4], out=buf6, out_c_off=0, **cv)         # conv5
     p = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     zn = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
-    b6p = b6 if Lp == L else torch.nn.functional.pad(b6, (0, Lp - L))
     if training and uniforms is None and rng_state is not None:
         # the module's Philox stream, generated in its own pass (same numbers as the in-kernel head would draw,
         # ~10x cheaper than evaluating Philox inside the conv epilogue)
         uniforms = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
         K.philox_uniform(uniforms, rng_state)
-    K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6p, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
+    K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
               uniforms=uniforms if training else None)                                              # conv6 + head
     return zn, p, [zin, buf6, buf5, act3] + wd
 
@@ -219,8 +218,7 @@ def encoder_forward(x, wbar, bias, sigma, w4, b4):
     K.conv3x3(a1, wf[1], B, H, W, cin=HID, bias=bias[1], act=ACT_LRELU, out=a2)
     K.conv3x3(a2, wf[2], B, H, W, cin=HID, bias=bias[2], act=ACT_LRELU, out=a3)
     z = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
-    b4p = b4 if Lp == L else torch.nn.functional.pad(b4, (0, Lp - L))
-    K.conv3x3(a3, wf[3], B, H, W, cin=HID, bias=b4p, act=ACT_SIGMOID, out_f32=z, n_valid=L)
+    K.conv3x3(a3, wf[3], B, H, W, cin=HID, bias=b4, act=ACT_SIGMOID, out_f32=z, n_valid=L)
     return z, [xin, a1, a2, a3] + wd
 
 
@@ -296,8 +294,7 @@ def decoder_forward(z, w1, b1, w2, b2):
     hidp = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     logits = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
-    b2p = b2 if cop == co else torch.nn.functional.pad(b2, (0, cop - co))
-    K.conv3x3(hidp, wf2, B, H, W, cin=hid, bias=b2p, act=ACT_NONE, out_f32=logits, n_valid=co)
+    K.conv3x3(hidp, wf2, B, H, W, cin=hid, bias=b2, act=ACT_NONE, out_f32=logits, n_valid=co)
     return logits, [zin, hidp, wd1, wd2]
 
 
@@ -370,7 +367,7 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     hidp = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     y2 = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
-    K.conv3x3(hidp, wf2, B, H, W, cin=RHID, bias=torch.nn.functional.pad(b2, (0, 16 - co)), act=ACT_NONE,
+    K.conv3x3(hidp, wf2, B, H, W, cin=RHID, bias=b2, act=ACT_NONE,
               out_f32=y2, n_valid=co)
     r = torch.empty((B, R), dtype=torch.float32, device=dev)
     h2, w2s = (H - 5) // 2 + 1, (W - 5) // 2 + 1
@@ -431,10 +428,7 @@ def coordconv_forward(x, w, b):
     K.pack_nchw(x, xin, c_pad=Cp, wrap=False)
     K.pack_coords(xin, Cc)
     y = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
-    bp = None
-    if b is not None:
-        bp = b if Np == co else torch.nn.functional.pad(b, (0, Np - co))
-    K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=bp, act=ACT_NONE, out_f32=y, n_valid=co)
+    K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=b, act=ACT_NONE, out_f32=y, n_valid=co)
     return y, [xin, wd]
 
 

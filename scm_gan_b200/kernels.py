@@ -75,6 +75,7 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     d.x, d.x_cs, d.x_c_off, d.cin = x_plane.data_ptr(), x_plane.shape[3], x_c_off, cin
     d.w, d.n = w_packed.data_ptr(), n
     d.scale, d.bias, d.sample_bias = scale, L.ptr(bias), L.ptr(sample_bias)
+    d.bias_n = 0 if bias is None else min(int(bias.numel()), n)  # shorter than n: the padded channels get no bias
     d.act, d.slope = act, LRELU_SLOPE
     d.out = L.ptr(out)
     d.out_cs = out.shape[3] if out is not None else 0

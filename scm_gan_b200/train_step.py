@@ -69,18 +69,18 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     z_orig = z.clone()
     # active_mask_t = prod_{s<=t} (1 - done_s)   (main.py:178)
     masks = torch.cumprod(1.0 - dones[:, 1:], dim=1)
-    loss = torch.zeros((), dtype=torch.float32, device=states.device)
-    lo_loss = torch.zeros((), dtype=torch.float32, device=states.device)
+    terms = []  # every loss term (0-dim device tensors); summed by ONE reduction at the end instead of an add per term
+    lo_loss = torch.zeros((), dtype=torch.float32, device=states.device) if latent_overshooting else None
     lo_z = {}
     for t in range(1, Hn - 1):
         mask = masks[:, t - 1]
         expected = rew(z)
         rd_scaled = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, theta * reward_coef)[0]
-        loss = loss + rd_scaled
+        terms.append(rd_scaled)
         rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
         if truncate_bptt and t > 1:
             z = z.detach()
-        loss = loss + rec
+        terms.append(rec)
         if collect is not None:
             collect[f"Rd Loss t={t}"] = torch.mean(torch.mean((expected.detach() - rewards[:, t]) ** 2, dim=1) * mask)
             collect[f"Reconstruction t={t}"] = rec
@@ -95,7 +95,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
                 lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
     mask = masks[:, Hn - 3] if Hn > 2 else torch.ones(B, device=states.device)
     if latent_overshooting:  # main.py:232-234
-        loss = loss + theta * lo_loss
+        terms.append(theta * lo_loss)
         if collect is not None:
             collect["LO total"] = lo_loss
 
@@ -112,7 +112,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, actions[:, t])
         cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
-        loss = loss + cf
+        terms.append(cf)
         if collect is not None:
             collect["CF Disentanglement Loss"] = cf
 
@@ -123,9 +123,12 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, cf_actions[:, t])
         cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
-        loss = loss + cf
+        terms.append(cf)
         if collect is not None:
             collect["CF Control Bias Loss"] = cf
+    if not terms:  # horizon 2: no rollout step (reference main.py:162 loop is empty)
+        return torch.zeros((), dtype=torch.float32, device=states.device, requires_grad=True), z
+    loss = torch.stack(terms).sum()
     return loss, z
 
 
