@@ -60,10 +60,12 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     eye = torch.eye(A, dtype=torch.float32, device=states.device)
     it = iter(uniforms) if uniforms is not None else None
 
-    def step(z, a_idx):
+    onehots = eye[actions.t()]  # [Hn, B, A]: one gather for the whole rollout, a contiguous [B, A] slice per step
+
+    def step(z, a_onehot):
         if it is not None:
             tr._uniforms = next(it)
-        return tr(z, eye[a_idx])
+        return tr(z, a_onehot)
 
     z = enc(states[:, 0:3])
     z_orig = z.clone()
@@ -84,12 +86,12 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         if collect is not None:
             collect[f"Rd Loss t={t}"] = torch.mean(torch.mean((expected.detach() - rewards[:, t]) ** 2, dim=1) * mask)
             collect[f"Reconstruction t={t}"] = rec
-        z = step(z, actions[:, t])
+        z = step(z, onehots[t])
 
         if latent_overshooting:  # Hafner et al., reference main.py:217-230
             lo_z[t] = enc(states[:, t - 1:t + 2])
             for t_left in range(1, t):
-                lo_z[t_left] = step(lo_z[t_left], actions[:, t - 1])
+                lo_z[t_left] = step(lo_z[t_left], onehots[t - 1])
             for t_a in range(2, t - 1):
                 lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
                 lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
@@ -110,7 +112,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         # main.py:253 assigns through views: net effect z[i, idx_a] <- z[i, idx_b], in place on z_orig
         z_cf_b[ar, cf_indices[:, 0]] = z_cf_b[ar, cf_indices[:, 1]]
         for t in range(1, counterfactual_horizon):
-            z_cf_b = step(z_cf_b, actions[:, t])
+            z_cf_b = step(z_cf_b, onehots[t])
         cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
         terms.append(cf)
         if collect is not None:
@@ -119,9 +121,9 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     if enable_action_control and cf_now:  # main.py:268-283
         z_cf_a = z.clone()
         z_cf_b = z_orig
-        cf_actions = actions[cf_perm]
+        cf_onehots = onehots[:, cf_perm]  # actions of another trajectory of the batch (main.py:275)
         for t in range(1, counterfactual_horizon):
-            z_cf_b = step(z_cf_b, cf_actions[:, t])
+            z_cf_b = step(z_cf_b, cf_onehots[t])
         cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
         terms.append(cf)
         if collect is not None:
