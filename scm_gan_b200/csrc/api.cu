@@ -964,8 +964,10 @@ int scmgan_cf_loss_fwd(const float* za, const float* zb, const float* unswapped,
                        int HW, int mode, float lambda, float* rowmean, float* loss, scmgan_stream_t stream) {
     SCM_REQUIRE(za && zb && mask && rowmean && loss && B > 0 && L > 0 && L <= 64 && HW > 0, "cf_loss_fwd: bad arguments");
     SCM_REQUIRE(mode == 1 || (mode == 0 && unswapped), "cf_loss_fwd: mode 0 needs the unswapped-factor map");
-    cf_loss_fwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(za, zb, unswapped, mask, B, L, HW, mode, lambda, rowmean,
-                                                           loss);
+    cf_rowmean_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(za, zb, HW, rowmean);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    cf_loss_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rowmean, unswapped, mask, B, L, mode, lambda, loss);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
