@@ -884,10 +884,10 @@ int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmga
         SCM_REQUIRE(s.g && s.wbar && s.u && s.v && s.sigma && s.dot && s.out, "spectral_norm_bwd: bad layer %d", i);
         L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols, s.accumulate};
     }
-    sn_bwd_dot_kernel<<<dim3(32, count), 256, 0, (cudaStream_t)stream>>>(L);
+    sn_bwd_dot_kernel<<<dim3(96, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    sn_bwd_apply_kernel<<<dim3(64, count), 256, 0, (cudaStream_t)stream>>>(L);
+    sn_bwd_apply_kernel<<<dim3(256, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
