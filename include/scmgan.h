@@ -142,6 +142,8 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* desc_host, scmgan_st
  * conv epilogue.  Replaces torch.rand_like of DifferentiableBernoulliSampler, reference models.py:27-31. */
 int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream);
 
+struct scmgan_wgrad_reduce_job;
+
 /* Weight gradient: g[co*g_s_co + ci*g_s_ci + tap'*g_s_tap] += scale * sum_interior dy[p][co] * x[p+tap][ci],
  * tap' = flip ? 8-tap : tap.  g is fp32 and must be pre-initialised (atomically accumulated into).
  * Replaces cuDNN wgrad under loss.backward() (reference main.py:285). */
@@ -161,7 +163,31 @@ typedef struct {
     long long workspace_bytes;
     float* db; /* optional bias gradient: db[co] += sum over interior pixels of dy[p][co]; written for
                   co < co_valid rounded up to a multiple of 8 (the buffer must hold that many floats) */
+    /* Deferred split-K reduction (optional).  With defer_jobs != NULL the call launches only the main kernel(s) and
+     * appends the reduction(s) they need to defer_jobs[*defer_count ...] (host array of defer_cap entries); the caller
+     * runs them later - e.g. on a second stream, overlapping the next layer - with scmgan_wgrad_reduce().  Partials of
+     * different deferred launches must not share scratch: the call sub-allocates `workspace` from byte offset
+     * *workspace_cursor (in/out, host). */
+    struct scmgan_wgrad_reduce_job* defer_jobs;
+    int defer_cap;
+    int* defer_count;
+    long long* workspace_cursor;
 } scmgan_wgrad_desc;
+
+/* One split-K reduction: g[m*g_sm + n*g_sn + tap'*g_st] += scale * sum_split ws[split][tap][n][m] (m < 128), and
+ * db[m] += sum_split ws_bias[split][m] when ws_bias is set.  lanes: 8 or 32 split lanes per block. */
+typedef struct scmgan_wgrad_reduce_job {
+    const float* ws;
+    int splits, n;
+    float* g;
+    long long g_sm, g_sn, g_st;
+    int flip, m_valid, n_valid;
+    float scale;
+    const float* ws_bias;
+    float* db;
+    int lanes;
+} scmgan_wgrad_reduce_job;
+int scmgan_wgrad_reduce(int count, const scmgan_wgrad_reduce_job* jobs_host, scmgan_stream_t stream);
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* desc_host, scmgan_stream_t stream);
 long long scmgan_wgrad_workspace_bytes(void);
 

@@ -35,13 +35,22 @@ class ConvDesc(C.Structure):
                 ("bias_n", C.c_int)]
 
 
+class WgradReduceJob(C.Structure):
+    _fields_ = [("ws", C.c_void_p), ("splits", C.c_int), ("n", C.c_int), ("g", C.c_void_p),
+                ("g_sm", C.c_longlong), ("g_sn", C.c_longlong), ("g_st", C.c_longlong),
+                ("flip", C.c_int), ("m_valid", C.c_int), ("n_valid", C.c_int), ("scale", C.c_float),
+                ("ws_bias", C.c_void_p), ("db", C.c_void_p), ("lanes", C.c_int)]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [("B", C.c_int), ("H", C.c_int), ("W", C.c_int),
                 ("dy", C.c_void_p), ("dy_cs", C.c_int), ("dy_c_off", C.c_int), ("cout", C.c_int),
                 ("x", C.c_void_p), ("x_cs", C.c_int), ("x_c_off", C.c_int), ("cin", C.c_int),
                 ("g", C.c_void_p), ("g_s_co", C.c_longlong), ("g_s_ci", C.c_longlong), ("g_s_tap", C.c_longlong),
                 ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("db", C.c_void_p)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("db", C.c_void_p),
+                ("defer_jobs", C.POINTER(WgradReduceJob)), ("defer_cap", C.c_int), ("defer_count", C.POINTER(C.c_int)),
+                ("workspace_cursor", C.POINTER(C.c_longlong))]
 
 
 class SnLayer(C.Structure):
@@ -106,6 +115,7 @@ SIGNATURES = {
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_wgrad_reduce": (C.c_int, [C.c_int, C.POINTER(WgradReduceJob), C.c_void_p]),
     "scmgan_pack_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scmgan_gru_conv_sweep_fwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_gru_conv_sweep_bwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),

@@ -388,6 +388,47 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     return CK == 64 ? launch_igemm<64>(ta, tb, P, st) : launch_igemm<16>(ta, tb, P, st);
 }
 
+// ---- split-K reductions: launched right away, or recorded for the caller (scmgan_wgrad_desc::defer_jobs) ----------
+static thread_local scmgan_wgrad_reduce_job* t_defer_jobs = nullptr;
+static thread_local int t_defer_cap = 0;
+static thread_local int* t_defer_count = nullptr;
+static thread_local long long t_ws_off = 0;  // bytes; advanced only while deferring
+
+// Scratch for one launch: the whole workspace when reductions run immediately (stream order protects it), a fresh
+// slice while deferring.  nullptr = does not fit.
+static float* ws_take(float* ws, long long ws_bytes, long long need_bytes) {
+    if (!ws) return nullptr;
+    if (!t_defer_jobs) return need_bytes <= ws_bytes ? ws : nullptr;
+    if (t_ws_off + need_bytes > ws_bytes) return nullptr;
+    float* p = ws + t_ws_off / 4;
+    t_ws_off += (need_bytes + 255) & ~255LL;
+    return p;
+}
+
+static int launch_reduce(const scmgan_wgrad_reduce_job& j, cudaStream_t st) {
+    const int total = 9 * j.n * 32;
+    const int blocks = (total + 31) / 32 + (j.ws_bias && j.db ? 1 : 0);
+    if (j.lanes == 32)
+        wgrad_reduce_kernel<32><<<blocks, dim3(32, 32), 0, st>>>(j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip,
+                                                                 j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
+    else
+        wgrad_reduce_kernel<8><<<blocks, dim3(32, 8), 0, st>>>(j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip,
+                                                               j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+static int emit_reduce(const float* ws, int splits, int n, float* g, long long g_sm, long long g_sn, long long g_st,
+                       int flip, int m_valid, int n_valid, float scale, const float* ws_bias, float* db, int lanes,
+                       cudaStream_t st) {
+    scmgan_wgrad_reduce_job j{ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, ws_bias, db, lanes};
+    if (!t_defer_jobs) return launch_reduce(j, st);
+    SCM_REQUIRE(*t_defer_count < t_defer_cap, "wgrad: more than %d deferred reductions", t_defer_cap);
+    t_defer_jobs[(*t_defer_count)++] = j;
+    return SCM_OK;
+}
+
 // Second-generation wgrad (conv_wgrad_v2.cuh): P = dY (interior view, 128 channels), Q = X (padded view, n channels),
 // W % 16 == 0, workspace required.  Returns 1 when the shape does not qualify.
 static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_c_off, const void* qp, int q_cs,
@@ -417,8 +458,9 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     P.kb_per_cta = (P.num_kblocks + splits - 1) / splits;
     splits = (P.num_kblocks + P.kb_per_cta - 1) / P.kb_per_cta;
     const long long main_floats = (long long)splits * 9 * n * 128;
-    if ((main_floats + (long long)splits * 128) * 4 > ws_bytes) return 1;
     if (db && 3 * n + 16 > 512) return 1;
+    ws = ws_take(ws, ws_bytes, (main_floats + (long long)splits * 128) * 4);
+    if (!ws) return 1;
     P.n = n; P.q_aw = q_aw; P.wq = wq; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.ws = ws;
     P.ws_bias = db ? ws + main_floats : nullptr;
     {
@@ -450,16 +492,8 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     conv3x3_wgrad_v2_kernel<<<dim3(splits, 3), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    const int total = 9 * n * 32;
-    if (n <= 32)
-        wgrad_reduce_kernel<32><<<(total + 31) / 32 + (db ? 1 : 0), dim3(32, 32), 0, st>>>(
-            ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db);
-    else
-        wgrad_reduce_kernel<8><<<(total + 31) / 32 + (db ? 1 : 0), dim3(32, 8), 0, st>>>(
-            ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db);
-    SCM_CUDA(cudaGetLastError());
-    ++g_launches;
-    return SCM_OK;
+    return emit_reduce(ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db,
+                       n <= 32 ? 32 : 8, st);
 }
 
 // 16-channel-on-one-side layers (conv_wgrad_narrow.cuh): all 128-channel blocks of the wide side in one launch.
@@ -495,7 +529,8 @@ static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* 
     const long long per_block = (long long)splits * 9 * kNarrowCo * 128;
     const long long main_floats = per_block * m_blocks;
     const bool with_ones = db != nullptr && !x_is_wide;
-    if ((main_floats + (with_ones ? (long long)m_blocks * splits * 128 : 0)) * 4 > ws_bytes) return 1;
+    ws = ws_take(ws, ws_bytes, (main_floats + (with_ones ? (long long)m_blocks * splits * 128 : 0)) * 4);
+    if (!ws) return 1;
     P.x_c_off = x_is_wide ? x_c_off : dy_c_off;
     P.dy_c_off = x_is_wide ? dy_c_off : x_c_off;
     P.n_sign = x_is_wide ? -1 : +1;
@@ -537,15 +572,14 @@ static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* 
         conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tdy, tx, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    const int total = 9 * kNarrowCo * 32;
     for (int mb = 0; mb < m_blocks; ++mb) {
         const int mv = std::min(128, m_valid - mb * 128);
         if (mv <= 0) break;
-        wgrad_reduce_kernel<32><<<(total + 31) / 32 + (with_ones ? 1 : 0), dim3(32, 32), 0, st>>>(
-            ws + mb * per_block, splits, kNarrowCo, g + mb * 128 * g_sm, g_sm, g_sn, g_st, flip, mv, n_valid, scale,
-            with_ones ? P.ws_bias + (long long)mb * splits * 128 : nullptr, with_ones ? db + mb * 128 : nullptr);
-        SCM_CUDA(cudaGetLastError());
-        ++g_launches;
+        const int rc = emit_reduce(ws + mb * per_block, splits, kNarrowCo, g + mb * 128 * g_sm, g_sm, g_sn, g_st, flip,
+                                   mv, n_valid, scale,
+                                   with_ones ? P.ws_bias + (long long)mb * splits * 128 : nullptr,
+                                   with_ones ? db + mb * 128 : nullptr, 32, st);
+        if (rc) return rc;
     }
     return SCM_OK;
 }
@@ -610,7 +644,7 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
         P.debug = dbg ? (atoi(dbg) & 8) : 0;
     }
     const long long ws_need = (long long)splits * 9 * n * 128 * 4;
-    P.ws = (ws && ws_bytes >= ws_need) ? ws : nullptr;
+    P.ws = ws_take(ws, ws_bytes, ws_need);
 
     auto make_view = [&](CUtensorMap* t, const void* base, int cs, bool interior, int box_c, int swz) -> int {
         const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base);
@@ -635,13 +669,7 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    if (P.ws) {
-        const int total = 9 * n * 32;
-        wgrad_reduce_kernel<8><<<(total + 31) / 32, dim3(32, 8), 0, st>>>(P.ws, splits, n, g, g_sm, g_sn, g_st, flip,
-                                                                          m_valid, n_valid, scale, nullptr, nullptr);
-        SCM_CUDA(cudaGetLastError());
-        ++g_launches;
-    }
+    if (P.ws) return emit_reduce(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, nullptr, nullptr, 8, st);
     return SCM_OK;
 }
 
@@ -716,8 +744,35 @@ int scmgan_conv3x3_dgrad(const scmgan_conv_desc* d, scmgan_stream_t stream) {
     return conv_impl(d, (cudaStream_t)stream);
 }
 
+static int wgrad_dispatch(const scmgan_wgrad_desc* d, scmgan_stream_t stream);
+
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     SCM_REQUIRE(d != nullptr, "wgrad: null descriptor");
+    if (d->defer_jobs) {
+        SCM_REQUIRE(d->defer_count && d->workspace_cursor && d->defer_cap > 0 && d->workspace,
+                    "wgrad: deferred reduction needs defer_count, workspace_cursor and a workspace");
+        t_defer_jobs = d->defer_jobs; t_defer_cap = d->defer_cap; t_defer_count = d->defer_count;
+        t_ws_off = *d->workspace_cursor;
+    }
+    const int rc = wgrad_dispatch(d, stream);
+    if (d->defer_jobs) {
+        *d->workspace_cursor = t_ws_off;
+        t_defer_jobs = nullptr; t_defer_cap = 0; t_defer_count = nullptr; t_ws_off = 0;
+    }
+    return rc;
+}
+
+int scmgan_wgrad_reduce(int count, const scmgan_wgrad_reduce_job* jobs, scmgan_stream_t stream) {
+    SCM_REQUIRE(count >= 0 && (count == 0 || jobs), "wgrad_reduce: bad arguments");
+    for (int i = 0; i < count; ++i) {
+        SCM_REQUIRE(jobs[i].ws && jobs[i].g && jobs[i].splits > 0 && jobs[i].n > 0, "wgrad_reduce: bad job %d", i);
+        const int rc = launch_reduce(jobs[i], (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return SCM_OK;
+}
+
+static int wgrad_dispatch(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     SCM_REQUIRE(d->B > 0 && d->H > 0 && d->W > 0 && d->dy && d->x && d->g, "wgrad: bad arguments");
     SCM_REQUIRE(d->cout % 16 == 0 && d->cin % 16 == 0 && d->cout > 0 && d->cin > 0, "wgrad: channels must be x16");
     SCM_REQUIRE(d->dy_cs % 8 == 0 && d->x_cs % 8 == 0 && d->dy_c_off % 8 == 0 && d->x_c_off % 8 == 0,

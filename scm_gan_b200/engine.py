@@ -159,32 +159,34 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     # the K-concatenated input of one dgrad GEMM (see transition_forward), so the partial sums of the skip
     # connections never go through memory.
     LS = wd[1].shape[2] - HID
+    dr = K.DeferredReduces(dev)  # split-K reductions run on a side stream behind the next conv
     DB = K.new_plane(B, H, W, HID + LS, dev)
     DA = K.new_plane(B, H, W, 2 * HID, dev)
     # d pre-activation of conv6: dz * p * (1 - p)
     K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
-    K.wgrad(DB, buf6, G[5], B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L)
+    K.wgrad(DB, buf6, G[5], B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
     K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
     K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0, **dg)  # d pre5
-    K.wgrad(DA, buf5, G[4], B, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, db=db[4])
+    K.wgrad(DA, buf5, G[4], B, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, db=db[4], defer=dr)
     d4 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, **dg)              # d pre4
-    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[3])
+    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[3], defer=dr)
     K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, **dg)                            # d pre3
-    K.wgrad(DA, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
+    K.wgrad(DA, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
     K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, **dg)        # d pre2
-    K.wgrad(DB, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
+    K.wgrad(DB, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, **dg)                    # d pre1
     c1 = L + A
-    K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L)
+    K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L, defer=dr)
     K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])
     K.action_wgrad(S1, a, L, G[0])
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
     # spectral norm backward with the u, v currently held by the module (= last forward call)
+    dr.join()
     dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
     K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
                           dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(5)])
@@ -247,17 +249,19 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
     db = [db[i] if gb[i] is None else gb[i] for i in range(3)]
     if gb4 is not None and Lp == L:
         db4 = gb4
+    dr = K.DeferredReduces(dev)
     d4 = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(dz, d4, wrap=False, sig=z)
-    K.wgrad(d4, a3, G[3], B, H, W, cout=Lp, cin=HID, g_s_co=HID * 9, g_s_ci=9, co_valid=L)
+    K.wgrad(d4, a3, G[3], B, H, W, cout=Lp, cin=HID, g_s_co=HID * 9, g_s_ci=9, co_valid=L, defer=dr)
     K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
     d3, d2, d1 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
     K.conv3x3(d4, wd[2], B, H, W, cin=Lp, out=d3, gate=a3, dgrad=True)
-    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2])
+    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
     K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
-    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1])
+    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
     K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
-    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0])
+    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0], defer=dr)
+    dr.join()
     dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
     K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
                           dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(3)])
@@ -320,17 +324,19 @@ def decoder_backward(dlogits, saved, w1, w2, sink=None):
         g2 = sink[2]
     if sink[3] is not None and cop == co:
         db2 = sink[3]
+    dr = K.DeferredReduces(dev)
     d2 = K.new_plane(B, H, W, cop, dev)
     K.pack_nchw(dlogits, d2, wrap=False)
     # ConvTranspose weight layout [Cin][Cout][3][3], taps flipped relative to the equivalent correlation
-    K.wgrad(d2, hidp, g2, B, H, W, cout=cop, cin=HID, g_s_co=9, g_s_ci=co * 9, flip=True, co_valid=co, ci_valid=hid)
+    K.wgrad(d2, hidp, g2, B, H, W, cout=cop, cin=HID, g_s_co=9, g_s_ci=co * 9, flip=True, co_valid=co, ci_valid=hid, defer=dr)
     K.plane_colsum(d2, 0, cop, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=cop, out=d1, gate=hidp, dgrad=True)
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L,
-            db=db1)
+            db=db1, defer=dr)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True)
+    dr.join()
     if sink[1] is not None and db1 is not sink[1]:
         sink[1].add_(db1[:hid])
     if sink[3] is not None and db2 is not sink[3]:
@@ -395,15 +401,17 @@ def reward_backward(dr, saved, w1, w2, sink=None):
         db1 = sink[1]
     if sink[2] is not None:
         g2 = sink[2]
+    red = K.DeferredReduces(dev)
     d2 = K.new_plane(B, H, W, 16, dev)
     K.reward_head_bwd(y2, dr, R, d2)
-    K.wgrad(d2, hidp, g2, B, H, W, cout=16, cin=HID, g_s_co=RHID * 9, g_s_ci=9, co_valid=co, ci_valid=RHID)
+    K.wgrad(d2, hidp, g2, B, H, W, cout=16, cin=HID, g_s_co=RHID * 9, g_s_ci=9, co_valid=co, ci_valid=RHID, defer=red)
     K.plane_colsum(d2, 0, 16, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=16, out=d1, gate=hidp, dgrad=True)
-    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1)
+    K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1, defer=red)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True)
+    red.join()
     if sink[3] is not None:
         sink[3].add_(db2[:co])
     return (dz, g1.clone() if sink[0] is None else None, db1[:RHID].clone() if sink[1] is None else None,

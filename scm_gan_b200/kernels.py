@@ -107,8 +107,53 @@ def _wgrad_workspace(device):
     return ws
 
 
+_WGRAD_RING = {}
+_SIDE_STREAM = {}
+_RING_BYTES = 320 << 20
+
+
+class DeferredReduces:
+    """The split-K reductions of the weight-gradient launches of ONE module backward, taken off the critical path:
+    `wgrad(..., defer=self)` launches only the tensor-core kernel and records the reduction, `kick()` (called by wgrad)
+    runs it on a side stream behind an event, and `join()` makes the compute stream wait for all of them.  The
+    reduction blocks are small (256 threads, 4-16 KB of shared memory) and co-reside with the next conv kernel's CTAs,
+    so the ~9 us per layer they cost disappear behind it.  Every deferred launch gets its own slice of a 320 MB
+    scratch ring (partials of different layers are alive at the same time).  Works eagerly and under CUDA-graph
+    capture (the fork/join becomes graph edges).  Disabled with SCMGAN_NO_DEFER=1."""
+    CAP = 32
+
+    def __init__(self, device):
+        import os
+        self.enabled = os.environ.get("SCMGAN_NO_DEFER", "0") != "1"
+        key = (device.type, device.index)
+        if key not in _WGRAD_RING:
+            _WGRAD_RING[key] = torch.empty(_RING_BYTES // 4, dtype=torch.float32, device=device)
+            _SIDE_STREAM[key] = torch.cuda.Stream(device=device)
+        self.ring, self.side = _WGRAD_RING[key], _SIDE_STREAM[key]
+        self.jobs = (L.WgradReduceJob * self.CAP)()
+        self.count = C.c_int(0)
+        self.cursor = C.c_longlong(0)
+        self.launched = 0
+
+    def kick(self):
+        n_new = self.count.value - self.launched
+        if n_new <= 0:
+            return
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        first = C.cast(C.byref(self.jobs, self.launched * C.sizeof(L.WgradReduceJob)), C.POINTER(L.WgradReduceJob))
+        L.check(L.lib().scmgan_wgrad_reduce(n_new, first, self.side.cuda_stream), "scmgan_wgrad_reduce")
+        self.launched = self.count.value
+
+    def join(self):
+        if self.launched:
+            torch.cuda.current_stream().wait_stream(self.side)
+
+
 def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
-          co_valid=None, ci_valid=None, scale=1.0, db=None):
+          co_valid=None, ci_valid=None, scale=1.0, db=None, defer=None):
     d = L.WgradDesc()
     d.B, d.H, d.W = B, H, W
     d.dy, d.dy_cs, d.dy_c_off, d.cout = dy_plane.data_ptr(), dy_plane.shape[3], dy_c_off, cout
@@ -118,9 +163,16 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
     d.co_valid = cout if co_valid is None else co_valid
     d.ci_valid = cin if ci_valid is None else ci_valid
     d.scale = scale
+    d.db = L.ptr(db)  # bias gradient accumulated alongside (zero-initialised by the caller)
+    if defer is not None and defer.enabled:
+        d.workspace, d.workspace_bytes = defer.ring.data_ptr(), defer.ring.numel() * 4
+        d.defer_jobs, d.defer_cap = defer.jobs, defer.CAP
+        d.defer_count, d.workspace_cursor = C.pointer(defer.count), C.pointer(defer.cursor)
+        L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
+        defer.kick()
+        return
     ws = _wgrad_workspace(g.device)
     d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
-    d.db = L.ptr(db)  # bias gradient accumulated alongside (zero-initialised by the caller)
     L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
 
 
