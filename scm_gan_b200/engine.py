@@ -166,7 +166,8 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
     K.wgrad(DB, buf6, G[5], B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
-    K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
+    with dr.side_section():
+        K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
     K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0, **dg)  # d pre5
     K.wgrad(DA, buf5, G[4], B, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, db=db[4], defer=dr)
@@ -181,8 +182,9 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, **dg)                    # d pre1
     c1 = L + A
     K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L, defer=dr)
-    K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])
-    K.action_wgrad(S1, a, L, G[0])
+    with dr.side_section():
+        K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])
+        K.action_wgrad(S1, a, L, G[0])
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
     # spectral norm backward with the u, v currently held by the module (= last forward call)
@@ -253,7 +255,8 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
     d4 = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(dz, d4, wrap=False, sig=z)
     K.wgrad(d4, a3, G[3], B, H, W, cout=Lp, cin=HID, g_s_co=HID * 9, g_s_ci=9, co_valid=L, defer=dr)
-    K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
+    with dr.side_section():
+        K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
     d3, d2, d1 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
     K.conv3x3(d4, wd[2], B, H, W, cin=Lp, out=d3, gate=a3, dgrad=True)
     K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
@@ -329,7 +332,8 @@ def decoder_backward(dlogits, saved, w1, w2, sink=None):
     K.pack_nchw(dlogits, d2, wrap=False)
     # ConvTranspose weight layout [Cin][Cout][3][3], taps flipped relative to the equivalent correlation
     K.wgrad(d2, hidp, g2, B, H, W, cout=cop, cin=HID, g_s_co=9, g_s_ci=co * 9, flip=True, co_valid=co, ci_valid=hid, defer=dr)
-    K.plane_colsum(d2, 0, cop, B, H, W, db=db2)
+    with dr.side_section():
+        K.plane_colsum(d2, 0, cop, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=cop, out=d1, gate=hidp, dgrad=True)
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L,
@@ -405,7 +409,8 @@ def reward_backward(dr, saved, w1, w2, sink=None):
     d2 = K.new_plane(B, H, W, 16, dev)
     K.reward_head_bwd(y2, dr, R, d2)
     K.wgrad(d2, hidp, g2, B, H, W, cout=16, cin=HID, g_s_co=RHID * 9, g_s_ci=9, co_valid=co, ci_valid=RHID, defer=red)
-    K.plane_colsum(d2, 0, 16, B, H, W, db=db2)
+    with red.side_section():
+        K.plane_colsum(d2, 0, 16, B, H, W, db=db2)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(d2, wd2, B, H, W, cin=16, out=d1, gate=hidp, dgrad=True)
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1, defer=red)

@@ -147,8 +147,22 @@ class DeferredReduces:
         L.check(L.lib().scmgan_wgrad_reduce(n_new, first, self.side.cuda_stream), "scmgan_wgrad_reduce")
         self.launched = self.count.value
 
+    def side_section(self):
+        """Context manager: kernels launched inside run on the side stream, after everything enqueued so far on the
+        compute stream (small reductions nothing on the critical path waits for: bias column sums, the folded action
+        weight gradient).  Their inputs must stay alive until join()."""
+        import contextlib
+        if not self.enabled:
+            return contextlib.nullcontext()
+        main = torch.cuda.current_stream()
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self.side.wait_event(ev)
+        self.forked = True
+        return torch.cuda.stream(self.side)
+
     def join(self):
-        if self.launched:
+        if self.launched or getattr(self, "forked", False):
             torch.cuda.current_stream().wait_stream(self.side)
 
 
