@@ -1,6 +1,6 @@
 // 3x3 implicit-GEMM convolution, second generation: weight-stationary persistent CTAs.
 //
-// Measured on B200 (profiles/r01_microbench_v1.txt): the first kernel re-streams weights and one activation tile
+// Measured on B200 (profiles/r01_notes.md): the first kernel re-streams weights and one activation tile
 // per filter tap through the L2->SM fabric (576 KB per 128-row tile, ~40 B/cycle/SM - the fabric limit) and spends
 // as long again in an epilogue of half-sector stores.  This version removes both:
 //   * the packed weights of the CTA's N slice stay RESIDENT in shared memory for the whole (persistent) kernel:
@@ -8,9 +8,10 @@
 //     fits (9 * Cin * n_cta * 2 bytes <= ~147 KB);
 //   * one activation "super tile" per K chunk serves SEVERAL filter taps: in the flattened plane the tap (ky,kx)
 //     operand is the same rows shifted by ky*(W+2)+kx, i.e. the same shared-memory tile at a row offset.  UMMA
-//     descriptors address it directly (start address + 128 B per row; the swizzle phase travels in the
-//     descriptor's base-offset field), so A traffic drops 3x (kx reuse) or ~4.5x (ky+kx reuse);
-//   * eight epilogue warps write their rows with 256-bit stores (igemm_epilogue.cuh); bias lives in shared memory.
+//     descriptors address it directly (start address + 128 B per row with base_offset = 0: the tensor core applies
+//     the swizzle to the absolute shared-memory address), so A traffic drops 3x (kx reuse) or ~4.5x (ky+kx reuse);
+//   * eight epilogue warps (sixteen in the narrow-K instantiation) write their rows with 256-bit stores
+//     (igemm_epilogue.cuh); bias lives in shared memory.
 // Warp roles and the double-buffered TMEM accumulator are as in conv_igemm.cuh.
 #pragma once
 #include "conv_igemm.cuh"
