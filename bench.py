@@ -251,7 +251,7 @@ def main():
         ge.build()
     if world > 1:
         dist.barrier()
-    from oracle import restated as R  # synthetic batch generator only (inputs, not compute)
+    from scm_gan_b200 import synthetic as R  # synthetic batch generator
     from scm_gan_b200 import kernels as K
     from scm_gan_b200.train_step import Trainer, build_nets
 

@@ -4,7 +4,7 @@ import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from torch.profiler import ProfilerActivity, profile
-from oracle import restated as R  # synthetic batch generator only
+from scm_gan_b200 import synthetic as R  # synthetic batch generator
 from scm_gan_b200.train_step import Trainer, build_nets
 
 cf = "--cf" in sys.argv

@@ -8,6 +8,7 @@ models): a few "agent" pixels move by the chosen action, "food" pixels are stati
 agent lands on them, a "ghost" drifts and costs -1 on contact.
 """
 import numpy as np
+import torch
 
 MOVES = [(0, 0), (-1, 0), (1, 0), (0, -1), (0, 1), (1, 1), (-1, -1)]  # action -> (dy, dx); extra actions reuse entries
 
@@ -105,3 +106,16 @@ class MovingDotsEnv:
         self.t += 1
         done = self.t >= self.episode_length or not self.food.any()
         return self._frame(), float(sum(info.values())), done, info
+
+
+def synthetic_batch(batch, horizon, channels, height, width, num_actions, num_rewards, seed=1234, p_done=0.0):
+    """i.i.d. benchmark trajectories of SURVEY.md section 8d (sparse binary frames, 5 % non-zero rewards): the shapes
+    and dtypes of `get_trajectories`, no dynamics - what bench.py feeds the step.  Returns CPU tensors
+    (states f32, rewards f32, dones f32) and a numpy int64 action array."""
+    g = torch.Generator().manual_seed(seed)
+    states = (torch.rand(batch, horizon, channels, height, width, generator=g) < 0.15).float()
+    r = torch.rand(batch, horizon, num_rewards, generator=g)
+    rewards = torch.where(r < 0.025, -1.0, torch.where(r > 0.975, 1.0, 0.0))
+    dones = (torch.rand(batch, horizon, generator=g) < p_done).float()
+    actions = torch.randint(num_actions, (batch, horizon), generator=g)
+    return states, rewards, dones, actions.numpy()
