@@ -65,3 +65,19 @@ def test_struct_layouts_match_header_sizes(lib):
     assert C.sizeof(lib.SnLayer) == 56
     assert C.sizeof(lib.SnBwdLayer) == 72
     assert C.sizeof(lib.AdamChunk) == 48
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/scmgan.h is the drop-in boundary: it must compile as C99 (and C++) with no torch / CUDA headers."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = tmp_path / "t.c"
+    src.write_text('#include "scmgan.h"\n'
+                   "int main(void) { scmgan_conv_desc c; scmgan_wgrad_desc d; scmgan_wgrad_reduce_job j;\n"
+                   "  (void)c; (void)d; (void)j; return scmgan_version() > 0 ? 0 : 1; }\n")
+    for cc, std, lang in (("gcc", "-std=c99", "c"), ("g++", "-std=c++17", "c++")):
+        if shutil.which(cc) is None:
+            pytest.skip(f"{cc} not available")
+        subprocess.run([cc, std, "-Wall", "-Werror", "-I", os.path.join(root, "include"), "-fsyntax-only", "-x", lang,
+                        str(src)], check=True)
