@@ -170,3 +170,23 @@ def test_synthetic_env_contract():
     assert steps <= env.episode_length
     net_frame, rgb = src.convert_frame(f)
     assert net_frame.shape == (3, 15, 19) and rgb.shape == (15, 19, 3) and rgb.dtype == np.uint8
+
+
+def test_planner_beam_table_matches_reference_enumeration():
+    """planner.beam_actions builds the plan table of reference main.py:463-473 (every action pair + no-op tail)."""
+    import numpy as np
+    import torch
+    from scm_gan_b200 import planner
+    A, depth = 4, 12
+    got = planner.beam_actions(A, lookahead=2, rollout_depth=depth, rollout_policy="noop")
+    ref = []
+    for i in range(A):
+        for j in range(A):
+            ref.append([i, j] + [0] * (depth - 2))
+    assert got.dtype == torch.int64 and got.shape == (A * A, depth)
+    assert np.array_equal(got.numpy(), np.asarray(ref))
+    rnd = planner.beam_actions(A, rollout_depth=depth, rollout_policy="random", rng=np.random.RandomState(0))
+    assert rnd.shape == (A * A, depth) and int(rnd.max()) < A and np.array_equal(rnd[:, :2].numpy(), np.asarray(ref)[:, :2])
+    oh = planner.onehot(torch.tensor([0, 3]), A, "cpu")
+    assert oh.shape == (2, A) and oh[1, 3] == 1 and oh.sum() == 2
+    assert planner.onehot(2, A, "cpu").shape == (1, A)
