@@ -165,9 +165,10 @@ def time_dominant_kernel(B, H, W, iters=30):
     dev = "cuda"
     plane_bytes = B * (H + 2) * (W + 2) * 128 * 2
     nbuf = max(2, int(300e6 // (2 * plane_bytes)) + 1)
-    xs = [torch.randn(B, H + 2, W + 2, 128, device=dev).to(torch.bfloat16) for _ in range(nbuf)]
-    ys = [K.new_plane(B, H, W, 128, dev) for _ in range(nbuf)]
-    w = (torch.randn(9, 128, 128, device=dev) * 0.03).to(torch.bfloat16)
+    # operands in the step's own storage format (kernels.FWD_DTYPE: fp16 activations and weights)
+    xs = [torch.randn(B, H + 2, W + 2, 128, device=dev).to(K.FWD_DTYPE) for _ in range(nbuf)]
+    ys = [K.fwd_plane(B, H, W, 128, dev) for _ in range(nbuf)]
+    w = (torch.randn(9, 128, 128, device=dev) * 0.03).to(K.FWD_DTYPE)
     bias = torch.zeros(128, device=dev)
     for i in range(3):
         K.conv3x3(xs[i % nbuf], w, B, H, W, cin=128, bias=bias, act=K.ACT_LRELU, out=ys[i % nbuf], wrap=True)
@@ -199,7 +200,9 @@ def main():
     ap.add_argument("--workload", default="pong64", choices=sorted(WORKLOADS))
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch (reference default, main.py:31)")
     ap.add_argument("--horizon", type=int, default=10, help="prediction horizon Hn (T = Hn - 2 rollout steps)")
-    ap.add_argument("--cpu-sample-batch", type=int, default=8)
+    ap.add_argument("--cpu-sample-batch", type=int, default=0,
+                    help="batch of the CPU arm's bounded sample (0: --impl reference runs min(batch, 32), i.e. the whole "
+                         "default workload; the cpu_baseline leg of the default run uses 8)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--cf-phase", type=int, default=0,
@@ -221,9 +224,13 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sb = args.cpu_sample_batch
+        sb = args.cpu_sample_batch or min(B, 32)
         fps, ms, cores = cpu_reference_run(args.workload, Hn, sb, max(args.steps, 1), args.warmup)
-        sample = f"oracle port of the reference step on host CPU, batch {sb} of the same {C}x{H}x{W} horizon-{Hn} workload"
+        sample = (f"oracle port of the reference step on host CPU (fp32 torch, all host threads), "
+                  + (f"the full per-GPU batch of {B}" if sb == B else f"batch {sb} of {B} (per-frame rate)")
+                  + f" of the same {C}x{H}x{W} horizon-{Hn} workload")
+        if sb != B:
+            config["cpu_sample_batch"] = sb
         print(json.dumps({
             "impl": "reference", "metric": "training rollout-frames/s", "value": fps, "unit": "frames/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
@@ -239,11 +246,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line: NCCL prints its version banner to stdout at any NCCL_DEBUG level
-        if "SCMGAN_NCCL_DEBUG" in os.environ:
-            os.environ["NCCL_DEBUG"] = os.environ["SCMGAN_NCCL_DEBUG"]
-        else:
-            os.environ.pop("NCCL_DEBUG", None)
+        # NCCL_DEBUG is left as the caller set it (the driver reads the communicator lines); its output goes to
+        # stderr so that stdout stays the one JSON line
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     import __graft_entry__ as ge
@@ -365,7 +369,9 @@ def main():
         out = {
             "metric": "training rollout-frames/s", "value": value, "unit": "frames/s", "n_gpus": world,
             "steps": args.steps, "warmup": warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config,
+            "scaling": "weak", "vs_baseline": None,
+            "dtype": ("fp16" if K.FWD_DTYPE == torch.float16 else "bf16") + " forward operands, bf16 gradient planes, f32 accumulate",
+            "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
@@ -381,7 +387,7 @@ def main():
             "use_cuda_graph": use_graph,
         }
         if not args.no_cpu_baseline and world == 1:
-            sb = args.cpu_sample_batch
+            sb = args.cpu_sample_batch or 8
             n_it = 8
             fps, ms, cores = cpu_reference_run(args.workload, Hn, sb, n_it, 1)
             out["cpu_baseline"] = {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port",

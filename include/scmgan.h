@@ -33,6 +33,12 @@ extern "C" {
 #define SCMGAN_ACT_LRELU 1
 #define SCMGAN_ACT_SIGMOID 2
 
+/* 16-bit storage formats of planes and packed weights.  Forward activations and weights are fp16 by default (11-bit
+ * significand: parameter gradients then stay within 1e-2 of the fp32 reference, profiles/r02_grad_precision_*.json),
+ * gradient planes are bf16 (fp32 exponent range).  tcgen05.mma kind::f16 takes either format per operand. */
+#define SCMGAN_FMT_BF16 0
+#define SCMGAN_FMT_F16 1
+
 typedef void* scmgan_stream_t; /* cudaStream_t */
 
 int scmgan_version(void);
@@ -47,12 +53,12 @@ long long scmgan_launch_count(void);
  * (reference models.py:103,154) fused into the packing of the incoming gradient.
  * Replaces x.view / torch.cat / F.pad(mode='circular') copies: reference models.py:69-73, 143, 76-103. */
 int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
-                     int c_off, int c_pad, int wrap, const float* sig, scmgan_stream_t stream);
+                     int c_off, int c_pad, int wrap, const float* sig, int fmt, scmgan_stream_t stream);
 
 /* CoordConv coordinate channels (reference coordconv.py:10-14; interface-only layer): plane channel c_off of interior
  * pixel (h, w) <- -1 + 2w/W and channel c_off+1 <- -1 + 2h/H, for every sample.  Run after scmgan_pack_nchw has
  * filled (zeroed) the channel window; replaces the arange/repeat/cat of the reference. */
-int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, scmgan_stream_t stream);
+int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, int fmt, scmgan_stream_t stream);
 
 /* Weight packing fp32 parameter -> bf16 [9][n_pad][k_pad] GEMM operand, optionally divided by *sigma
  * (the `w / sigma` of reference spectral_normalization.py:35).
@@ -69,6 +75,7 @@ typedef struct {
     int k_src_off;
     int flip;
     int out_ld;
+    int fmt; /* SCMGAN_FMT_* of `out` */
 } scmgan_pack_job;
 int scmgan_pack_weights(int count, const scmgan_pack_job* jobs_host, scmgan_stream_t stream);
 
@@ -104,6 +111,7 @@ typedef struct {
                                       in-kernel Philox4x32-10 stream and the offset is advanced; NULL => threshold 0.5 */
     int bias_n; /* number of valid entries of `bias` (channels beyond it get 0); 0 = n.  Lets a layer with 3 or 12
                    real output channels pass its own bias vector although n is padded to 16. */
+    int x_fmt, w_fmt, out_fmt; /* SCMGAN_FMT_* of the input plane, the packed weights and the output plane */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
@@ -172,6 +180,7 @@ typedef struct {
     int defer_cap;
     int* defer_count;
     long long* workspace_cursor;
+    int dy_fmt, x_fmt; /* SCMGAN_FMT_* of the gradient plane and of the input plane */
 } scmgan_wgrad_desc;
 
 /* One split-K reduction: g[m*g_sm + n*g_sn + tap'*g_st] += scale * sum_split ws[split][tap][n][m] (m < 128), and
@@ -232,13 +241,16 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
                         scmgan_stream_t stream);
 
 /* Reward regression term of the rollout loss (reference main.py:182-186):
- *   loss[0] = scale * mean_b( mask[b] * mean_r (pred[b][r] - target[b][r])^2 ),  dpred = d loss / d pred.
+ *   loss[0] = scale * (*scale_dev) * mean_b( mask[b] * mean_r (pred[b][r] - target[b][r])^2 ),  dpred = d loss / d pred.
+ * scale_dev (device scalar or NULL = 1) carries theta = train_iter / train_iters (main.py:143,185) so that a captured
+ * CUDA graph does not bake the training progress in; loss_raw (or NULL) receives the unscaled masked mean the
+ * reference logs as "Rd Loss" (main.py:184).
  * target rows are target_bstride elements apart (a time slice of the [B][Hn][R] reward tensor), mask elements
  * mask_stride apart (a time slice of the [B][Hn-1] active mask).  One launch instead of six elementwise / reduction
  * kernels forward and as many backward. */
 int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
-                      long long mask_stride, int B, int R, float scale, float* loss, float* dpred,
-                      scmgan_stream_t stream);
+                      long long mask_stride, int B, int R, float scale, const float* scale_dev, float* loss,
+                      float* loss_raw, float* dpred, scmgan_stream_t stream);
 
 /* loss[0] += mean_b( mask[b] * mean_chw BCE(sigmoid(x), y) ); dx (optional) = d loss / d x.
  * Fuses torch.sigmoid + F.binary_cross_entropy + means (reference main.py:188-197, 310-312). */

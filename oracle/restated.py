@@ -56,12 +56,33 @@ def spectral_norm_weight(sd, prefix):
 # differences of fp32 gradients (sign flips of near-zero pre-activations), see DESIGN.md "Parity".
 # --------------------------------------------------------------------------------------------------------------
 OPERAND_DTYPE = None
+# Finer control for the precision study (profiles/grad_precision.py): rounding of the forward activations, of the
+# (normalised) weights and of the gradients entering each conv's backward can be chosen separately; each defaults to
+# OPERAND_DTYPE.  Values: None (fp32), a torch dtype, or "tf32" (10-bit mantissa, fp32 range, round-to-nearest-even
+# emulated on the fp32 bit pattern).
+ROUND = {"act": "inherit", "w": "inherit", "grad": "inherit"}
+# When a list, every LeakyReLU appends the sign pattern (pre-activation > 0) of its input: lets a study count how many
+# kinks two evaluations of the same network put on different sides.
+RECORD_SIGNS = None
+
+
+def _dtype_of(kind):
+    d = ROUND[kind]
+    return OPERAND_DTYPE if d == "inherit" else d
+
+
+def _round_to(x, dtype):
+    if dtype == "tf32":
+        i = x.contiguous().view(torch.int32)
+        i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF  # round to nearest even at 13 dropped mantissa bits
+        return i.view(torch.float32).view_as(x)
+    return x.to(dtype).to(x.dtype)
 
 
 class _RoundSTE(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, dtype):
-        return x.to(dtype).to(x.dtype)
+        return _round_to(x, dtype)
 
     @staticmethod
     def backward(ctx, g):
@@ -76,17 +97,36 @@ class _RoundGrad(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g.to(ctx.dtype).to(g.dtype), None
+        return _round_to(g, ctx.dtype), None
 
 
 def _q(x):
-    """operand rounding (forward), straight-through gradient"""
-    return x if OPERAND_DTYPE is None else _RoundSTE.apply(x, OPERAND_DTYPE)
+    """activation-operand rounding (forward), straight-through gradient"""
+    d = _dtype_of("act")
+    return x if d is None else _RoundSTE.apply(x, d)
+
+
+def _qw(w):
+    """weight-operand rounding (forward), straight-through gradient"""
+    d = _dtype_of("w")
+    return w if d is None else _RoundSTE.apply(w, d)
 
 
 def _qg(x):
     """identity forward; the gradient flowing back through this point is rounded (gradient planes are bf16)"""
-    return x if OPERAND_DTYPE is None else _RoundGrad.apply(x, OPERAND_DTYPE)
+    d = _dtype_of("grad")
+    return x if d is None else _RoundGrad.apply(x, d)
+
+
+def _lrelu(x, tag=""):
+    """F.leaky_relu with the default slope 0.01 (reference models.py:77-99, 145-151, 239, 276)"""
+    if RECORD_SIGNS is not None:
+        RECORD_SIGNS.append((tag, x.detach() > 0))
+    return F.leaky_relu(x)
+
+
+def _rounding_on():
+    return any(_dtype_of(k) is not None for k in ("act", "w", "grad"))
 
 
 def _sn_conv(sd, name, x, circular, exact_tail=0):
@@ -96,12 +136,12 @@ def _sn_conv(sd, name, x, circular, exact_tail=0):
     action channels of Transition.conv1, which the product folds into an fp32 per-sample bias)."""
     w = spectral_norm_weight(sd, name + ".module.")
     b = sd[name + ".module.bias"]
-    if OPERAND_DTYPE is not None and exact_tail:
+    if _rounding_on() and exact_tail:
         n = x.shape[1] - exact_tail
         xq = torch.cat([_q(x[:, :n]), x[:, n:]], dim=1)
-        wq = torch.cat([_q(w[:, :n]), w[:, n:]], dim=1)
+        wq = torch.cat([_qw(w[:, :n]), w[:, n:]], dim=1)
     else:
-        xq, wq = _q(x), _q(w)
+        xq, wq = _q(x), _qw(w)
     if circular:
         return _qg(F.conv2d(F.pad(xq, (1, 1, 1, 1), mode="circular"), wq, b))
     return _qg(F.conv2d(xq, wq, b, padding=1))
@@ -115,10 +155,10 @@ def encoder_forward(sd, x):
     (models.py:130) but never applied."""
     b, frames, ch, h, w = x.shape
     x = x.reshape(b, frames * ch, h, w)
-    x = F.leaky_relu(_sn_conv(sd, "conv1", x, False))
-    x = F.leaky_relu(_sn_conv(sd, "conv2", x, False))
-    x = F.leaky_relu(_sn_conv(sd, "conv3", x, False))
-    x = _qg(F.conv2d(_q(x), _q(sd["conv4.weight"]), sd["conv4.bias"], padding=1))
+    x = _lrelu(_sn_conv(sd, "conv1", x, False), "enc.conv1")
+    x = _lrelu(_sn_conv(sd, "conv2", x, False), "enc.conv2")
+    x = _lrelu(_sn_conv(sd, "conv3", x, False), "enc.conv3")
+    x = _qg(F.conv2d(_q(x), _qw(sd["conv4.weight"]), sd["conv4.bias"], padding=1))
     return torch.sigmoid(x)
 
 
@@ -140,19 +180,19 @@ def transition_forward(sd, z, a, training=True, uniforms=None, return_all=False,
     assert a.shape[0] == b  # models.py:66
     actions = a.unsqueeze(-1).unsqueeze(-1).repeat(1, 1, h, w)
     x = torch.cat([z, actions], dim=1)
-    x = F.leaky_relu(_sn_conv(sd, "conv1", x, True, exact_tail=a.shape[1]))
+    x = _lrelu(_sn_conv(sd, "conv1", x, True, exact_tail=a.shape[1]), "tr.conv1")
     skip1 = x
-    x = F.leaky_relu(_sn_conv(sd, "conv2", x, True))
+    x = _lrelu(_sn_conv(sd, "conv2", x, True), "tr.conv2")
     skip2 = x
-    x = F.leaky_relu(_sn_conv(sd, "conv3", x, True))
+    x = _lrelu(_sn_conv(sd, "conv3", x, True), "tr.conv3")
     out3 = x
-    x = F.leaky_relu(_sn_conv(sd, "conv4", x, True))
+    x = _lrelu(_sn_conv(sd, "conv4", x, True), "tr.conv4")
     out4 = x
     x = torch.cat([x, skip2], dim=1)
-    x = F.leaky_relu(_sn_conv(sd, "conv5", x, True))
+    x = _lrelu(_sn_conv(sd, "conv5", x, True), "tr.conv5")
     out5 = x
     x = torch.cat([x, skip1], dim=1)
-    x = _qg(F.conv2d(F.pad(_q(x), (1, 1, 1, 1), mode="circular"), _q(sd["conv6.weight"]), sd["conv6.bias"]))
+    x = _qg(F.conv2d(F.pad(_q(x), (1, 1, 1, 1), mode="circular"), _qw(sd["conv6.weight"]), sd["conv6.bias"]))
     p = torch.sigmoid(x)
     if training:
         if callable(uniforms):  # hook(p) -> uniforms, lets a test keep its draws away from p (margin-safe sampling)
@@ -172,16 +212,16 @@ def transition_forward(sd, z, a, training=True, uniforms=None, return_all=False,
 def decoder_forward(sd, z, visualize=False):
     """reference models.py:270-291.  Returns logits [B, C, H, W] (caller applies sigmoid, main.py:189)."""
     b, latent, h, w = z.shape
-    x = _qg(F.conv_transpose2d(_q(z), _q(sd["conv1.weight"]), sd["conv1.bias"], stride=1, padding=1))
-    x = F.leaky_relu(x)
+    x = _qg(F.conv_transpose2d(_q(z), _qw(sd["conv1.weight"]), sd["conv1.bias"], stride=1, padding=1))
+    x = _lrelu(x, "dec.conv1")
     w2, b2 = sd["conv2.weight"], sd["conv2.bias"]
     color = w2.shape[1] // latent
-    if OPERAND_DTYPE is not None and not visualize:
+    if _rounding_on() and not visualize:
         # the product sums the latent groups of the (linear) last layer in fp32 *before* rounding the weights
         w2f = w2.view(w2.shape[0], latent, color, 3, 3).sum(1)
         b2f = b2.view(latent, color).sum(0)
-        return _qg(F.conv_transpose2d(_q(x), _q(w2f), b2f, stride=1, padding=1))
-    x = _qg(F.conv_transpose2d(_q(x), _q(w2), b2, stride=1, padding=1))
+        return _qg(F.conv_transpose2d(_q(x), _qw(w2f), b2f, stride=1, padding=1))
+    x = _qg(F.conv_transpose2d(_q(x), _qw(w2), b2, stride=1, padding=1))
     x = x.view(b, latent, color, h, w)
     vis = x[0]
     x = torch.sum(x, dim=1)
@@ -192,8 +232,8 @@ def decoder_forward(sd, z, visualize=False):
 
 def reward_forward(sd, z, visualize=False):
     """reference models.py:235-250.  [B, L, H, W] -> [B, R]"""
-    x = F.leaky_relu(_qg(F.conv2d(_q(z), _q(sd["conv1.weight"]), sd["conv1.bias"])))
-    x = _qg(F.conv2d(_q(x), _q(sd["conv2.weight"]), sd["conv2.bias"], stride=2))
+    x = _lrelu(_qg(F.conv2d(_q(z), _qw(sd["conv1.weight"]), sd["conv1.bias"])), "rew.conv1")
+    x = _qg(F.conv2d(_q(x), _qw(sd["conv2.weight"]), sd["conv2.bias"], stride=2))
     b, ch, h, w = x.shape
     x = torch.softmax(x.view(b, 3, ch // 3, h, w), dim=1)
     x = x[:, 0] - x[:, 2]

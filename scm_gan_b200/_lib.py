@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libscmgan.so")
 
 ACT_NONE, ACT_LRELU, ACT_SIGMOID = 0, 1, 2
+FMT_BF16, FMT_F16 = 0, 1
 
 c_f32p = C.c_void_p  # device pointers travel as integers
 
@@ -18,7 +19,7 @@ class PackJob(C.Structure):
     _fields_ = [("w", C.c_void_p), ("out", C.c_void_p), ("sigma", C.c_void_p),
                 ("n_pad", C.c_int), ("k_pad", C.c_int), ("n_valid", C.c_int), ("k_valid", C.c_int),
                 ("s_n", C.c_longlong), ("s_k", C.c_longlong), ("k_src_off", C.c_int), ("flip", C.c_int),
-                ("out_ld", C.c_int)]
+                ("out_ld", C.c_int), ("fmt", C.c_int)]
 
 
 class ConvDesc(C.Structure):
@@ -32,7 +33,7 @@ class ConvDesc(C.Structure):
                 ("gate", C.c_void_p), ("gate_cs", C.c_int), ("gate_c_off", C.c_int),
                 ("out_f32", C.c_void_p), ("n_valid", C.c_int),
                 ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p),
-                ("bias_n", C.c_int)]
+                ("bias_n", C.c_int), ("x_fmt", C.c_int), ("w_fmt", C.c_int), ("out_fmt", C.c_int)]
 
 
 class WgradReduceJob(C.Structure):
@@ -50,7 +51,7 @@ class WgradDesc(C.Structure):
                 ("flip", C.c_int), ("co_valid", C.c_int), ("ci_valid", C.c_int), ("scale", C.c_float),
                 ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong), ("db", C.c_void_p),
                 ("defer_jobs", C.POINTER(WgradReduceJob)), ("defer_cap", C.c_int), ("defer_count", C.POINTER(C.c_int)),
-                ("workspace_cursor", C.POINTER(C.c_longlong))]
+                ("workspace_cursor", C.POINTER(C.c_longlong)), ("dy_fmt", C.c_int), ("x_fmt", C.c_int)]
 
 
 class SnLayer(C.Structure):
@@ -84,7 +85,7 @@ SIGNATURES = {
     "scmgan_num_sms": (C.c_int, []),
     "scmgan_launch_count": (C.c_longlong, []),
     "scmgan_pack_nchw": (C.c_int, [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
-                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     "scmgan_pack_weights": (C.c_int, [C.c_int, C.POINTER(PackJob), C.c_void_p]),
     "scmgan_conv3x3_fwd": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
     "scmgan_conv3x3_dgrad": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
@@ -114,9 +115,9 @@ SIGNATURES = {
                                      C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
-                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                    C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_wgrad_reduce": (C.c_int, [C.c_int, C.POINTER(WgradReduceJob), C.c_void_p]),
-    "scmgan_pack_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "scmgan_pack_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scmgan_gru_conv_sweep_fwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_gru_conv_sweep_bwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),
     "scmgan_philox_uniform": (C.c_int, [C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),

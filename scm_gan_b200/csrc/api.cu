@@ -91,6 +91,25 @@ int num_sms() {
     return sms;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt every kernel in once per device ordinal
+// (a process that drives several GPUs through this C ABI launches on each of them).
+template <class Kernel>
+static cudaError_t opt_in_smem(Kernel kernel, std::atomic<unsigned long long>& done, int bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (done.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e == cudaSuccess) done.fetch_or(bit, std::memory_order_release);
+    return e;
+}
+#define SCM_OPT_IN_SMEM(kernel, bytes)                                   \
+    do {                                                                 \
+        static std::atomic<unsigned long long> _done{0};                 \
+        SCM_CUDA(opt_in_smem(kernel, _done, bytes));                     \
+    } while (0)
+
 constexpr int kSmemBudget = 200 * 1024;  // tiles; barriers/alignment slack on top (<= 227 KB per CTA)
 
 template <int CK>
@@ -102,12 +121,7 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Igem
         return SCM_EUNSUPPORTED;
     }
     const int smem = stages * stage_bytes + 1024 + 256;
-    static bool attr_set = false;  // per template instantiation
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_kernel<CK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      227 * 1024));
-        attr_set = true;
-    }
+    SCM_OPT_IN_SMEM(conv3x3_igemm_kernel<CK>, 227 * 1024);
     const int grid = std::min(P.num_tiles, num_sms());
     conv3x3_igemm_kernel<CK><<<grid, kIgemmThreads, smem, st>>>(ta, tb, P, stages);
     SCM_CUDA(cudaGetLastError());
@@ -121,12 +135,7 @@ constexpr int kSmemMax = 227 * 1024;
 template <int CK, int TPG>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& P, const IgemmV2Geom& G,
                           int gx, int nsplit, int smem, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v2_kernel<CK, TPG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSmemMax));
-        attr_set = true;
-    }
+    SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG>), kSmemMax);
     conv3x3_igemm_v2_kernel<CK, TPG><<<dim3(gx, nsplit), v2_threads<CK>(), smem, st>>>(ta, tb, P, G);
     SCM_CUDA(cudaGetLastError());
     return SCM_OK;
@@ -190,20 +199,11 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
         if (rc) return rc;
     }
     const int smem = fixed + G.num_stages * G.a_stage_bytes;
-    static bool attr9 = false, attr3 = false;
     if (tpg == 9) {
-        if (!attr9) {
-            SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v3_kernel<64, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSmemMax));
-            attr9 = true;
-        }
+        SCM_OPT_IN_SMEM((conv3x3_igemm_v3_kernel<64, 9>), kSmemMax);
         conv3x3_igemm_v3_kernel<64, 9><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
     } else {
-        if (!attr3) {
-            SCM_CUDA(cudaFuncSetAttribute(conv3x3_igemm_v3_kernel<64, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          kSmemMax));
-            attr3 = true;
-        }
+        SCM_OPT_IN_SMEM((conv3x3_igemm_v3_kernel<64, 3>), kSmemMax);
         conv3x3_igemm_v3_kernel<64, 3><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
     }
     SCM_CUDA(cudaGetLastError());
@@ -354,6 +354,9 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     P.gate = reinterpret_cast<const __nv_bfloat16*>(d->gate); P.gate_cs = d->gate_cs; P.gate_c_off = d->gate_c_off;
     P.out_f32 = d->out_f32; P.n_valid = d->n_valid; P.sample_out = d->sample_out; P.uniforms = d->uniforms;
     P.rng = d->rng_state;
+    SCM_REQUIRE((d->x_fmt | 1) == 1 && (d->w_fmt | 1) == 1 && (d->out_fmt | 1) == 1, "conv3x3: bad format code");
+    SCM_REQUIRE(!d->add || d->out_fmt == SCMGAN_FMT_BF16, "conv3x3: `add` planes are bf16 only");
+    P.a_fmt = d->x_fmt; P.b_fmt = d->w_fmt; P.out_fmt = d->out_fmt;
     {
         const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? atoi(dbg) : 0;
@@ -393,6 +396,7 @@ static thread_local scmgan_wgrad_reduce_job* t_defer_jobs = nullptr;
 static thread_local int t_defer_cap = 0;
 static thread_local int* t_defer_count = nullptr;
 static thread_local long long t_ws_off = 0;  // bytes; advanced only while deferring
+static thread_local int t_dy_fmt = 0, t_x_fmt = 0;  // operand formats of the wgrad call being dispatched
 
 // Scratch for one launch: the whole workspace when reductions run immediately (stream order protects it), a fresh
 // slice while deferring.  nullptr = does not fit.
@@ -463,6 +467,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     if (!ws) return 1;
     P.n = n; P.q_aw = q_aw; P.wq = wq; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.ws = ws;
     P.ws_bias = db ? ws + main_floats : nullptr;
+    P.p_fmt = t_dy_fmt; P.q_fmt = t_x_fmt;
     {
         static const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? (atoi(dbg) & (8 | 16)) : 0;
@@ -483,11 +488,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
         int rc = encode_tmap_bf16(&tq, qp, 4, dims, str, box, q_aw * 2);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr_set = true;
-    }
+    SCM_OPT_IN_SMEM(conv3x3_wgrad_v2_kernel, kSmemMax);
     const int smem = stages * stage_bytes + 1024 + 1024;
     conv3x3_wgrad_v2_kernel<<<dim3(splits, 3), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
@@ -537,6 +538,8 @@ static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* 
     P.with_ones = with_ones ? 1 : 0;
     P.ws = ws;
     P.ws_bias = with_ones ? ws + main_floats : nullptr;
+    P.m_fmt = x_is_wide ? t_x_fmt : t_dy_fmt;
+    P.n_fmt = x_is_wide ? t_dy_fmt : t_x_fmt;
     {
         static const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? (atoi(dbg) & 16) : 0;
@@ -559,12 +562,7 @@ static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* 
         int rc = encode_tmap_bf16(&tdy, bp, 4, dims, str, box, x_is_wide ? 32 : 128);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_narrow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      kSmemMax));
-        attr_set = true;
-    }
+    SCM_OPT_IN_SMEM(conv3x3_wgrad_narrow_kernel, kSmemMax);
     const int smem = stages * stage_bytes + 1024 + 1024;
     if (x_is_wide)
         conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tx, tdy, P, stages);
@@ -639,6 +637,8 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     P.tap0_stride = tg; P.n = n; P.q_aw = q_aw; P.p_c_off = p_c_off; P.q_c_off = q_c_off; P.q_sign = q_sign;
     P.flip = flip; P.scale = scale; P.g = g; P.g_sm = g_sm; P.g_sn = g_sn; P.g_st = g_st;
     P.m_valid = m_valid; P.n_valid = n_valid;
+    P.p_fmt = p_interior ? t_dy_fmt : t_x_fmt;  // the interior-view operand is always the gradient plane
+    P.q_fmt = p_interior ? t_x_fmt : t_dy_fmt;
     {
         static const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? (atoi(dbg) & 8) : 0;
@@ -660,11 +660,7 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
     rc = make_view(&tq, qp, q_cs, !p_interior, q_aw, q_aw * 2);
     if (rc) return rc;
 
-    static bool attr_set = false;
-    if (!attr_set) {
-        SCM_CUDA(cudaFuncSetAttribute(conv3x3_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-        attr_set = true;
-    }
+    SCM_OPT_IN_SMEM(conv3x3_wgrad_kernel, 227 * 1024);
     const int smem = stages * stage_bytes + 1024 + 256;
     conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
@@ -685,7 +681,8 @@ int scmgan_num_sms(void) { return num_sms(); }
 long long scmgan_launch_count(void) { return g_launches.load(); }
 
 int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int H, int W, void* dst_plane, int Cs,
-                     int c_off, int c_pad, int wrap, const float* sig, scmgan_stream_t stream) {
+                     int c_off, int c_pad, int wrap, const float* sig, int fmt, scmgan_stream_t stream) {
+    SCM_REQUIRE((fmt | 1) == 1, "pack_nchw: bad format code");
     SCM_REQUIRE(src && dst_plane, "pack_nchw: null pointer");
     SCM_REQUIRE(B > 0 && H > 0 && W > 0 && C > 0, "pack_nchw: bad geometry");
     SCM_REQUIRE(Cs % 8 == 0 && c_off % 8 == 0 && c_pad % 8 == 0 && c_pad >= C && c_off + c_pad <= Cs,
@@ -694,18 +691,19 @@ int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int 
     const int threads = 128;
     const long long blocks = (rows + threads - 1) / threads;
     pack_nchw_to_plane_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap, sig);
+        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap, sig, fmt);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
 }
 
-int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, scmgan_stream_t stream) {
+int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, int fmt, scmgan_stream_t stream) {
+    SCM_REQUIRE((fmt | 1) == 1, "pack_coords: bad format code");
     SCM_REQUIRE(dst_plane && B > 0 && H > 0 && W > 0, "pack_coords: bad arguments");
     SCM_REQUIRE(c_off % 2 == 0 && c_off + 2 <= Cs, "pack_coords: bad channel window (Cs=%d off=%d)", Cs, c_off);
     const long long total = (long long)B * H * W;
     pack_coords_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, B, H, W);
+        reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, B, H, W, fmt);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -728,6 +726,8 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t 
             d.s_n = s.s_n; d.s_k = s.s_k; d.k_src_off = s.k_src_off; d.flip = s.flip;
             SCM_REQUIRE(s.out_ld == 0 || s.out_ld >= s.k_pad, "pack_weights: job %d: out_ld < k_pad", base + i);
             d.out_ld = s.out_ld ? s.out_ld : s.k_pad;
+            SCM_REQUIRE((s.fmt | 1) == 1, "pack_weights: job %d: bad format code", base + i);
+            d.fmt = s.fmt;
             max_total = std::max(max_total, 9LL * s.n_pad * s.k_pad);
         }
         const int threads = 256;
@@ -748,6 +748,8 @@ static int wgrad_dispatch(const scmgan_wgrad_desc* d, scmgan_stream_t stream);
 
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     SCM_REQUIRE(d != nullptr, "wgrad: null descriptor");
+    SCM_REQUIRE((d->dy_fmt | 1) == 1 && (d->x_fmt | 1) == 1, "wgrad: bad format code");
+    t_dy_fmt = d->dy_fmt; t_x_fmt = d->x_fmt;
     if (d->defer_jobs) {
         SCM_REQUIRE(d->defer_count && d->workspace_cursor && d->defer_cap > 0 && d->workspace,
                     "wgrad: deferred reduction needs defer_count, workspace_cursor and a workspace");
@@ -970,11 +972,11 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
 }
 
 int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
-                      long long mask_stride, int B, int R, float scale, float* loss, float* dpred,
-                      scmgan_stream_t stream) {
+                      long long mask_stride, int B, int R, float scale, const float* scale_dev, float* loss,
+                      float* loss_raw, float* dpred, scmgan_stream_t stream) {
     SCM_REQUIRE(pred && target && loss && B > 0 && R > 0, "masked_mse: bad arguments");
     masked_mse_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, target_bstride, mask, mask_stride, B, R, scale,
-                                                          loss, dpred);
+                                                          scale_dev, loss, loss_raw, dpred);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1089,11 +1091,7 @@ int scmgan_gru_conv_sweep_fwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t s
         set_error("gru_conv_sweep_fwd: line of %d x %d does not fit shared memory", P.n, P.C);
         return SCM_EUNSUPPORTED;
     }
-    static bool attr = false;
-    if (!attr) {
-        SCM_CUDA(cudaFuncSetAttribute(csrn_sweep_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr = true;
-    }
+    SCM_OPT_IN_SMEM(csrn_sweep_fwd_kernel, kSmemMax);
     csrn_sweep_fwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
@@ -1109,11 +1107,7 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t s
         set_error("gru_conv_sweep_bwd: line of %d x %d does not fit shared memory", P.n, P.C);
         return SCM_EUNSUPPORTED;
     }
-    static bool attr = false;
-    if (!attr) {
-        SCM_CUDA(cudaFuncSetAttribute(csrn_sweep_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemMax));
-        attr = true;
-    }
+    SCM_OPT_IN_SMEM(csrn_sweep_bwd_kernel, kSmemMax);
     csrn_sweep_bwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;

@@ -59,6 +59,9 @@ struct IgemmParams {
     const float* uniforms;  // fp32 NCHW or nullptr (nullptr => threshold at 0.5)
     const unsigned long long* rng;  // device {seed, offset} for the in-kernel Philox stream, or nullptr
     int debug;              // profiling aid (env SCMGAN_DEBUG): bit0 skip global stores, bit1 skip TMEM loads
+    // 16-bit formats (FMT_BF16 / FMT_F16) of the input plane, the packed weights and the output plane.  The gate plane
+    // is only tested for "> 0", which reads the same bits in both formats.
+    int a_fmt, b_fmt, out_fmt;
 };
 
 // Philox4x32-10 (Salmon et al., SC'11), the counter-based generator torch/cuRAND use.  One 128-bit counter yields four
@@ -171,7 +174,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
         if (lane == 0) {
-            const uint32_t idesc = make_idesc_f16(128, P.n, /*bf16*/ 1, 0, 0);
+            const uint32_t idesc = make_idesc_ab(128, P.n, P.a_fmt, P.b_fmt, 0, 0);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -279,13 +282,13 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                 }
                 if (P.out) {
                     uint4 o0, o1;
-                    __nv_bfloat162* w0 = reinterpret_cast<__nv_bfloat162*>(&o0);
-                    __nv_bfloat162* w1 = reinterpret_cast<__nv_bfloat162*>(&o1);
+                    uint32_t* w0 = reinterpret_cast<uint32_t*>(&o0);
+                    uint32_t* w1 = reinterpret_cast<uint32_t*>(&o1);
                     if (interior) {
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
-                            w0[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
-                            w1[i] = __floats2bfloat162_rn(v[8 + 2 * i], v[8 + 2 * i + 1]);
+                            w0[i] = pack2_fmt(v[2 * i], v[2 * i + 1], P.out_fmt);
+                            w1[i] = pack2_fmt(v[8 + 2 * i], v[8 + 2 * i + 1], P.out_fmt);
                         }
                     } else {
                         o0 = make_uint4(0, 0, 0, 0);

@@ -175,7 +175,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         // One elected lane issues every tcgen05.mma; with N = 64 an instruction retires in ~32 cycles, so the issue
         // loop is fully unrolled, descriptor arithmetic is one 64-bit add per operand, and control flow stays
         // warp-uniform so that the descriptors live in uniform registers (no per-instruction convergence loop).
-        const uint32_t idesc = make_idesc_f16(128, G.n_cta, /*bf16*/ 1, 0, 0);
+        const uint32_t idesc = make_idesc_ab(128, G.n_cta, P.a_fmt, P.b_fmt, 0, 0);
         const uint64_t bdesc0 = make_smem_desc(smem_u32(s_b), 16, Cfg::kSbo, Cfg::kLayout);
         const uint64_t adesc0 = make_smem_desc(smem_u32(s_a), 16, Cfg::kSbo, Cfg::kLayout);
         const uint32_t b_tile16 = uint32_t(G.b_tile_bytes) >> 4;

@@ -123,7 +123,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     } else if (warp == 1) {
         // ------------------------------ MMA issuer (leader CTA only) ------------------------------
         if (rank == 0) {
-            const uint32_t idesc = make_idesc_f16(256, n_full, /*bf16*/ 1, 0, 0);
+            const uint32_t idesc = make_idesc_ab(256, n_full, P.a_fmt, P.b_fmt, 0, 0);
             const uint64_t bdesc0 = make_smem_desc(smem_u32(s_b), 16, Cfg::kSbo, Cfg::kLayout);
             const uint64_t adesc0 = make_smem_desc(smem_u32(s_a), 16, Cfg::kSbo, Cfg::kLayout);
             const uint32_t b_tile16 = uint32_t(G.b_tile_bytes) >> 4;

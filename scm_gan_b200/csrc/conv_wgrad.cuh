@@ -40,6 +40,7 @@ struct WgradParams {
     int m_valid, n_valid;
     int debug;  // profiling aid (env SCMGAN_DEBUG bit3): skip the reduction
     float* ws;  // split-K partials [split][tap][n][128] (fp32) or nullptr => red.global.add straight into g
+    int p_fmt, q_fmt;  // 16-bit formats of the two operand planes (FMT_BF16 / FMT_F16)
 };
 
 constexpr int kWgradThreads = 192;
@@ -119,7 +120,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = make_idesc_f16(128, P.n, 1, 1, 1);
+            const uint32_t idesc = make_idesc_ab(128, P.n, P.p_fmt, P.q_fmt, 1, 1);
             const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
             const uint32_t q_sbo = 8u * P.q_aw * 2u;
             const uint32_t q_kstep16 = (16u * P.q_aw * 2u) >> 4;

@@ -34,6 +34,7 @@ struct WgradNarrowParams {
     float* ws;        // split-K partials [m block][split][tap][16][128]
     float* ws_bias;   // [m block][split][128] (with_ones)
     int debug;
+    int m_fmt, n_fmt;  // 16-bit formats of the 128-wide (M) and the 16-wide (N) operand planes
 };
 
 constexpr int kNarrowCo = 16;
@@ -81,7 +82,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     if (P.with_ones) {  // tile 9 of every stage: bf16 1.0 (never touched by TMA)
         for (int s = 0; s < num_stages; ++s) {
             uint32_t* ones = reinterpret_cast<uint32_t*>(smem + size_t(s) * stage_bytes + a_bytes + 9 * b_tile_bytes);
-            for (int i = threadIdx.x; i < b_tile_bytes / 4; i += blockDim.x) ones[i] = 0x3F803F80u;
+            for (int i = threadIdx.x; i < b_tile_bytes / 4; i += blockDim.x) ones[i] = P.n_fmt == FMT_F16 ? 0x3C003C00u : 0x3F803F80u;
         }
         fence_proxy_async_smem();
     }
@@ -113,7 +114,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t idesc = make_idesc_f16(128, n_tiles * kNarrowCo, 1, 1, 1);  // both operands MN-major (K = pixels)
+        const uint32_t idesc = make_idesc_ab(128, n_tiles * kNarrowCo, P.m_fmt, P.n_fmt, 1, 1);  // both operands MN-major (K = pixels)
         const uint64_t adesc0 = make_smem_desc(smem_u32(smem), uint32_t(a_atom_bytes), 1024, kLayoutSw128);
         const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + uint32_t(a_bytes), uint32_t(b_tile_bytes), 256, kLayoutSw32);
         const uint32_t stage16 = uint32_t(stage_bytes) >> 4;

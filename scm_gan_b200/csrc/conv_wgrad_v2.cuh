@@ -29,6 +29,7 @@ struct WgradV2Params {
     float* ws;        // split-K partials [split][tap][n][128]
     float* ws_bias;   // optional bias-gradient partials [split][128] (nullptr: not requested)
     int debug;
+    int p_fmt, q_fmt;  // 16-bit formats of dY (P) and X (Q)
 };
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
@@ -105,7 +106,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = make_idesc_f16(128, P.n, 1, 1, 1);
+            const uint32_t idesc = make_idesc_ab(128, P.n, P.p_fmt, P.q_fmt, 1, 1);
             const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
             const uint64_t adesc0 = make_smem_desc(smem_u32(smem), p_atom_bytes, 1024, kLayoutSw128);
             const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + p_bytes, q_atom_bytes, 8u * q_row_bytes, q_layout);
@@ -113,7 +114,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
             const uint32_t q_tile16 = uint32_t(q_tile_bytes) >> 4;
             const uint32_t q_row16 = uint32_t(q_row_bytes) >> 4;
             const int ksteps = P.W / 16;
-            const uint32_t idesc_b = make_idesc_f16(128, 16, 1, 1, 1);
+            const uint32_t idesc_b = make_idesc_ab(128, 16, P.p_fmt, FMT_BF16, 1, 1);  // ones tile is bf16 1.0
             const uint64_t ones_desc = make_smem_desc(smem_u32(s_ones), 512, 256, kLayoutSw32);
             const uint32_t tmem_b = tmem_base + uint32_t(3 * P.n);
             int stage = 0;

@@ -13,7 +13,7 @@ namespace scm {
 // probability map (backward of the Encoder / Transition output sigmoid, reference models.py:103,154).
 __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long long src_bstride, int C, int B, int H,
                                           int W, __nv_bfloat16* __restrict__ dst, int Cs, int c_off, int c_pad,
-                                          int wrap, const float* __restrict__ sig) {
+                                          int wrap, const float* __restrict__ sig, int fmt) {
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -34,7 +34,8 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
     __nv_bfloat16* d = dst + p * Cs + c_off;
     for (int c0 = 0; c0 < c_pad; c0 += 8) {
         uint4 o;
-        __nv_bfloat16* oh = reinterpret_cast<__nv_bfloat16*>(&o);
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+        float xv[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int c = c0 + i;
@@ -46,21 +47,23 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
                     x *= q * (1.f - q);
                 }
             }
-            oh[i] = __float2bfloat16_rn(x);
+            xv[i] = x;
         }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) ow[i] = pack2_fmt(xv[2 * i], xv[2 * i + 1], fmt);
         *reinterpret_cast<uint4*>(d + c0) = o;
     }
 }
 
 // CoordConv coordinate channels: x coordinate -1 + 2w/W at channel c_off, y coordinate -1 + 2h/H at c_off + 1 of every
 // interior pixel (reference coordconv.py:10-14).
-__global__ void pack_coords_kernel(__nv_bfloat16* __restrict__ dst, int Cs, int c_off, int B, int H, int W) {
+__global__ void pack_coords_kernel(__nv_bfloat16* __restrict__ dst, int Cs, int c_off, int B, int H, int W, int fmt) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * H * W) return;
     const int w = int(i % W), h = int((i / W) % H), b = int(i / ((long long)W * H));
     const long long p = ((long long)b * (H + 2) + (h + 1)) * (W + 2) + (w + 1);
-    const __nv_bfloat162 v = __floats2bfloat162_rn(-1.f + 2.f * float(w) / float(W), -1.f + 2.f * float(h) / float(H));
-    *reinterpret_cast<__nv_bfloat162*>(dst + p * Cs + c_off) = v;
+    *reinterpret_cast<uint32_t*>(dst + p * Cs + c_off) =
+        pack2_fmt(-1.f + 2.f * float(w) / float(W), -1.f + 2.f * float(h) / float(H), fmt);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -77,6 +80,7 @@ struct PackJob {
     int k_src_off;  // first source k (e.g. skip nothing: 0)
     int flip;
     int out_ld;     // row pitch of out in elements (>= k_pad)
+    int fmt;        // FMT_BF16 / FMT_F16
 };
 constexpr int kMaxPackJobs = 16;
 struct PackJobs {
@@ -97,7 +101,10 @@ __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
         float x = 0.f;
         if (n < J.n_valid && k < J.k_valid)
             x = __ldg(J.w + n * J.s_n + (long long)(k + J.k_src_off) * J.s_k + (J.flip ? 8 - tap : tap)) * inv;
-        J.out[r * J.out_ld + k] = __float2bfloat16_rn(x);
+        if (J.fmt == FMT_F16)
+            reinterpret_cast<__half*>(J.out)[r * J.out_ld + k] = __float2half_rn(fminf(fmaxf(x, -65504.f), 65504.f));
+        else
+            J.out[r * J.out_ld + k] = __float2bfloat16_rn(x);
     }
 }
 
@@ -448,13 +455,18 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
 
 // ----------------------------------------------------------------------------------------------
 // Masked mean-squared error of the reward predictions (reference main.py:182-186), forward and gradient in one
-// single-block launch:  loss = scale/(B*R) * sum_b mask[b] * sum_r (pred - target)^2
+// single-block launch:  loss = scale * (*scale_dev) / (B*R) * sum_b mask[b] * sum_r (pred - target)^2
+// scale_dev (optional device scalar) carries the training-progress factor theta = iter/iters of main.py:143,185 so
+// that one captured CUDA graph serves every iteration; loss_raw (optional) receives the unscaled masked mean, the
+// value the reference logs as "Rd Loss" (main.py:184).
 // ----------------------------------------------------------------------------------------------
 __global__ void masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
                                   long long t_bstride, const float* __restrict__ mask, long long m_stride, int B, int R,
-                                  float scale, float* __restrict__ loss, float* __restrict__ dpred) {
+                                  float scale, const float* __restrict__ scale_dev, float* __restrict__ loss,
+                                  float* __restrict__ loss_raw, float* __restrict__ dpred) {
     __shared__ float red[33];
-    const float k = scale / (float(B) * float(R));
+    const float k0 = 1.f / (float(B) * float(R));
+    const float k = scale * (scale_dev ? __ldg(scale_dev) : 1.f) * k0;
     float acc = 0.f;
     for (int i = threadIdx.x; i < B * R; i += blockDim.x) {
         const int b = i / R, r = i - b * R;
@@ -464,7 +476,10 @@ __global__ void masked_mse_kernel(const float* __restrict__ pred, const float* _
         if (dpred) dpred[i] = 2.f * k * m * d;
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) *loss = acc * k;
+    if (threadIdx.x == 0) {
+        *loss = acc * k;
+        if (loss_raw) *loss_raw = acc * k0;
+    }
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -212,10 +212,12 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             for (int j = 0; j < GROUP / 16; ++j) {
                 uint32_t o[8];
                 if (R.interior) {
+                    if (P.out_fmt == FMT_F16) {  // warp-uniform
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const __nv_bfloat162 h = __floats2bfloat162_rn(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
-                        o[i] = *reinterpret_cast<const uint32_t*>(&h);
+                        for (int i = 0; i < 8; ++i) o[i] = pack2_f16(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = pack2_bf16(v[16 * j + 2 * i], v[16 * j + 2 * i + 1]);
                     }
                 } else {
 #pragma unroll

@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda.h>
 #include <stdint.h>
 
@@ -159,6 +160,38 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 __host__ __device__ constexpr uint32_t make_idesc_f16(int m, int n, int fmt, int a_mn, int b_mn) {
     return (1u << 4) | (uint32_t(fmt) << 7) | (uint32_t(fmt) << 10) | (uint32_t(a_mn) << 15) |
            (uint32_t(b_mn) << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// Operand formats of the C ABI (SCMGAN_FMT_*): 0 = bf16, 1 = fp16.  kind::f16 takes either format per operand (the A
+// and B format fields of the instruction descriptor are independent), fp32 accumulation in both cases.
+enum : int { FMT_BF16 = 0, FMT_F16 = 1 };
+__host__ __device__ constexpr uint32_t make_idesc_ab(int m, int n, int a_fmt, int b_fmt, int a_mn, int b_mn) {
+    // descriptor encoding: 0 = fp16, 1 = bf16
+    return (1u << 4) | (uint32_t(a_fmt == FMT_F16 ? 0 : 1) << 7) | (uint32_t(b_fmt == FMT_F16 ? 0 : 1) << 10) |
+           (uint32_t(a_mn) << 15) | (uint32_t(b_mn) << 16) | (uint32_t(n >> 3) << 17) | (uint32_t(m >> 4) << 24);
+}
+
+// two fp32 -> packed 16-bit pair (first value in the low half), round to nearest even; fp16 saturates to +-65504
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack2_f16(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ uint32_t pack2_fmt(float lo, float hi, int fmt) {
+    return fmt == FMT_F16 ? pack2_f16(lo, hi) : pack2_bf16(lo, hi);
+}
+__device__ __forceinline__ float unpack_lo(uint32_t w, int fmt) {
+    if (fmt == FMT_F16) return __half2float(__ushort_as_half((unsigned short)(w & 0xFFFFu)));
+    return __uint_as_float(w << 16);
+}
+__device__ __forceinline__ float unpack_hi(uint32_t w, int fmt) {
+    if (fmt == FMT_F16) return __half2float(__ushort_as_half((unsigned short)(w >> 16)));
+    return __uint_as_float(w & 0xFFFF0000u);
 }
 
 constexpr uint64_t kLayoutSw128 = 2, kLayoutSw64 = 4, kLayoutSw32 = 6;

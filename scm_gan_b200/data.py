@@ -63,11 +63,18 @@ class InputPipeline:
             static = self.trainer.static_inputs(slot, theta, cf_now)
             for k, v in slot.items():
                 static[k].copy_(v, non_blocking=True)
-            src = static
-        else:
-            src = slot
+            # the slot has been read: the device-to-device copies into the graph's static inputs are ordered before
+            # this point, the replay only touches the static tensors
+            self._release(j, cur)
+            return self.trainer.step(static, theta, cf_now=cf_now, use_graph=True)
+        # eager iteration: its kernels read the slot itself (states[:, t] at every rollout step, ...), so the slot
+        # may only be refilled once the whole iteration has been enqueued
+        loss = self.trainer.step(slot, theta, cf_now=cf_now, use_graph=False)
+        self._release(j, cur)
+        return loss
+
+    def _release(self, j, stream):
         ev = torch.cuda.Event()
-        ev.record(cur)  # the slot has been read (device-to-device copies are ordered before this point)
+        ev.record(stream)
         self.consumed[j] = ev
         self.free.append(j)
-        return self.trainer.step(src, theta, cf_now=cf_now, use_graph=use_graph)

@@ -97,11 +97,11 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     sbias = torch.empty((B, HID), dtype=torch.float32, device=dev)
     K.action_bias(wbar[0], sigma[0:1], bias[0], a, L, sbias)
 
-    zin = K.new_plane(B, H, W, Lp, dev)
+    zin = K.fwd_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=True)
-    buf6 = K.new_plane(B, H, W, 2 * HID, dev)  # [act5 | act1]  = input of conv6 (models.py:101)
-    buf5 = K.new_plane(B, H, W, 2 * HID, dev)  # [act4 | act2]  = input of conv5 (models.py:95)
-    act3 = K.new_plane(B, H, W, HID, dev)
+    buf6 = K.fwd_plane(B, H, W, 2 * HID, dev)  # [act5 | act1]  = input of conv6 (models.py:101)
+    buf5 = K.fwd_plane(B, H, W, 2 * HID, dev)  # [act4 | act2]  = input of conv5 (models.py:95)
+    act3 = K.fwd_plane(B, H, W, HID, dev)
     cv = dict(act=ACT_LRELU, wrap=True)
     K.conv3x3(zin, wf[0], B, H, W, cin=Lp, sample_bias=sbias, out=buf6, out_c_off=HID, **cv)        # conv1 -> skip1
     K.conv3x3(buf6, wf[1], B, H, W, cin=HID, x_c_off=HID, bias=bias[1], out=buf5, out_c_off=HID, **cv)  # conv2 -> skip2
@@ -215,9 +215,9 @@ def encoder_forward(x, wbar, bias, sigma, w4, b4):
     jobs += [_conv2d_dgrad_job(wbar[1], wd[0], sigma[1:2]), _conv2d_dgrad_job(wbar[2], wd[1], sigma[2:3]),
              _conv2d_dgrad_job(w4, wd[2], None, co_valid=L)]
     K.pack_weights(jobs)
-    xin = K.new_plane(B, H, W, Cp, dev)
+    xin = K.fwd_plane(B, H, W, Cp, dev)
     K.pack_nchw(x, xin, wrap=False)
-    a1, a2, a3 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
+    a1, a2, a3 = (K.fwd_plane(B, H, W, HID, dev) for _ in range(3))
     K.conv3x3(xin, wf[0], B, H, W, cin=Cp, bias=bias[0], act=ACT_LRELU, out=a1)
     K.conv3x3(a1, wf[1], B, H, W, cin=HID, bias=bias[1], act=ACT_LRELU, out=a2)
     K.conv3x3(a2, wf[2], B, H, W, cin=HID, bias=bias[2], act=ACT_LRELU, out=a3)
@@ -296,9 +296,9 @@ def decoder_forward(z, w1, b1, w2, b2):
     wd2 = K.packed_weight(hid, cop, dev)
     K.pack_weights([_convT_fwd_job(w1, wf1), _convT_fwd_job(w2, wf2), _convT_dgrad_job(w1, wd1),
                     _convT_dgrad_job(w2, wd2)])
-    zin = K.new_plane(B, H, W, Lp, dev)
+    zin = K.fwd_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=False)
-    hidp = K.new_plane(B, H, W, HID, dev)
+    hidp = K.fwd_plane(B, H, W, HID, dev)
     K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     logits = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(hidp, wf2, B, H, W, cin=hid, bias=b2, act=ACT_NONE, out_f32=logits, n_valid=co)
@@ -372,9 +372,9 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     wd2 = K.packed_weight(RHID, 16, dev)
     K.pack_weights([_conv2d_fwd_job(w1, wf1), _conv2d_fwd_job(w2, wf2),
                     _conv2d_dgrad_job(w1, wd1), _conv2d_dgrad_job(w2, wd2)])
-    zin = K.new_plane(B, H, W, Lp, dev)
+    zin = K.fwd_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=False)
-    hidp = K.new_plane(B, H, W, HID, dev)
+    hidp = K.fwd_plane(B, H, W, HID, dev)
     K.conv3x3(zin, wf1, B, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
     y2 = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(hidp, wf2, B, H, W, cin=RHID, bias=b2, act=ACT_NONE,
@@ -437,7 +437,7 @@ def coordconv_forward(x, w, b):
     wf = K.packed_weight(Np, Cp, dev)
     wd = K.packed_weight(_r16(Cc), HID if Np <= HID else Np, dev)  # dgrad reads the 128-wide gradient plane
     K.pack_weights([_conv2d_fwd_job(w, wf), _conv2d_dgrad_job(w, wd, None, 0, Cc)])
-    xin = K.new_plane(B, H, W, Cp, dev)
+    xin = K.fwd_plane(B, H, W, Cp, dev)
     K.pack_nchw(x, xin, c_pad=Cp, wrap=False)
     K.pack_coords(xin, Cc)
     y = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)

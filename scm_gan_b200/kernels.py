@@ -12,6 +12,22 @@ from ._lib import ACT_LRELU, ACT_NONE, ACT_SIGMOID  # noqa: F401
 
 LRELU_SLOPE = 0.01  # F.leaky_relu default used by reference models.py:77-99
 
+# Storage format of the FORWARD operands (activation planes and packed weights).  fp16 (11-bit significand) keeps every
+# parameter gradient within 1e-2 of the fp32 reference at the benchmarked shapes; bf16 (the round-1 contract) is
+# 3-4x further away, almost all of it from the weight rounding (profiles/r02_grad_precision_*.json).  Gradient planes
+# are always bf16: back-propagated values go down to 1e-9, far below fp16's range.
+import os as _os
+FWD_DTYPE = torch.bfloat16 if _os.environ.get("SCMGAN_FWD_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
+GRAD_DTYPE = torch.bfloat16
+
+
+def _fmt(t):
+    """SCMGAN_FMT_* code of a 16-bit tensor."""
+    if t.dtype == torch.float16:
+        return L.FMT_F16
+    assert t.dtype == torch.bfloat16, f"planes / packed weights are bf16 or fp16, got {t.dtype}"
+    return L.FMT_BF16
+
 
 def launch_count():
     """Kernels launched through the C ABI so far (bench.py reports the per-step delta as gpu_launches)."""
@@ -22,9 +38,14 @@ def _stream():
     return torch.cuda.current_stream().cuda_stream
 
 
-def new_plane(B, H, W, Cs, device):
+def new_plane(B, H, W, Cs, device, dtype=None):
+    """dtype: FWD_DTYPE for forward activations, GRAD_DTYPE (default) for gradient planes."""
     # every element (halo included) is written by the producing kernel, so empty() is enough
-    return torch.empty((B, H + 2, W + 2, Cs), dtype=torch.bfloat16, device=device)
+    return torch.empty((B, H + 2, W + 2, Cs), dtype=dtype or GRAD_DTYPE, device=device)
+
+
+def fwd_plane(B, H, W, Cs, device):
+    return new_plane(B, H, W, Cs, device, FWD_DTYPE)
 
 
 def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False, sig=None):
@@ -38,13 +59,13 @@ def pack_nchw(src, dst_plane, c_off=0, c_pad=None, wrap=False, sig=None):
         c_pad = (Cc + 15) // 16 * 16
     assert sig is None or (sig.is_contiguous() and sig.shape == src.shape)
     L.check(L.lib().scmgan_pack_nchw(src.data_ptr(), src.stride(0), Cc, B, H, W, dst_plane.data_ptr(), Cs, c_off,
-                                     c_pad, int(wrap), L.ptr(sig), _stream()), "scmgan_pack_nchw")
+                                     c_pad, int(wrap), L.ptr(sig), _fmt(dst_plane), _stream()), "scmgan_pack_nchw")
 
 
 def pack_coords(dst_plane, c_off):
     """CoordConv coordinate channels into plane channels c_off (x) and c_off + 1 (y)."""
     B, Hp, Wp, Cs = dst_plane.shape
-    L.check(L.lib().scmgan_pack_coords(dst_plane.data_ptr(), Cs, c_off, B, Hp - 2, Wp - 2, _stream()),
+    L.check(L.lib().scmgan_pack_coords(dst_plane.data_ptr(), Cs, c_off, B, Hp - 2, Wp - 2, _fmt(dst_plane), _stream()),
             "scmgan_pack_coords")
 
 
@@ -57,19 +78,20 @@ def pack_weights(jobs):
         assert out.stride(2) == 1 and out.stride(0) == out.shape[1] * out.stride(1)
         arr[i] = L.PackJob(j["w"].data_ptr(), out.data_ptr(), L.ptr(j.get("sigma")), j["n_pad"], j["k_pad"],
                            j["n_valid"], j["k_valid"], j["s_n"], j["s_k"], j.get("k_src_off", 0), j.get("flip", 0),
-                           out.stride(1))
+                           out.stride(1), _fmt(out))
     L.check(L.lib().scmgan_pack_weights(len(jobs), arr, _stream()), "scmgan_pack_weights")
 
 
-def packed_weight(n_pad, k_pad, device):
-    return torch.empty((9, n_pad, k_pad), dtype=torch.bfloat16, device=device)
+def packed_weight(n_pad, k_pad, device, dtype=None):
+    """GEMM B operand [9][n_pad][k_pad]; FWD_DTYPE unless stated (all weights, forward and dgrad, use it)."""
+    return torch.empty((9, n_pad, k_pad), dtype=dtype or FWD_DTYPE, device=device)
 
 
 def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, act=ACT_NONE,
             out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
             n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False):
     n = w_packed.shape[1]
-    assert w_packed.shape[2] == cin and w_packed.dtype == torch.bfloat16
+    assert w_packed.shape[2] == cin
     d = L.ConvDesc()
     d.B, d.H, d.W = B, H, W
     d.x, d.x_cs, d.x_c_off, d.cin = x_plane.data_ptr(), x_plane.shape[3], x_c_off, cin
@@ -89,6 +111,8 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     d.out_f32, d.n_valid = L.ptr(out_f32), n_valid
     d.sample_out, d.uniforms = L.ptr(sample_out), L.ptr(uniforms)
     d.rng_state = L.ptr(rng_state)  # int64 [2] = {seed, offset}; advanced by the library after the launch
+    d.x_fmt, d.w_fmt = _fmt(x_plane), _fmt(w_packed)
+    d.out_fmt = _fmt(out) if out is not None else L.FMT_BF16
     fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
     L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
 
@@ -178,6 +202,7 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
     d.ci_valid = cin if ci_valid is None else ci_valid
     d.scale = scale
     d.db = L.ptr(db)  # bias gradient accumulated alongside (zero-initialised by the caller)
+    d.dy_fmt, d.x_fmt = _fmt(dy_plane), _fmt(x_plane)
     if defer is not None and defer.enabled:
         d.workspace, d.workspace_bytes = defer.ring.data_ptr(), defer.ring.numel() * 4
         d.defer_jobs, d.defer_cap = defer.jobs, defer.CAP
@@ -274,13 +299,14 @@ def bce_logits(x, y, mask, loss, dx=None):
                                       L.ptr(dx), _stream()), "scmgan_bce_logits")
 
 
-def masked_mse(pred, target, mask, scale, loss, dpred=None):
-    """pred [B,R] contiguous; target [B,R] with unit inner stride; mask [B] (any stride) or None."""
+def masked_mse(pred, target, mask, scale, loss, dpred=None, scale_dev=None, loss_raw=None):
+    """pred [B,R] contiguous; target [B,R] with unit inner stride; mask [B] (any stride) or None.
+    scale_dev: optional device scalar multiplied into the loss (theta); loss_raw: optional [1] unscaled mean."""
     B, R = pred.shape
     assert pred.is_contiguous() and target.shape == pred.shape and (R == 1 or target.stride(1) == 1)
     L.check(L.lib().scmgan_masked_mse(pred.data_ptr(), target.data_ptr(), target.stride(0), L.ptr(mask),
-                                      mask.stride(0) if mask is not None else 0, B, R, float(scale), loss.data_ptr(),
-                                      L.ptr(dpred), _stream()), "scmgan_masked_mse")
+                                      mask.stride(0) if mask is not None else 0, B, R, float(scale), L.ptr(scale_dev),
+                                      loss.data_ptr(), L.ptr(loss_raw), L.ptr(dpred), _stream()), "scmgan_masked_mse")
 
 
 def reward_head_fwd(y2, R, r, rmap=None):

@@ -44,7 +44,9 @@ def _sinks_of(params):
         if s is not None and s[2]() is None:   # the registering parameter died: its address may have been reused
             del _GRAD_SINK[p.data_ptr()]
             s = None
-        if s is not None and s[0].shape == p.shape:
+        # the sink stands in for autograd's own accumulation only while it IS the parameter's .grad: after
+        # zero_grad(set_to_none=True), or once another owner has re-homed .grad, autograd gets the gradient back
+        if s is not None and s[0].shape == p.shape and p.grad is not None and p.grad.data_ptr() == s[0].data_ptr():
             bufs.append(s[0])
             mask |= 1 << i
     return bufs, mask
@@ -280,17 +282,21 @@ bce_logits.register_autograd(_bce_backward, setup_context=_bce_setup)
 # Masked reward MSE (reference main.py:182-186), one kernel for value and gradient
 # ------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("scmgan::masked_mse", mutates_args=())
-def masked_mse(pred: Tensor, target: Tensor, mask: Tensor, scale: float) -> List[Tensor]:
+def masked_mse(pred: Tensor, target: Tensor, mask: Tensor, scale: float,
+               scale_dev: Optional[Tensor] = None) -> List[Tensor]:
+    """-> [scale * scale_dev * masked mean, d loss / d pred, unscaled masked mean].  scale_dev is a 0-dim / 1-element
+    device tensor (theta of main.py:143): no gradient flows to it."""
     _require_cuda(pred, target, mask)
     pred = pred.contiguous().float()
     if not (target.dtype == torch.float32 and (target.shape[1] == 1 or target.stride(1) == 1)):
         target = target.contiguous().float()
     if mask.dtype != torch.float32:
         mask = mask.float()
-    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    out = torch.empty(2, dtype=torch.float32, device=pred.device)
     dpred = torch.empty_like(pred)
-    K.masked_mse(pred, target, mask, scale, loss, dpred)
-    return [loss.view(()), dpred]
+    K.masked_mse(pred, target, mask, scale, out[0:1], dpred,
+                 scale_dev=None if scale_dev is None else scale_dev.reshape(1).float(), loss_raw=out[1:2])
+    return [out[0], dpred, out[1]]
 
 
 def _mse_setup(ctx, inputs, output):
@@ -301,7 +307,7 @@ def _mse_setup(ctx, inputs, output):
 def _mse_backward(ctx, grads):
     (dpred,) = ctx.saved_tensors
     g = grads[0]
-    return (None if g is None else dpred * g), None, None, None
+    return (None if g is None else dpred * g), None, None, None, None
 
 
 masked_mse.register_autograd(_mse_backward, setup_context=_mse_setup)

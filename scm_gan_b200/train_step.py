@@ -10,6 +10,7 @@ Differences from running main.py itself (all outside the arithmetic):
   * sigmoid + BCE + means are one fused kernel (scmgan::bce_logits) and clip + Adam is one multi-tensor kernel;
   * loss terms stay on the device (reference: ts.collect() syncs per term).
 """
+import collections
 import os
 import sys
 
@@ -51,11 +52,17 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     """Loss of one iteration (reference main.py:155-283).  All arguments are device tensors.
 
     states [B,Hn,C,H,W] f32, rewards [B,Hn,R] f32, dones [B,Hn] f32, actions [B,Hn] int64.
+    theta: training progress train_iter/train_iters (main.py:143), a Python float or - for CUDA-graph replay, where
+    one captured graph must serve every iteration - a 0-dim device tensor read by the kernels at run time.
     cf_indices [B,2] int64, cf_perm [B] int64 (when the CF losses fire); uniforms: optional list of [B,L,H,W]
     tensors consumed by successive Transition calls (parity tests), else torch's CUDA generator is used.
+    collect: optional dict receiving the named loss terms the reference hands to ts.collect() (main.py:184,196,233,
+    262,283) as 0-dim device tensors (no host synchronisation).
     """
     enc, dec, rew, tr = nets["encoder"], nets["decoder"], nets["reward_predictor"], nets["transition"]
     B, Hn = states.shape[0], states.shape[1]
+    if not torch.is_tensor(theta):
+        theta = torch.tensor(float(theta), dtype=torch.float32, device=states.device)
     A = tr.conv1.module.weight_bar.shape[1] - tr.latent_size
     eye = torch.eye(A, dtype=torch.float32, device=states.device)
     it = iter(uniforms) if uniforms is not None else None
@@ -77,14 +84,14 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     for t in range(1, Hn - 1):
         mask = masks[:, t - 1]
         expected = rew(z)
-        rd_scaled = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, theta * reward_coef)[0]
-        terms.append(rd_scaled)
+        rd = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, reward_coef, theta)
+        terms.append(rd[0])
         rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
         if truncate_bptt and t > 1:
             z = z.detach()
         terms.append(rec)
         if collect is not None:
-            collect[f"Rd Loss t={t}"] = torch.mean(torch.mean((expected.detach() - rewards[:, t]) ** 2, dim=1) * mask)
+            collect[f"Rd Loss t={t}"] = rd[2]
             collect[f"Reconstruction t={t}"] = rec
         z = step(z, onehots[t])
 
@@ -179,7 +186,14 @@ class Trainer:
         self._counting = False
         self._counts = {}
         self._profiles = {}   # (Hn, cf_now) -> {param id: number of gradient accumulations per iteration}
-        self._graphs = {}
+        self._graphs = {}     # (batch shape, cf_now) -> (graph, static inputs, loss); insertion order = LRU order
+        self._graph_pool = torch.cuda.graph_pool_handle() if torch.cuda.is_available() else None
+        self.captures = 0
+        self._log_ring = torch.zeros((self.LOG_RING, self.LOG_WIDTH), dtype=torch.float32, device=dev)
+        self._log_slot = torch.zeros(1, dtype=torch.int64, device=dev)
+        self._log_names = {}  # (Hn, cf_now) -> term names of that configuration
+        self._log_keys = collections.deque(maxlen=self.LOG_RING)  # configuration of the last iterations, oldest first
+        self._log_count = 0
         self.sync = None      # dp.BucketedGradSync, attached by the data-parallel launcher
         self.world_size = 1
         self.launches_per_step = {}
@@ -205,10 +219,14 @@ class Trainer:
             return
         self.flat_grad.zero_()
 
-    def _loss(self, batch, theta, cf_now):
+    def _loss(self, batch, theta, cf_now, collect=None):
         loss, _ = rollout_loss(self.nets, batch["states"], batch["rewards"], batch["dones"], batch["actions"],
                                theta=theta, reward_coef=self.reward_coef, cf_now=cf_now,
-                               cf_indices=batch.get("cf_indices"), cf_perm=batch.get("cf_perm"), **self.loss_kwargs)
+                               cf_indices=batch.get("cf_indices"), cf_perm=batch.get("cf_perm"), collect=collect,
+                               # parity tests inject the Bernoulli uniforms as one more (graph-static) input
+                               # [calls, B, L, H, W]; normally the Transition draws from its device Philox stream
+                               uniforms=list(batch["uniforms"].unbind(0)) if "uniforms" in batch else None,
+                               **self.loss_kwargs)
         return loss
 
     def _profile(self, batch, theta, cf_now):
@@ -233,7 +251,9 @@ class Trainer:
     def _iteration(self, batch, theta, cf_now, profile):
         """Everything from zero_grad to the optimizer step (graph-capturable)."""
         self._zero_grads()
-        loss = self._loss(batch, theta, cf_now)
+        terms = {}
+        loss = self._loss(batch, theta, cf_now, collect=terms)
+        self._log_terms((batch["states"].shape[1], bool(cf_now)), terms, loss)
         if self.sync is not None:
             self.sync.arm(profile)
         loss.backward()
@@ -253,6 +273,38 @@ class Trainer:
                          gscale=1.0 / self.world_size)
         return loss
 
+    # -- loss-term log (reference main.py:184,196,233,262,283 ts.collect + 297 ts.print_every(10)) ---------------------
+    LOG_RING = 16    # iterations kept on the device between two read-backs
+    LOG_WIDTH = 64   # named terms per iteration (2 per rollout step + LO + 2 CF + total)
+
+    def _log_terms(self, key, terms, loss):
+        """Append this iteration's named loss terms to a device-side ring (graph-capturable: the slot index lives on
+        the device).  The reference synchronises on every ts.collect(); here nothing leaves the device until
+        read_log()."""
+        names = list(terms.keys()) + ["loss"]
+        assert len(names) <= self.LOG_WIDTH
+        self._log_names[key] = names
+        row = torch.stack([v.detach().reshape(()) for v in terms.values()] + [loss.detach().reshape(())])
+        row = torch.nn.functional.pad(row, (0, self.LOG_WIDTH - row.numel())).unsqueeze(0)
+        self._log_ring.index_copy_(0, self._log_slot, row)
+        self._log_slot.add_(1).remainder_(self.LOG_RING)
+
+    def read_log(self, last=10):
+        """ONE device->host copy: the named loss terms of the last `last` iterations (oldest first) as a list of dicts.
+        Call it every 10 iterations where the reference calls ts.print_every(10) (main.py:297)."""
+        last = min(last, len(self._log_keys), self.LOG_RING)
+        if last == 0:
+            return []
+        ring = self._log_ring.cpu()
+        n = self._log_count
+        out = []
+        for j in range(n - last, n):
+            key = self._log_keys[j - n]
+            names = self._log_names[key]
+            row = ring[j % self.LOG_RING]
+            out.append({name: row[i].item() for i, name in enumerate(names)})
+        return out
+
     def _snapshot_sn(self):
         out = []
         for net in self.nets.values():
@@ -267,31 +319,61 @@ class Trainer:
             for p, val in snap:
                 p.copy_(val)
 
+    def _theta_tensor(self, theta, like):
+        if torch.is_tensor(theta):
+            return theta
+        return torch.tensor(float(theta), dtype=torch.float32, device=like.device)
+
     def step(self, batch, theta, cf_now=False, use_graph=False):
-        """batch: dict of device tensors.  Returns the (device) loss tensor of this iteration."""
-        if not use_graph:
-            return self._iteration(batch, theta, cf_now, self._profile(batch, theta, cf_now))
-        key = (tuple(batch["states"].shape), bool(cf_now), float(theta))
+        """batch: dict of device tensors; theta: training progress train_iter/train_iters (float or 0-dim tensor).
+        Returns the (device) loss tensor of this iteration.  With use_graph the iteration replays ONE CUDA graph per
+        (batch shape, cf_now): theta is a device scalar, not part of the graph."""
+        key = (batch["states"].shape[1], bool(cf_now))
+        self._log_keys.append(key)
+        self._log_count += 1
+        try:
+            if not use_graph:
+                return self._iteration(batch, self._theta_tensor(theta, batch["states"]), cf_now,
+                                       self._profile(batch, theta, cf_now))
+            graph, static, loss = self._graph_for(batch, cf_now)
+            for k, v in batch.items():
+                if static[k] is not v:
+                    static[k].copy_(v, non_blocking=True)
+            if torch.is_tensor(theta):
+                if theta is not static["theta"]:
+                    static["theta"].copy_(theta, non_blocking=True)
+            elif theta is not None:
+                static["theta"].fill_(float(theta))
+            graph.replay()
+            return loss
+        finally:
+            # the fused optimiser updates parameters through raw pointers (no version bump): drop the decoder's
+            # folded-weight cache so that a later stand-alone forward cannot see pre-update weights
+            self.nets["decoder"]._fold = None
+
+    def _graph_for(self, batch, cf_now):
+        key = (tuple(batch["states"].shape), bool(cf_now))
         g = self._graphs.get(key)
         if g is None:
-            g = self._capture(batch, theta, cf_now)
-            self._graphs[key] = g
-        graph, static, loss = g
-        for k, v in batch.items():
-            if static[k] is not v:
-                static[k].copy_(v, non_blocking=True)
-        graph.replay()
-        return loss
+            if len(self._graphs) >= self.MAX_GRAPHS:  # bounded: evict the least recently used graph
+                self._graphs.pop(next(iter(self._graphs)))
+            g = self._capture(batch, cf_now)
+        else:
+            self._graphs.pop(key)
+        self._graphs[key] = g  # most recently used last
+        return g
 
-    def static_inputs(self, batch, theta, cf_now=False):
-        """Capture (if needed) and return the graph's static input tensors, so callers can fill them in place."""
-        key = (tuple(batch["states"].shape), bool(cf_now), float(theta))
-        if key not in self._graphs:
-            self._graphs[key] = self._capture(batch, theta, cf_now)
-        return self._graphs[key][1]
+    MAX_GRAPHS = 24  # 8 horizons x {regular, CF} of the default schedule (main.py:40-41,143-145) with room to spare
 
-    def _capture(self, batch, theta, cf_now):
+    def static_inputs(self, batch, theta=None, cf_now=False):
+        """Capture (if needed) and return the graph's static input tensors, so callers can fill them in place
+        (`theta` included: a 0-dim tensor)."""
+        return self._graph_for(batch, cf_now)[1]
+
+    def _capture(self, batch, cf_now):
         static = {k: v.clone() for k, v in batch.items()}
+        static["theta"] = torch.ones((), dtype=torch.float32, device=batch["states"].device)
+        theta = static["theta"]
         profile = self._profile(static, theta, cf_now)
         # warm-up on a side stream (allocator pools, lazy init); training state is restored afterwards
         snap_sn = self._snapshot_sn()
@@ -299,24 +381,35 @@ class Trainer:
         snap_m = [t.clone() for t in self.m]
         snap_v = [t.clone() for t in self.v]
         step0 = self.step_dev.clone()
+        log0 = (self._log_ring.clone(), self._log_slot.clone())
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             for _ in range(2):
                 self._iteration(static, theta, cf_now, profile)
         torch.cuda.current_stream().wait_stream(s)
-        with torch.no_grad():
-            self._restore_sn(snap_sn)
-            for p, val in snap_p:
-                p.copy_(val)
-            for t, val in zip(self.m, snap_m):
-                t.copy_(val)
-            for t, val in zip(self.v, snap_v):
-                t.copy_(val)
-            self.step_dev.copy_(step0)
+
+        def restore():
+            with torch.no_grad():
+                self._restore_sn(snap_sn)
+                for p, val in snap_p:
+                    p.copy_(val)
+                for t, val in zip(self.m, snap_m):
+                    t.copy_(val)
+                for t, val in zip(self.v, snap_v):
+                    t.copy_(val)
+                self.step_dev.copy_(step0)
+                self._log_ring.copy_(log0[0])
+                self._log_slot.copy_(log0[1])
+        restore()
         n0 = self.K.launch_count()
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        # all graphs of this trainer draw their temporaries from one private pool: they are replayed one at a time and
+        # exchange nothing through pool memory (inputs are the static tensors, the only output is the loss scalar,
+        # which stays referenced), so memory is bounded by the largest graph instead of growing with every
+        # (horizon, cf) configuration
+        with torch.cuda.graph(graph, pool=self._graph_pool):
             loss = self._iteration(static, theta, cf_now, profile)
         self.launches_per_step[(static["states"].shape[1], bool(cf_now))] = self.K.launch_count() - n0
+        self.captures += 1
         return graph, static, loss

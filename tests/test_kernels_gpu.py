@@ -1,8 +1,9 @@
 """Kernel-level parity (-m gpu): every C-ABI kernel against a plain fp32 torch statement of the same op.
 
-The tensor-core kernels take bf16 operands; the references below are fed the *same bf16-rounded operands* in fp32
-(TF32 off), so the only differences are fp32 summation order and the bf16 rounding of stored outputs.
-Tolerances are written next to each check.
+The tensor-core kernels take 16-bit operands (fp16 for forward activations and weights, bf16 for gradient planes; the
+round-1 all-bf16 contract stays selectable); the references below are fed the *same rounded operands* in fp32 (TF32 off),
+so the only differences are fp32 summation order and the rounding of stored outputs.  Tolerances are written next to
+each check.
 """
 import os
 
@@ -24,6 +25,15 @@ def bf(x):
     return x.to(torch.bfloat16).to(torch.float32)
 
 
+# forward-operand formats under test: fp16 (default product path) and bf16 (round-1 contract, SCMGAN_FWD_DTYPE=bf16)
+FWD_DTYPES = [torch.float16, torch.bfloat16]
+OUT_TOL = {torch.float16: 6e-4, torch.bfloat16: 4e-3}  # stored-output rounding: 2^-12 / 2^-9 relative per element
+
+
+def rnd(x, dtype):
+    return x.to(dtype).to(torch.float32)
+
+
 def plane_interior(plane, c_off, C):
     """[B,Hp,Wp,Cs] bf16 -> [B,C,H,W] fp32"""
     return plane[:, 1:-1, 1:-1, c_off:c_off + C].permute(0, 3, 1, 2).float().contiguous()
@@ -38,19 +48,19 @@ def ref_conv(x_nchw, w, wrap):
     return F.conv2d(ref_plane(x_nchw, wrap), w)
 
 
-def make_plane(x_nchw, Cs, c_off, wrap):
+def make_plane(x_nchw, Cs, c_off, wrap, dtype=torch.bfloat16):
     from scm_gan_b200 import kernels as K
     B, C, H, W = x_nchw.shape
-    plane = torch.full((B, H + 2, W + 2, Cs), float("nan"), dtype=torch.bfloat16, device=DEV)
+    plane = torch.full((B, H + 2, W + 2, Cs), float("nan"), dtype=dtype, device=DEV)
     K.pack_nchw(x_nchw, plane, c_off=c_off, c_pad=(C + 15) // 16 * 16, wrap=wrap)
     return plane
 
 
-def pack_conv_weight(w, n_pad, k_pad, sigma=None, dgrad=False, k_src_off=0, k_valid=None):
+def pack_conv_weight(w, n_pad, k_pad, sigma=None, dgrad=False, k_src_off=0, k_valid=None, dtype=torch.bfloat16):
     """w: Conv2d weight [Co,Ci,3,3] -> packed [9][n_pad][k_pad]"""
     from scm_gan_b200 import kernels as K
     Co, Ci = w.shape[:2]
-    out = K.packed_weight(n_pad, k_pad, w.device)
+    out = K.packed_weight(n_pad, k_pad, w.device, dtype)
     if not dgrad:
         job = dict(w=w, out=out, sigma=sigma, n_pad=n_pad, k_pad=k_pad, n_valid=Co,
                    k_valid=Ci if k_valid is None else k_valid, s_n=Ci * 9, s_k=9, k_src_off=k_src_off, flip=0)
@@ -81,16 +91,18 @@ def report(name, got, ref, tol):
 
 # ------------------------------------------------------------------------------------------------------------
 
+@pytest.mark.parametrize("dt", FWD_DTYPES)
 @pytest.mark.parametrize("wrap", [False, True])
-def test_pack_nchw(wrap):
+def test_pack_nchw(wrap, dt):
     _setup()
     torch.manual_seed(1)
     B, C, H, W = 3, 9, 5, 7
     x = torch.randn(B, C, H, W, device=DEV)
-    plane = make_plane(x, 32, 16, wrap)
+    x[0, 0, 0, 0] = 1e5  # beyond fp16's range: saturates to 65504 instead of becoming inf
+    plane = make_plane(x, 32, 16, wrap, dt)
     got = plane[:, :, :, 16:32].permute(0, 3, 1, 2).float()
     ref = torch.zeros(B, 16, H + 2, W + 2, device=DEV)
-    ref[:, :C] = bf(ref_plane(x, wrap))
+    ref[:, :C] = rnd(ref_plane(x, wrap).clamp(-65504, 65504) if dt == torch.float16 else ref_plane(x, wrap), dt)
     assert torch.equal(got, ref)
 
 
@@ -109,27 +121,27 @@ CONV_CASES = [
 ]
 
 
+@pytest.mark.parametrize("dt", FWD_DTYPES)
 @pytest.mark.parametrize("case", CONV_CASES)
-def test_conv_fwd_plane(case):
-    """bias + activation epilogue, bf16 plane output incl. halo handling."""
+def test_conv_fwd_plane(case, dt):
+    """bias + activation epilogue, 16-bit plane output incl. halo handling."""
     _setup()
     from scm_gan_b200 import kernels as K
     B, H, W, Ci, Co, wrap, act = case
     torch.manual_seed(2)
-    x = bf(torch.randn(B, Ci, H, W, device=DEV))
-    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    x = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5), dt)
     bias = torch.randn(Co, device=DEV)
-    xp = make_plane(x, Ci, 0, wrap)
-    wp = pack_conv_weight(w, Co, Ci)
-    out = torch.full((B, H + 2, W + 2, Co + 16), float("nan"), dtype=torch.bfloat16, device=DEV)
+    xp = make_plane(x, Ci, 0, wrap, dt)
+    wp = pack_conv_weight(w, Co, Ci, dtype=dt)
+    out = torch.full((B, H + 2, W + 2, Co + 16), float("nan"), dtype=dt, device=DEV)
     K.conv3x3(xp, wp, B, H, W, cin=Ci, bias=bias, act=act, out=out, out_c_off=16, wrap=wrap)
     torch.cuda.synchronize()
     ref = ref_conv(x, w, wrap) + bias.view(1, -1, 1, 1)
     if act == 1:
         ref = F.leaky_relu(ref)
     got = plane_interior(out, 16, Co)
-    # bf16 output rounding: 2^-9 relative per element
-    assert report(f"conv_fwd {case}", got, ref, 4e-3)
+    assert report(f"conv_fwd {case} {dt}", got, ref, OUT_TOL[dt])
     # halo of the produced plane: wrapped copy or zeros
     full = out[:, :, :, 16:16 + Co].permute(0, 3, 1, 2).float()
     assert torch.equal(full, ref_plane(got, wrap)), "halo mismatch"
@@ -137,19 +149,20 @@ def test_conv_fwd_plane(case):
     assert torch.isnan(out[:, :, :, :16].float()).all()
 
 
-def test_conv_sample_bias_and_f32_head():
+@pytest.mark.parametrize("dt", FWD_DTYPES)
+def test_conv_sample_bias_and_f32_head(dt):
     """Transition conv1-style per-sample bias; conv6-style sigmoid + Bernoulli head with fp32 NCHW outputs."""
     _setup()
     from scm_gan_b200 import kernels as K
     torch.manual_seed(3)
     B, H, W, Ci, Co = 4, 15, 19, 256, 16
-    x = bf(torch.randn(B, Ci, H, W, device=DEV))
-    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    x = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5), dt)
     bias = torch.randn(Co, device=DEV)
     sb = torch.randn(B, Co, device=DEV)
     u = torch.rand(B, Co, H, W, device=DEV)
-    xp = make_plane(x, Ci, 0, True)
-    wp = pack_conv_weight(w, Co, Ci)
+    xp = make_plane(x, Ci, 0, True, dt)
+    wp = pack_conv_weight(w, Co, Ci, dtype=dt)
     p = torch.empty(B, Co, H, W, device=DEV)
     z = torch.empty(B, Co, H, W, device=DEV)
     K.conv3x3(xp, wp, B, H, W, cin=Ci, bias=bias, sample_bias=sb, act=2, out_f32=p, n_valid=Co, sample_out=z,
@@ -163,21 +176,24 @@ def test_conv_sample_bias_and_f32_head():
     assert torch.equal(z, (p > 0.5).float())
 
 
-def test_conv_dgrad_epilogue():
-    """dgrad = conv with flipped/transposed weights; epilogue adds a residual plane and gates with lrelu'."""
+@pytest.mark.parametrize("dt", FWD_DTYPES)
+def test_conv_dgrad_epilogue(dt):
+    """dgrad = conv with flipped/transposed weights; epilogue adds a residual plane and gates with lrelu'.
+    The gradient planes are bf16 whatever the forward format: with dt = fp16 the MMA mixes a bf16 A operand with an
+    fp16 B operand, and the gate is read from an fp16 plane."""
     _setup()
     from scm_gan_b200 import kernels as K
     torch.manual_seed(4)
     B, H, W, Ci, Co = 2, 15, 19, 128, 128
-    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
+    w = rnd(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5), dt)
     dy = bf(torch.randn(B, Co, H, W, device=DEV))
     resid = bf(torch.randn(B, Ci, H, W, device=DEV))
-    actv = bf(torch.randn(B, Ci, H, W, device=DEV))
+    actv = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
     for wrap in (True, False):
         dyp = make_plane(dy, Co, 0, wrap)
         rp = make_plane(resid, Ci, 0, wrap)
-        ap = make_plane(actv, Ci, 0, wrap)
-        wd = pack_conv_weight(w, Ci, Co, dgrad=True)
+        ap = make_plane(actv, Ci, 0, wrap, dt)
+        wd = pack_conv_weight(w, Ci, Co, dgrad=True, dtype=dt)
         out = K.new_plane(B, H, W, Ci, DEV)
         K.conv3x3(dyp, wd, B, H, W, cin=Co, out=out, wrap=wrap, add=rp, gate=ap, dgrad=True)
         # reference: autograd of the forward conv
@@ -208,15 +224,17 @@ WGRAD_CASES = [
 ]
 
 
+@pytest.mark.parametrize("dt", FWD_DTYPES)
 @pytest.mark.parametrize("case", WGRAD_CASES)
-def test_wgrad(case):
+def test_wgrad(case, dt):
+    """dY is a bf16 gradient plane, X a forward plane in `dt` (mixed-format MMA when dt = fp16)."""
     _setup()
     from scm_gan_b200 import kernels as K
     B, H, W, Ci, Co, wrap = case
     torch.manual_seed(5)
-    x = bf(torch.randn(B, Ci, H, W, device=DEV))
+    x = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
     dy = bf(torch.randn(B, Co, H, W, device=DEV))
-    xp = make_plane(x, Ci, 0, wrap)
+    xp = make_plane(x, Ci, 0, wrap, dt)
     dyp = make_plane(dy, Co, 0, wrap)  # halo deliberately non-zero in wrap mode: must be ignored
     g = torch.zeros(Co, Ci, 3, 3, device=DEV)
     db = torch.zeros(Co, device=DEV)
@@ -345,16 +363,19 @@ if __name__ == "__main__":
 
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     if only in ("", "pack"):
-        run(test_pack_nchw, False)
-        run(test_pack_nchw, True)
+        for dt in FWD_DTYPES:
+            run(test_pack_nchw, False, dt)
+            run(test_pack_nchw, True, dt)
     if only in ("", "conv"):
-        for c in CONV_CASES:
-            run(test_conv_fwd_plane, c)
-        run(test_conv_sample_bias_and_f32_head)
-        run(test_conv_dgrad_epilogue)
+        for dt in FWD_DTYPES:
+            for c in CONV_CASES:
+                run(test_conv_fwd_plane, c, dt)
+            run(test_conv_sample_bias_and_f32_head, dt)
+            run(test_conv_dgrad_epilogue, dt)
     if only in ("", "wgrad"):
-        for c in WGRAD_CASES:
-            run(test_wgrad, c)
+        for dt in FWD_DTYPES:
+            for c in WGRAD_CASES:
+                run(test_wgrad, c, dt)
     if only in ("", "misc"):
         run(test_spectral_norm_fwd_bwd)
         run(test_colsum_action_bce_adam)
@@ -483,6 +504,14 @@ def test_masked_mse():
     (ggot,) = torch.autograd.grad(got * 2.0, p2)
     assert report("masked mse", got, ref, 1e-6)
     assert report("masked mse grad", ggot, 2.0 * gref, 1e-6)
+    # theta as a device scalar (one CUDA graph for every training iteration) + the unscaled value the reference logs
+    theta = torch.tensor(0.25, device=DEV)
+    p3 = pred.detach().clone().requires_grad_(True)
+    out = torch.ops.scmgan.masked_mse(p3, rewards[:, 4], masks[:, 3], 0.37, theta)
+    (g3,) = torch.autograd.grad(out[0], p3)
+    assert report("masked mse (device theta)", out[0], 0.25 * ref, 1e-6)
+    assert report("masked mse grad (device theta)", g3, 0.25 * gref, 1e-6)
+    assert report("masked mse raw", out[2], ref / 0.37, 1e-6)
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 6, 7), (3, 16, 12, 9), (2, 32, 16, 16)])

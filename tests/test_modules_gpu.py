@@ -133,10 +133,14 @@ def _margin_hook(gen, margin, record):
 
 
 def _oracle_step(nets, cfg, batch, cf_h, cf_indices, cf_perm, uniforms, operand_dtype):
+    """operand_dtype None: the plain fp32 oracle.  Otherwise the same algorithm with the forward operands (conv inputs,
+    normalised weights) rounded to that format and the gradients entering each conv backward rounded to bf16 - the
+    storage formats of the product path (kernels.FWD_DTYPE / GRAD_DTYPE), fp32 accumulation."""
     from oracle import restated as R
     onets = oracle_nets(nets, requires_grad=True)
     states, rewards, dones, actions = batch
-    R.OPERAND_DTYPE = operand_dtype
+    if operand_dtype is not None:
+        R.ROUND.update(act=operand_dtype, w=operand_dtype, grad=torch.bfloat16)
     try:
         loss, terms, z = R.train_step_loss(
             onets, states, rewards, dones, actions.cpu().numpy(), num_actions=cfg["A"], theta=0.5, uniforms=uniforms,
@@ -144,21 +148,19 @@ def _oracle_step(nets, cfg, batch, cf_h, cf_indices, cf_perm, uniforms, operand_
             cf_indices=cf_indices.cpu(), cf_perm=cf_perm.cpu())
         loss.backward()
     finally:
-        R.OPERAND_DTYPE = None
+        R.ROUND.update(act="inherit", w="inherit", grad="inherit")
     return onets, loss, terms, z
 
 
-# Gradient tolerance vs the *fp32* oracle.  A LeakyReLU net differentiated at operands rounded to bf16 (2^-9) has a
-# fraction f ~ 1e-3..1e-2 of near-zero pre-activations on the other side of the kink, which alone moves the fp32
-# gradient by ~sqrt(f) in relative L2 (measured 1-8 %); so the 1e-2 bound of the north_star is asserted against the
-# oracle evaluated on the same bf16 operands (identical algorithm, fp32 accumulation), and the distance to the pure
-# fp32 oracle is bounded separately and reported.
-GRAD_TOL_VS_FP32 = 1.2e-1
-COSINE_VS_FP32 = 0.99
-# Even two bf16-operand evaluations that differ only in fp32 summation order (the kernel sums taps/chunks in a
-# different order than torch) disagree by an ulp on a few stored activations, which moves a handful of kinks:
-# measured worst case 1.1e-2 (sc2, Transition conv3, a layer whose gradient is tiny because most of the batch is
-# masked), <= 8e-3 everywhere else.
+# Gradient tolerance vs the *fp32* oracle on the tiny golden shapes (B = 2..3, 12x10 .. 16x16 frames).  The north_star's
+# 1e-2 is asserted at the benchmarked shapes by test_bench_shape_graph_replay_vs_oracle below; here a parameter
+# gradient is a sum over only a few hundred pixels, so the handful of LeakyReLU kinks that operand rounding moves
+# across zero (fp16: ~1e-4 of the pre-activations, profiles/r02_grad_precision_*.json) is not averaged out.  The same
+# oracle evaluated on the same rounded operands (identical algorithm, fp32 accumulation) must agree much more closely.
+GRAD_TOL_VS_FP32 = 4e-2
+COSINE_VS_FP32 = 0.999
+# Even two same-operand evaluations that differ only in fp32 summation order (the kernel sums taps/chunks in a
+# different order than torch) disagree by an ulp on a few stored activations, which moves a handful of kinks.
 GRAD_TOL_VS_BF16_ORACLE = 1.5e-2
 
 
@@ -180,8 +182,9 @@ def test_training_step_vs_oracle(name, cf_h):
     used = []
     o32, loss32, terms32, z32 = _oracle_step(nets, cfg, batch, cf_h, cf_indices, cf_perm,
                                              _margin_hook(gen, 0.02, used), None)
+    from scm_gan_b200 import kernels as K
     o16, loss16, terms16, z16 = _oracle_step(nets, cfg, batch, cf_h, cf_indices, cf_perm, copy.copy(used),
-                                             torch.bfloat16)
+                                             K.FWD_DTYPE)
     for n in nets.values():
         n.train()
     terms = {}
@@ -277,8 +280,8 @@ def test_gradient_sinks_match_autograd():
     cb_counts = {}
     sinks = {}
     for p in params:
-        p.grad = None
         sinks[id(p)] = torch.zeros_like(p)
+        p.grad = sinks[id(p)]   # a sink is honoured only while it is the parameter's .grad (ops._sinks_of)
         ops.register_grad_sink(p, sinks[id(p)], lambda q: cb_counts.__setitem__(id(q), cb_counts.get(id(q), 0) + 1))
     try:
         l_sink = run(copy.copy(used))
@@ -287,7 +290,8 @@ def test_gradient_sinks_match_autograd():
     assert l_sink == l_ref
     n_sunk = 0
     for p in params:
-        got = sinks[id(p)] if p.grad is None else sinks[id(p)] + p.grad   # whatever autograd still delivered
+        assert p.grad is sinks[id(p)]
+        got = sinks[id(p)]   # kernels and (for the few parameters without kernel-side accumulation) autograd add here
         if ref[id(p)] is None:
             assert got.abs().max().item() == 0
             continue
@@ -297,9 +301,21 @@ def test_gradient_sinks_match_autograd():
             n_sunk += 1
             # autograd sums a shared weight's gradients before one AccumulateGrad (one hook call); the sink
             # callback runs once per backward op that touched the parameter
-            assert p.grad is None and cb_counts[id(p)] >= hook_counts[id(p)] == 1
+            assert cb_counts[id(p)] >= hook_counts[id(p)] == 1
     print(f"{n_sunk} of {len(params)} parameters accumulated by the kernels")
     assert n_sunk >= len(params) - 4   # the decoder's folded conv2 weight/bias reach autograd as derived tensors
+    # a sink that is no longer the parameter's .grad (zero_grad(set_to_none=True), a reference-style loop with torch
+    # optimisers on the same modules) must be ignored: autograd then delivers the gradient itself
+    for p in params:
+        ops.register_grad_sink(p, sinks[id(p)])
+        p.grad = None
+    try:
+        run(copy.copy(used))
+    finally:
+        ops.clear_grad_sinks()
+    for p in params:
+        if ref[id(p)] is not None:
+            assert p.grad is not None and p.grad is not sinks[id(p)] and rel(p.grad, ref[id(p)]) < 1e-6
 
 
 def test_reference_main_loop_runs_on_dropin_modules():
