@@ -35,7 +35,10 @@ extern "C" {
 
 /* 16-bit storage formats of planes and packed weights.  Forward activations and weights are fp16 by default (11-bit
  * significand: parameter gradients then stay within 1e-2 of the fp32 reference, profiles/r02_grad_precision_*.json),
- * gradient planes are bf16 (fp32 exponent range).  tcgen05.mma kind::f16 takes either format per operand. */
+ * gradient planes are bf16 (fp32 exponent range).  One tcgen05.mma (kind::f16) needs both operands in the SAME format
+ * (mixing faults with an illegal instruction on B200), so: forward = fp16 x fp16; dgrad = bf16 gradient x bf16-packed
+ * weights; wgrad = bf16 gradient x fp16 activation, the activation tile being rewritten to bf16 in shared memory by
+ * the kernel (scm_gan_b200/csrc/conv_wgrad.cuh). */
 #define SCMGAN_FMT_BF16 0
 #define SCMGAN_FMT_F16 1
 
@@ -251,6 +254,20 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
 int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
                       long long mask_stride, int B, int R, float scale, const float* scale_dev, float* loss,
                       float* loss_raw, float* dpred, scmgan_stream_t stream);
+
+/* Sequence forms of the two loss kernels.  The decoder and the reward predictor are stateless, so the T decodes /
+ * reward predictions of one iteration (reference main.py:181-197, once per rollout step) run as ONE batch of T*B
+ * samples: x / pred are t-major ([T][B][...]), while the targets and masks stay where they are - step t of sample b is
+ * found at  base + b*bstride + t*tstride  (a [B, T] window of the [B][Hn][...] input tensors).
+ *   bce:  loss_t[t] += mean_b( mask[b,t] * mean_chw BCE(sigmoid(x[t,b]), y[b,t]) )           (loss_t zeroed by caller)
+ *   mse:  loss[0] = scale * (*scale_dev) * sum_t mean_b( mask[b,t] * mean_r (pred-target)^2 ), loss_raw[t] unscaled */
+int scmgan_bce_logits_seq(const float* x, const float* y, long long y_bstride, long long y_tstride, const float* mask,
+                          long long mask_bstride, long long mask_tstride, int T, int B, long long per, float* loss_t,
+                          float* dx, scmgan_stream_t stream);
+int scmgan_masked_mse_seq(const float* pred, const float* target, long long target_bstride, long long target_tstride,
+                          const float* mask, long long mask_bstride, long long mask_tstride, int T, int B, int R,
+                          float scale, const float* scale_dev, float* loss, float* loss_raw, float* dpred,
+                          scmgan_stream_t stream);
 
 /* loss[0] += mean_b( mask[b] * mean_chw BCE(sigmoid(x), y) ); dx (optional) = d loss / d x.
  * Fuses torch.sigmoid + F.binary_cross_entropy + means (reference main.py:188-197, 310-312). */

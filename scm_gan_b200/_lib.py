@@ -116,6 +116,12 @@ SIGNATURES = {
     "scmgan_transition_tail": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_masked_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_longlong, C.c_int, C.c_int,
                                     C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_bce_logits_seq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
+                                        C.c_longlong, C.c_int, C.c_int, C.c_longlong, C.c_void_p, C.c_void_p,
+                                        C.c_void_p]),
+    "scmgan_masked_mse_seq": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p, C.c_longlong,
+                                        C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_wgrad_reduce": (C.c_int, [C.c_int, C.POINTER(WgradReduceJob), C.c_void_p]),
     "scmgan_pack_coords": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "scmgan_gru_conv_sweep_fwd": (C.c_int, [C.POINTER(CsrnSweepDesc), C.c_void_p]),

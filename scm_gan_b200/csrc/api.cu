@@ -355,6 +355,8 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     P.out_f32 = d->out_f32; P.n_valid = d->n_valid; P.sample_out = d->sample_out; P.uniforms = d->uniforms;
     P.rng = d->rng_state;
     SCM_REQUIRE((d->x_fmt | 1) == 1 && (d->w_fmt | 1) == 1 && (d->out_fmt | 1) == 1, "conv3x3: bad format code");
+    SCM_REQUIRE(d->x_fmt == d->w_fmt, "conv3x3: input plane and packed weights must share one 16-bit format "
+                                      "(tcgen05.mma kind::f16 faults on mixed bf16/fp16 operands)");
     SCM_REQUIRE(!d->add || d->out_fmt == SCMGAN_FMT_BF16, "conv3x3: `add` planes are bf16 only");
     P.a_fmt = d->x_fmt; P.b_fmt = d->w_fmt; P.out_fmt = d->out_fmt;
     {
@@ -749,6 +751,8 @@ static int wgrad_dispatch(const scmgan_wgrad_desc* d, scmgan_stream_t stream);
 int scmgan_conv3x3_wgrad(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     SCM_REQUIRE(d != nullptr, "wgrad: null descriptor");
     SCM_REQUIRE((d->dy_fmt | 1) == 1 && (d->x_fmt | 1) == 1, "wgrad: bad format code");
+    SCM_REQUIRE(d->dy_fmt == d->x_fmt || (d->dy_fmt == SCMGAN_FMT_BF16 && d->x_fmt == SCMGAN_FMT_F16),
+                "wgrad: supported formats are dy == x, or a bf16 gradient plane with an fp16 input plane");
     t_dy_fmt = d->dy_fmt; t_x_fmt = d->x_fmt;
     if (d->defer_jobs) {
         SCM_REQUIRE(d->defer_count && d->workspace_cursor && d->defer_cap > 0 && d->workspace,
@@ -971,12 +975,37 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
     return SCM_OK;
 }
 
+int scmgan_masked_mse_seq(const float* pred, const float* target, long long target_bstride, long long target_tstride,
+                          const float* mask, long long mask_bstride, long long mask_tstride, int T, int B, int R,
+                          float scale, const float* scale_dev, float* loss, float* loss_raw, float* dpred,
+                          scmgan_stream_t stream) {
+    SCM_REQUIRE(pred && target && loss && T > 0 && B > 0 && R > 0, "masked_mse: bad arguments");
+    masked_mse_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, target_bstride, target_tstride, mask,
+                                                          mask_bstride, mask_tstride, T, B, R, scale, scale_dev, loss,
+                                                          loss_raw, dpred);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 int scmgan_masked_mse(const float* pred, const float* target, long long target_bstride, const float* mask,
                       long long mask_stride, int B, int R, float scale, const float* scale_dev, float* loss,
                       float* loss_raw, float* dpred, scmgan_stream_t stream) {
-    SCM_REQUIRE(pred && target && loss && B > 0 && R > 0, "masked_mse: bad arguments");
-    masked_mse_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, target_bstride, mask, mask_stride, B, R, scale,
-                                                          scale_dev, loss, loss_raw, dpred);
+    return scmgan_masked_mse_seq(pred, target, target_bstride, 0, mask, mask_stride, 0, 1, B, R, scale, scale_dev, loss,
+                                 loss_raw, dpred, stream);
+}
+
+int scmgan_bce_logits_seq(const float* x, const float* y, long long y_bstride, long long y_tstride, const float* mask,
+                          long long mask_bstride, long long mask_tstride, int T, int B, long long per, float* loss_t,
+                          float* dx, scmgan_stream_t stream) {
+    SCM_REQUIRE(x && y && loss_t && T > 0 && B > 0 && per > 0, "bce_logits: bad arguments");
+    SCM_REQUIRE((long long)T * B <= 65535, "bce_logits: T*B = %lld rows exceed the grid limit", (long long)T * B);
+    const int threads = 256;
+    int bx = int(std::min<long long>((per + threads * 4 - 1) / (threads * 4), std::max(1, 8 * num_sms() / (T * B))));
+    bx = std::max(bx, 1);
+    bce_logits_kernel<<<dim3(bx, T * B), threads, 0, (cudaStream_t)stream>>>(x, y, y_bstride, y_tstride, mask,
+                                                                            mask_bstride, mask_tstride, T, B, per,
+                                                                            loss_t, dx);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -984,14 +1013,7 @@ int scmgan_masked_mse(const float* pred, const float* target, long long target_b
 
 int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
                       float* loss, float* dx, scmgan_stream_t stream) {
-    SCM_REQUIRE(x && y && loss && B > 0 && per > 0, "bce_logits: bad arguments");
-    const int threads = 256;
-    int bx = int(std::min<long long>((per + threads * 4 - 1) / (threads * 4), std::max(1, 8 * num_sms() / B)));
-    bx = std::max(bx, 1);
-    bce_logits_kernel<<<dim3(bx, B), threads, 0, (cudaStream_t)stream>>>(x, y, y_bstride, mask, B, per, loss, dx);
-    SCM_CUDA(cudaGetLastError());
-    ++g_launches;
-    return SCM_OK;
+    return scmgan_bce_logits_seq(x, y, y_bstride, 0, mask, 1, 0, 1, B, per, loss, dx, stream);
 }
 
 int scmgan_reward_head_fwd(const float* y2, int B, int R, int H, int W, float* r, float* map,

@@ -44,6 +44,28 @@ struct WgradParams {
 };
 
 constexpr int kWgradThreads = 192;
+constexpr int kWgradConvThreads = 128;  // warps 2..5: operand-format converters during the main loop, epilogue after it
+
+// tcgen05.mma kind::f16 needs both operands in ONE 16-bit format (measured on B200: a bf16 A with an fp16 B raises an
+// illegal-instruction fault), but the weight gradient multiplies a bf16 gradient plane by an fp16 forward activation.
+// The four epilogue warps, idle during the main loop, therefore rewrite the activation tile of every pipeline stage in
+// place from fp16 to bf16 (same size, elementwise, so the swizzled layout is irrelevant) between the TMA completion and
+// the MMAs.  Dropping three significand bits of X only perturbs dW linearly (2^-9 per element, averaged over ~1e5
+// pixels); the kink-sensitive forward pass keeps its fp16 operands.
+__device__ __forceinline__ uint32_t f16x2_to_bf16x2(uint32_t w) {
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    const float2 f = __half22float2(h);
+    return pack2_bf16(f.x, f.y);
+}
+__device__ __forceinline__ void convert_region_f16_to_bf16(uint8_t* base, int bytes, int tid) {
+    uint4* p = reinterpret_cast<uint4*>(base);
+    const int n = bytes >> 4;
+    for (int i = tid; i < n; i += kWgradConvThreads) {
+        uint4 v = p[i];
+        v.x = f16x2_to_bf16x2(v.x); v.y = f16x2_to_bf16x2(v.y); v.z = f16x2_to_bf16x2(v.z); v.w = f16x2_to_bf16x2(v.w);
+        p[i] = v;
+    }
+}
 
 __global__ void __launch_bounds__(kWgradThreads, 1)
 conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_constant__ CUtensorMap tmap_q,
@@ -63,6 +85,12 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
     uint64_t* empty_bar = bars + 8;
     uint64_t* acc_full = bars + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* conv_bar = bars + 24;  // [8] stage converted (only used when the operand formats differ)
+    // which operand (if any) has to be rewritten to the other's format: the fp16 one
+    const bool conv_p = P.p_fmt != P.q_fmt && P.p_fmt == FMT_F16;
+    const bool conv_q = P.p_fmt != P.q_fmt && P.q_fmt == FMT_F16;
+    const bool convert = conv_p || conv_q;
+    const int mma_fmt = convert ? FMT_BF16 : P.p_fmt;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -79,6 +107,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], kWgradConvThreads);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -120,7 +149,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = make_idesc_ab(128, P.n, P.p_fmt, P.q_fmt, 1, 1);
+            const uint32_t idesc = make_idesc_ab(128, P.n, mma_fmt, mma_fmt, 1, 1);
             const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
             const uint32_t q_sbo = 8u * P.q_aw * 2u;
             const uint32_t q_kstep16 = (16u * P.q_aw * 2u) >> 4;
@@ -132,7 +161,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(convert ? &conv_bar[stage] : &full_bar[stage], phase);
                 tc_fence_after();
                 const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * stage16);
                 const uint64_t b_st = bdesc0 + uint64_t(uint32_t(stage) * stage16);
@@ -152,6 +181,20 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
             if (elect_one()) umma_commit(acc_full);
             __syncwarp();
         } else {
+            if (convert) {  // fp16 operand -> bf16 in place, stage by stage
+                int stage = 0;
+                uint32_t phase = 0;
+                const int ctid = threadIdx.x - 64;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    uint8_t* sp = smem + size_t(stage) * stage_bytes;
+                    if (conv_p) convert_region_f16_to_bf16(sp, p_bytes, ctid);
+                    else convert_region_f16_to_bf16(sp + p_bytes, ntaps * q_tap_bytes, ctid);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&conv_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
             const int q = warp & 3;
             const int m = q * 32 + lane;
             mbar_wait(acc_full, 0);

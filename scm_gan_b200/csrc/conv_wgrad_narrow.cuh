@@ -57,6 +57,11 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     uint64_t* empty_bar = bars + 8;
     uint64_t* acc_full = bars + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* conv_bar = bars + 24;  // [8] fp16 operand of the stage rewritten to bf16 (conv_wgrad.cuh)
+    const bool conv_m = P.m_fmt != P.n_fmt && P.m_fmt == FMT_F16;
+    const bool conv_n = P.m_fmt != P.n_fmt && P.n_fmt == FMT_F16;
+    const bool convert = conv_m || conv_n;
+    const int mma_fmt = convert ? FMT_BF16 : P.m_fmt;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -71,6 +76,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], kWgradConvThreads);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -82,7 +88,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
     if (P.with_ones) {  // tile 9 of every stage: bf16 1.0 (never touched by TMA)
         for (int s = 0; s < num_stages; ++s) {
             uint32_t* ones = reinterpret_cast<uint32_t*>(smem + size_t(s) * stage_bytes + a_bytes + 9 * b_tile_bytes);
-            for (int i = threadIdx.x; i < b_tile_bytes / 4; i += blockDim.x) ones[i] = P.n_fmt == FMT_F16 ? 0x3C003C00u : 0x3F803F80u;
+            for (int i = threadIdx.x; i < b_tile_bytes / 4; i += blockDim.x) ones[i] = mma_fmt == FMT_F16 ? 0x3C003C00u : 0x3F803F80u;
         }
         fence_proxy_async_smem();
     }
@@ -114,7 +120,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         }
     } else if (warp == 1) {
         // ------------------------------ MMA issuer ------------------------------
-        const uint32_t idesc = make_idesc_ab(128, n_tiles * kNarrowCo, P.m_fmt, P.n_fmt, 1, 1);  // both operands MN-major (K = pixels)
+        const uint32_t idesc = make_idesc_ab(128, n_tiles * kNarrowCo, mma_fmt, mma_fmt, 1, 1);  // both operands MN-major (K = pixels)
         const uint64_t adesc0 = make_smem_desc(smem_u32(smem), uint32_t(a_atom_bytes), 1024, kLayoutSw128);
         const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + uint32_t(a_bytes), uint32_t(b_tile_bytes), 256, kLayoutSw32);
         const uint32_t stage16 = uint32_t(stage_bytes) >> 4;
@@ -122,7 +128,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         int stage = 0;
         uint32_t phase = 0;
         for (int i = 0; i < nkb; ++i) {
-            mbar_wait(&full_bar[stage], phase);
+            mbar_wait(convert ? &conv_bar[stage] : &full_bar[stage], phase);
             tc_fence_after();
             const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * stage16);
             const uint64_t b_st = bdesc0 + uint64_t(uint32_t(stage) * stage16);
@@ -141,6 +147,19 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         __syncwarp();
     } else {
         // ------------------------------ epilogue: partials [tap][co][ci] ------------------------------
+        if (convert) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int i = 0; i < nkb; ++i) {
+                mbar_wait(&full_bar[stage], phase);
+                uint8_t* sp = smem + size_t(stage) * stage_bytes;
+                if (conv_m) convert_region_f16_to_bf16(sp, a_bytes, threadIdx.x - 64);
+                else convert_region_f16_to_bf16(sp + a_bytes, 9 * b_tile_bytes, threadIdx.x - 64);  // not the ones tile
+                fence_proxy_async_smem();
+                mbar_arrive(&conv_bar[stage]);
+                if (++stage == num_stages) { stage = 0; phase ^= 1; }
+            }
+        }
         const int q = warp & 3;
         const int m = q * 32 + lane;
         float* wsb = P.ws + (size_t(blockIdx.y) * gridDim.x + blockIdx.x) * (9 * kNarrowCo * 128);

@@ -50,13 +50,16 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
     uint64_t* empty_bar = bars + 8;
     uint64_t* acc_full = bars + 16;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+    uint64_t* conv_bar = bars + 24;  // [8] X tile of the stage rewritten to dY's format (conv_wgrad.cuh)
     uint8_t* s_ones = reinterpret_cast<uint8_t*>(bars + 32);  // 512 B: 16 pixels x 16 channels of bf16 1.0
+    const bool convert = P.p_fmt == FMT_BF16 && P.q_fmt == FMT_F16;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int ky = blockIdx.y;  // this CTA's filter row: taps ky*3 + {0,1,2}
     const bool do_bias = (P.ws_bias != nullptr) && ky == 1;
-    if (do_bias && threadIdx.x < 128) reinterpret_cast<uint32_t*>(s_ones)[threadIdx.x] = 0x3F803F80u;
+    if (do_bias && threadIdx.x < 128)
+        reinterpret_cast<uint32_t*>(s_ones)[threadIdx.x] = P.p_fmt == FMT_F16 ? 0x3C003C00u : 0x3F803F80u;
     if (do_bias) fence_proxy_async_smem();  // generic-proxy writes must be visible to the tensor core (async proxy)
     const int kb_begin = blockIdx.x * P.kb_per_cta;
     const int kb_end = min(P.num_kblocks, kb_begin + P.kb_per_cta);
@@ -68,6 +71,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
         for (int s = 0; s < num_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
+            mbar_init(&conv_bar[s], kWgradConvThreads);
         }
         mbar_init(acc_full, 1);
         fence_barrier_init();
@@ -106,7 +110,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
                 if (++stage == num_stages) { stage = 0; phase ^= 1; }
             }
         } else if (warp == 1) {
-            const uint32_t idesc = make_idesc_ab(128, P.n, P.p_fmt, P.q_fmt, 1, 1);
+            const uint32_t idesc = make_idesc_ab(128, P.n, P.p_fmt, convert ? FMT_BF16 : P.q_fmt, 1, 1);
             const uint64_t q_layout = P.q_aw == 64 ? kLayoutSw128 : (P.q_aw == 32 ? kLayoutSw64 : kLayoutSw32);
             const uint64_t adesc0 = make_smem_desc(smem_u32(smem), p_atom_bytes, 1024, kLayoutSw128);
             const uint64_t bdesc0 = make_smem_desc(smem_u32(smem) + p_bytes, q_atom_bytes, 8u * q_row_bytes, q_layout);
@@ -114,13 +118,13 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
             const uint32_t q_tile16 = uint32_t(q_tile_bytes) >> 4;
             const uint32_t q_row16 = uint32_t(q_row_bytes) >> 4;
             const int ksteps = P.W / 16;
-            const uint32_t idesc_b = make_idesc_ab(128, 16, P.p_fmt, FMT_BF16, 1, 1);  // ones tile is bf16 1.0
+            const uint32_t idesc_b = make_idesc_ab(128, 16, P.p_fmt, P.p_fmt, 1, 1);  // ones tile in dY's format
             const uint64_t ones_desc = make_smem_desc(smem_u32(s_ones), 512, 256, kLayoutSw32);
             const uint32_t tmem_b = tmem_base + uint32_t(3 * P.n);
             int stage = 0;
             uint32_t phase = 0;
             for (int i = 0; i < nkb; ++i) {
-                mbar_wait(&full_bar[stage], phase);
+                mbar_wait(convert ? &conv_bar[stage] : &full_bar[stage], phase);
                 tc_fence_after();
                 const uint64_t a_st = adesc0 + uint64_t(uint32_t(stage) * stage16);
                 const uint64_t b_st = bdesc0 + uint64_t(uint32_t(stage) * stage16);
@@ -149,6 +153,18 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
             if (elect_one()) umma_commit(acc_full);
             __syncwarp();
         } else {
+            if (convert) {
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int i = 0; i < nkb; ++i) {
+                    mbar_wait(&full_bar[stage], phase);
+                    convert_region_f16_to_bf16(smem + size_t(stage) * stage_bytes + p_bytes, P.BH * q_tile_bytes,
+                                               threadIdx.x - 64);
+                    fence_proxy_async_smem();
+                    mbar_arrive(&conv_bar[stage]);
+                    if (++stage == num_stages) { stage = 0; phase ^= 1; }
+                }
+            }
             const int q = warp & 3;
             const int m = q * 32 + lane;
             mbar_wait(acc_full, 0);

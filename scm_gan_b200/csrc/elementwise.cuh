@@ -431,15 +431,21 @@ __global__ void action_wgrad_kernel(const float* __restrict__ S, const float* __
 //   dx = (sigmoid(x) - y) * mask[b] / (B*C*H*W)
 // The gradient is produced in the same pass (forward+backward fusion); autograd scales it by grad_output.
 // ----------------------------------------------------------------------------------------------
+// Sequence form: x holds the logits of T rollout steps, t-major ([T][B][per]); step t's target rows are
+// y + b*y_bstride + t*y_tstride (a [B, T] window of the [B][Hn][C][H][W] frame tensor) and its mask entries
+// mask + b*m_bstride + t*m_tstride; loss_t[t] += the step's term (T = 1: the single-step op).  The decoder has no
+// state, so the T decodes of one iteration (main.py:188-197) run as ONE batch of T*B samples.
 __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __restrict__ y, long long y_bstride,
-                                  const float* __restrict__ mask, int B, long long per, float* __restrict__ loss,
+                                  long long y_tstride, const float* __restrict__ mask, long long m_bstride,
+                                  long long m_tstride, int T, int B, long long per, float* __restrict__ loss_t,
                                   float* __restrict__ dx) {
     __shared__ float red[33];
-    const int b = blockIdx.y;
-    const float m = mask ? __ldg(mask + b) : 1.f;
+    const int row = blockIdx.y;  // t * B + b
+    const int t = row / B, b = row - t * B;
+    const float m = mask ? __ldg(mask + (long long)b * m_bstride + (long long)t * m_tstride) : 1.f;
     const float inv = 1.f / (float(B) * float(per));
-    const float* xb = x + (long long)b * per;
-    const float* yb = y + (long long)b * y_bstride;
+    const float* xb = x + (long long)row * per;
+    const float* yb = y + (long long)b * y_bstride + (long long)t * y_tstride;
     float acc = 0.f;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per;
          i += (long long)gridDim.x * blockDim.x) {
@@ -447,10 +453,10 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
         const float p = 1.f / (1.f + __expf(-xv));
         const float lp = fmaxf(__logf(p), -100.f), lq = fmaxf(__logf(1.f - p), -100.f);
         acc -= yv * lp + (1.f - yv) * lq;
-        if (dx) dx[(long long)b * per + i] = (p - yv) * m * inv;
+        if (dx) dx[(long long)row * per + i] = (p - yv) * m * inv;
     }
     acc = block_sum(acc, red);
-    if (threadIdx.x == 0) atomicAdd(loss, acc * m * inv);
+    if (threadIdx.x == 0) atomicAdd(loss_t + t, acc * m * inv);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -460,26 +466,33 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
 // that one captured CUDA graph serves every iteration; loss_raw (optional) receives the unscaled masked mean, the
 // value the reference logs as "Rd Loss" (main.py:184).
 // ----------------------------------------------------------------------------------------------
+// Sequence form like bce_logits_kernel: pred is [T][B][R] (t-major), target / mask are [B, T] windows addressed by
+// (b, t) strides; loss = scale * theta * sum_t mean_t, loss_raw[t] = the unscaled masked mean of step t.  One block
+// walks the T steps in order (deterministic sum; T*B*R is a few hundred elements).
 __global__ void masked_mse_kernel(const float* __restrict__ pred, const float* __restrict__ target,
-                                  long long t_bstride, const float* __restrict__ mask, long long m_stride, int B, int R,
-                                  float scale, const float* __restrict__ scale_dev, float* __restrict__ loss,
+                                  long long t_bstride, long long t_tstride, const float* __restrict__ mask,
+                                  long long m_bstride, long long m_tstride, int T, int B, int R, float scale,
+                                  const float* __restrict__ scale_dev, float* __restrict__ loss,
                                   float* __restrict__ loss_raw, float* __restrict__ dpred) {
     __shared__ float red[33];
     const float k0 = 1.f / (float(B) * float(R));
     const float k = scale * (scale_dev ? __ldg(scale_dev) : 1.f) * k0;
-    float acc = 0.f;
-    for (int i = threadIdx.x; i < B * R; i += blockDim.x) {
-        const int b = i / R, r = i - b * R;
-        const float m = mask ? __ldg(mask + (long long)b * m_stride) : 1.f;
-        const float d = pred[i] - __ldg(target + (long long)b * t_bstride + r);
-        acc = fmaf(m * d, d, acc);
-        if (dpred) dpred[i] = 2.f * k * m * d;
+    float total = 0.f;
+    for (int t = 0; t < T; ++t) {
+        float acc = 0.f;
+        for (int i = threadIdx.x; i < B * R; i += blockDim.x) {
+            const int b = i / R, r = i - b * R;
+            const float m = mask ? __ldg(mask + (long long)b * m_bstride + (long long)t * m_tstride) : 1.f;
+            const float d = pred[(long long)t * B * R + i] -
+                            __ldg(target + (long long)b * t_bstride + (long long)t * t_tstride + r);
+            acc = fmaf(m * d, d, acc);
+            if (dpred) dpred[(long long)t * B * R + i] = 2.f * k * m * d;
+        }
+        acc = block_sum(acc, red);
+        total += acc;
+        if (threadIdx.x == 0 && loss_raw) loss_raw[t] = acc * k0;
     }
-    acc = block_sum(acc, red);
-    if (threadIdx.x == 0) {
-        *loss = acc * k;
-        if (loss_raw) *loss_raw = acc * k0;
-    }
+    if (threadIdx.x == 0) *loss = total * k;
 }
 
 // ----------------------------------------------------------------------------------------------

@@ -79,8 +79,10 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     #   d act1 = [d pre2 | d pre6] x [Wd2 ; Wd6(skip half)]     (K = 128 + 64, the 16 latent gradients zero-padded)
     LS = 64  # channel slot of d pre6 inside the [d pre2 | d pre6] plane
     assert Lp <= LS
-    wd = [K.packed_weight(Lp, HID, dev), K.packed_weight(HID, HID + LS, dev), K.packed_weight(HID, 2 * HID, dev),
-          K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, Lp, dev)]
+    G16 = K.GRAD_DTYPE  # dgrad multiplies bf16 gradient planes: its weight operands are packed in the same format
+    wd = [K.packed_weight(Lp, HID, dev, G16), K.packed_weight(HID, HID + LS, dev, G16),
+          K.packed_weight(HID, 2 * HID, dev, G16), K.packed_weight(HID, HID, dev, G16),
+          K.packed_weight(HID, HID, dev, G16), K.packed_weight(HID, Lp, dev, G16)]
     jobs = [_conv2d_fwd_job(wbar[0], wf[0], sigma[0:1], k_valid=L)]
     jobs += [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(1, 5)]
     jobs += [_conv2d_fwd_job(w6, wf[5])]
@@ -210,7 +212,8 @@ def encoder_forward(x, wbar, bias, sigma, w4, b4):
     Lp = _r16(L)
     wf = [K.packed_weight(HID, Cp, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
           K.packed_weight(Lp, HID, dev)]
-    wd = [K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, Lp, dev)]
+    G16 = K.GRAD_DTYPE
+    wd = [K.packed_weight(HID, HID, dev, G16), K.packed_weight(HID, HID, dev, G16), K.packed_weight(HID, Lp, dev, G16)]
     jobs = [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(3)] + [_conv2d_fwd_job(w4, wf[3])]
     jobs += [_conv2d_dgrad_job(wbar[1], wd[0], sigma[1:2]), _conv2d_dgrad_job(wbar[2], wd[1], sigma[2:3]),
              _conv2d_dgrad_job(w4, wd[2], None, co_valid=L)]
@@ -292,8 +295,8 @@ def decoder_forward(z, w1, b1, w2, b2):
     # unwritten upper channels only ever reach wgrad outputs beyond co_valid / ci_valid, which are discarded
     wf1 = K.packed_weight(hid, Lp, dev)
     wf2 = K.packed_weight(cop, hid, dev)
-    wd1 = K.packed_weight(Lp, hid, dev)
-    wd2 = K.packed_weight(hid, cop, dev)
+    wd1 = K.packed_weight(Lp, hid, dev, K.GRAD_DTYPE)
+    wd2 = K.packed_weight(hid, cop, dev, K.GRAD_DTYPE)
     K.pack_weights([_convT_fwd_job(w1, wf1), _convT_fwd_job(w2, wf2), _convT_dgrad_job(w1, wd1),
                     _convT_dgrad_job(w2, wd2)])
     zin = K.fwd_plane(B, H, W, Lp, dev)
@@ -368,8 +371,8 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     # hidden plane 128 channels wide for wgrad, only RHID computed (see decoder_forward)
     wf1 = K.packed_weight(RHID, Lp, dev)
     wf2 = K.packed_weight(16, RHID, dev)
-    wd1 = K.packed_weight(Lp, RHID, dev)
-    wd2 = K.packed_weight(RHID, 16, dev)
+    wd1 = K.packed_weight(Lp, RHID, dev, K.GRAD_DTYPE)
+    wd2 = K.packed_weight(RHID, 16, dev, K.GRAD_DTYPE)
     K.pack_weights([_conv2d_fwd_job(w1, wf1), _conv2d_fwd_job(w2, wf2),
                     _conv2d_dgrad_job(w1, wd1), _conv2d_dgrad_job(w2, wd2)])
     zin = K.fwd_plane(B, H, W, Lp, dev)
@@ -435,7 +438,7 @@ def coordconv_forward(x, w, b):
     assert cin == Cc + 2 and Cc % 2 == 0, "CoordConv2d expects in_channels + 2 (even number of data channels)"
     Cp, Np = _r16(cin), _r16(co)
     wf = K.packed_weight(Np, Cp, dev)
-    wd = K.packed_weight(_r16(Cc), HID if Np <= HID else Np, dev)  # dgrad reads the 128-wide gradient plane
+    wd = K.packed_weight(_r16(Cc), HID if Np <= HID else Np, dev, K.GRAD_DTYPE)  # dgrad reads the 128-wide gradient plane
     K.pack_weights([_conv2d_fwd_job(w, wf), _conv2d_dgrad_job(w, wd, None, 0, Cc)])
     xin = K.fwd_plane(B, H, W, Cp, dev)
     K.pack_nchw(x, xin, c_pad=Cp, wrap=False)

@@ -299,6 +299,27 @@ def bce_logits(x, y, mask, loss, dx=None):
                                       L.ptr(dx), _stream()), "scmgan_bce_logits")
 
 
+def bce_logits_seq(x, y_bt, mask_bt, loss_t, dx=None):
+    """x [T*B, ...] dense fp32 logits (t-major); y_bt [B, T, ...] (a view: any batch / time stride, dense per frame);
+    mask_bt [B, T] (any strides); loss_t [T] zero-initialised."""
+    B, T = y_bt.shape[0], y_bt.shape[1]
+    per = x.numel() // (T * B)
+    assert x.is_contiguous() and x.shape[0] == T * B and y_bt[0, 0].is_contiguous() and y_bt[0, 0].numel() == per
+    L.check(L.lib().scmgan_bce_logits_seq(x.data_ptr(), y_bt.data_ptr(), y_bt.stride(0), y_bt.stride(1),
+                                          L.ptr(mask_bt), mask_bt.stride(0), mask_bt.stride(1), T, B, per,
+                                          loss_t.data_ptr(), L.ptr(dx), _stream()), "scmgan_bce_logits_seq")
+
+
+def masked_mse_seq(pred, target_bt, mask_bt, scale, loss, loss_raw, dpred=None, scale_dev=None):
+    """pred [T*B, R] contiguous (t-major); target_bt [B, T, R], mask_bt [B, T] views; loss [1], loss_raw [T]."""
+    B, T, R = target_bt.shape
+    assert pred.is_contiguous() and pred.shape == (T * B, R) and (R == 1 or target_bt.stride(2) == 1)
+    L.check(L.lib().scmgan_masked_mse_seq(pred.data_ptr(), target_bt.data_ptr(), target_bt.stride(0),
+                                          target_bt.stride(1), L.ptr(mask_bt), mask_bt.stride(0), mask_bt.stride(1),
+                                          T, B, R, float(scale), L.ptr(scale_dev), loss.data_ptr(), L.ptr(loss_raw),
+                                          L.ptr(dpred), _stream()), "scmgan_masked_mse_seq")
+
+
 def masked_mse(pred, target, mask, scale, loss, dpred=None, scale_dev=None, loss_raw=None):
     """pred [B,R] contiguous; target [B,R] with unit inner stride; mask [B] (any stride) or None.
     scale_dev: optional device scalar multiplied into the loss (theta); loss_raw: optional [1] unscaled mean."""

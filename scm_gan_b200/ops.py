@@ -279,6 +279,66 @@ bce_logits.register_autograd(_bce_backward, setup_context=_bce_setup)
 
 
 # ------------------------------------------------------------------------------------------------------------
+# Sequence forms: the decoder / reward losses of all T rollout steps in one launch (see include/scmgan.h)
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::bce_logits_seq", mutates_args=())
+def bce_logits_seq(logits: Tensor, target_bt: Tensor, mask_bt: Tensor) -> List[Tensor]:
+    """logits [T*B, C, H, W] (t-major); target_bt [B, T, C, H, W] and mask_bt [B, T] are views of the batch tensors.
+    -> [per-step loss terms [T], d sum(terms) / d logits]."""
+    _require_cuda(logits, target_bt, mask_bt)
+    logits = logits.contiguous().float()
+    if not (target_bt.dtype == torch.float32 and target_bt[0, 0].is_contiguous()):
+        target_bt = target_bt.contiguous().float()
+    if mask_bt.dtype != torch.float32:
+        mask_bt = mask_bt.float()
+    T = target_bt.shape[1]
+    terms = torch.zeros(T, dtype=torch.float32, device=logits.device)
+    dx = torch.empty_like(logits)
+    K.bce_logits_seq(logits, target_bt, mask_bt, terms, dx)
+    return [terms, dx]
+
+
+def _bce_seq_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    ctx.save_for_backward(output[1])
+
+
+def _bce_seq_backward(ctx, grads):
+    (dx,) = ctx.saved_tensors
+    g = grads[0]
+    if g is None:
+        return None, None, None
+    T = g.shape[0]
+    return (dx.view(T, -1) * g.view(T, 1)).view_as(dx), None, None
+
+
+bce_logits_seq.register_autograd(_bce_seq_backward, setup_context=_bce_seq_setup)
+
+
+@torch.library.custom_op("scmgan::masked_mse_seq", mutates_args=())
+def masked_mse_seq(pred: Tensor, target_bt: Tensor, mask_bt: Tensor, scale: float,
+                   scale_dev: Optional[Tensor] = None) -> List[Tensor]:
+    """pred [T*B, R] (t-major); target_bt [B, T, R], mask_bt [B, T] views.
+    -> [scale * scale_dev * sum_t masked mean_t (0-dim), d / d pred, unscaled per-step means [T]]."""
+    _require_cuda(pred, target_bt, mask_bt)
+    pred = pred.contiguous().float()
+    if not (target_bt.dtype == torch.float32 and (target_bt.shape[2] == 1 or target_bt.stride(2) == 1)):
+        target_bt = target_bt.contiguous().float()
+    if mask_bt.dtype != torch.float32:
+        mask_bt = mask_bt.float()
+    T = target_bt.shape[1]
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    raw = torch.empty(T, dtype=torch.float32, device=pred.device)
+    dpred = torch.empty_like(pred)
+    K.masked_mse_seq(pred, target_bt, mask_bt, scale, loss, raw, dpred,
+                     scale_dev=None if scale_dev is None else scale_dev.reshape(1).float())
+    return [loss.view(()), dpred, raw]
+
+
+masked_mse_seq.register_autograd(lambda ctx, grads: _mse_backward(ctx, grads), setup_context=lambda ctx, inputs, output: _mse_setup(ctx, inputs, output))
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Masked reward MSE (reference main.py:182-186), one kernel for value and gradient
 # ------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("scmgan::masked_mse", mutates_args=())
@@ -292,11 +352,12 @@ def masked_mse(pred: Tensor, target: Tensor, mask: Tensor, scale: float,
         target = target.contiguous().float()
     if mask.dtype != torch.float32:
         mask = mask.float()
-    out = torch.empty(2, dtype=torch.float32, device=pred.device)
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    raw = torch.empty(1, dtype=torch.float32, device=pred.device)
     dpred = torch.empty_like(pred)
-    K.masked_mse(pred, target, mask, scale, out[0:1], dpred,
-                 scale_dev=None if scale_dev is None else scale_dev.reshape(1).float(), loss_raw=out[1:2])
-    return [out[0], dpred, out[1]]
+    K.masked_mse(pred, target, mask, scale, loss, dpred,
+                 scale_dev=None if scale_dev is None else scale_dev.reshape(1).float(), loss_raw=raw)
+    return [loss.view(()), dpred, raw.view(())]
 
 
 def _mse_setup(ctx, inputs, output):

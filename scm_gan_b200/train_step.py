@@ -19,6 +19,9 @@ import torch
 _DROPIN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "dropin")
 
 CF_REGULARIZATION_LAMBDA = 0.01  # reference main.py:55
+# SCMGAN_SEQUENTIAL_HEADS=1: evaluate reward predictor / decoder once per rollout step like main.py's loop instead of
+# once per iteration on the batch of all steps (A/B measurements; the results are the same)
+SEQUENTIAL_HEADS = os.environ.get("SCMGAN_SEQUENTIAL_HEADS", "0") == "1"
 CLIP_VALUE = 0.1                 # reference main.py:288-290
 
 
@@ -78,30 +81,51 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     z_orig = z.clone()
     # active_mask_t = prod_{s<=t} (1 - done_s)   (main.py:178)
     masks = torch.cumprod(1.0 - dones[:, 1:], dim=1)
-    terms = []  # every loss term (0-dim device tensors); summed by ONE reduction at the end instead of an add per term
+    terms = []  # loss terms (0-dim or 1-dim device tensors); summed by ONE reduction at the end instead of an add per term
     lo_loss = torch.zeros((), dtype=torch.float32, device=states.device) if latent_overshooting else None
     lo_z = {}
-    for t in range(1, Hn - 1):
-        mask = masks[:, t - 1]
-        expected = rew(z)
-        rd = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, reward_coef, theta)
-        terms.append(rd[0])
-        rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
-        if truncate_bptt and t > 1:
-            z = z.detach()
-        terms.append(rec)
+    T = Hn - 2
+    if T > 0 and not latent_overshooting and not SEQUENTIAL_HEADS:
+        # The reward predictor and the decoder are stateless (no spectral norm, no sampling) and nothing downstream of
+        # them feeds the rollout, so the T per-step calls of main.py:181-197 are evaluated as ONE batch of T*B
+        # latents after the rollout: same arithmetic per sample, 1/T of the launches, kernels large enough to be
+        # bandwidth- instead of latency-bound.  The Transition calls keep the reference's order (its spectral-norm
+        # state and random stream advance per call).
+        zs = []
+        for t in range(1, Hn - 1):
+            zs.append(z)
+            z = step(z.detach() if (truncate_bptt and t > 1) else z, onehots[t])   # main.py:192-193, 206-207
+        zcat = torch.cat(zs, dim=0)                                # [T*B, L, H, W], t-major
+        mask_bt = masks[:, :T]
+        rd = torch.ops.scmgan.masked_mse_seq(rew(zcat), rewards[:, 1:Hn - 1], mask_bt, reward_coef, theta)
+        rec = torch.ops.scmgan.bce_logits_seq(dec(zcat), states[:, 1:Hn - 1], mask_bt)[0]
+        terms += [rd[0], rec]
         if collect is not None:
-            collect[f"Rd Loss t={t}"] = rd[2]
-            collect[f"Reconstruction t={t}"] = rec
-        z = step(z, onehots[t])
+            for t in range(1, Hn - 1):
+                collect[f"Rd Loss t={t}"] = rd[2][t - 1]
+                collect[f"Reconstruction t={t}"] = rec[t - 1]
+    else:
+        for t in range(1, Hn - 1):
+            mask = masks[:, t - 1]
+            expected = rew(z)
+            rd = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, reward_coef, theta)
+            terms.append(rd[0])
+            rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
+            if truncate_bptt and t > 1:
+                z = z.detach()
+            terms.append(rec)
+            if collect is not None:
+                collect[f"Rd Loss t={t}"] = rd[2]
+                collect[f"Reconstruction t={t}"] = rec
+            z = step(z, onehots[t])
 
-        if latent_overshooting:  # Hafner et al., reference main.py:217-230
-            lo_z[t] = enc(states[:, t - 1:t + 2])
-            for t_left in range(1, t):
-                lo_z[t_left] = step(lo_z[t_left], onehots[t - 1])
-            for t_a in range(2, t - 1):
-                lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
-                lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
+            if latent_overshooting:  # Hafner et al., reference main.py:217-230
+                lo_z[t] = enc(states[:, t - 1:t + 2])
+                for t_left in range(1, t):
+                    lo_z[t_left] = step(lo_z[t_left], onehots[t - 1])
+                for t_a in range(2, t - 1):
+                    lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
+                    lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
     mask = masks[:, Hn - 3] if Hn > 2 else torch.ones(B, device=states.device)
     if latent_overshooting:  # main.py:232-234
         terms.append(theta * lo_loss)
@@ -137,7 +161,7 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
             collect["CF Control Bias Loss"] = cf
     if not terms:  # horizon 2: no rollout step (reference main.py:162 loop is empty)
         return torch.zeros((), dtype=torch.float32, device=states.device, requires_grad=True), z
-    loss = torch.stack(terms).sum()
+    loss = torch.cat([t.reshape(-1) for t in terms]).sum()
     return loss, z
 
 

@@ -179,13 +179,13 @@ def test_conv_sample_bias_and_f32_head(dt):
 @pytest.mark.parametrize("dt", FWD_DTYPES)
 def test_conv_dgrad_epilogue(dt):
     """dgrad = conv with flipped/transposed weights; epilogue adds a residual plane and gates with lrelu'.
-    The gradient planes are bf16 whatever the forward format: with dt = fp16 the MMA mixes a bf16 A operand with an
-    fp16 B operand, and the gate is read from an fp16 plane."""
+    The gradient planes and the dgrad weight operand are bf16 whatever the forward format (one MMA cannot mix formats);
+    the gate is read from a forward plane in `dt`."""
     _setup()
     from scm_gan_b200 import kernels as K
     torch.manual_seed(4)
     B, H, W, Ci, Co = 2, 15, 19, 128, 128
-    w = rnd(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5), dt)
+    w = bf(torch.randn(Co, Ci, 3, 3, device=DEV) / (3.0 * Ci ** 0.5))
     dy = bf(torch.randn(B, Co, H, W, device=DEV))
     resid = bf(torch.randn(B, Ci, H, W, device=DEV))
     actv = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
@@ -193,7 +193,7 @@ def test_conv_dgrad_epilogue(dt):
         dyp = make_plane(dy, Co, 0, wrap)
         rp = make_plane(resid, Ci, 0, wrap)
         ap = make_plane(actv, Ci, 0, wrap, dt)
-        wd = pack_conv_weight(w, Ci, Co, dgrad=True, dtype=dt)
+        wd = pack_conv_weight(w, Ci, Co, dgrad=True)
         out = K.new_plane(B, H, W, Ci, DEV)
         K.conv3x3(dyp, wd, B, H, W, cin=Co, out=out, wrap=wrap, add=rp, gate=ap, dgrad=True)
         # reference: autograd of the forward conv
@@ -227,7 +227,8 @@ WGRAD_CASES = [
 @pytest.mark.parametrize("dt", FWD_DTYPES)
 @pytest.mark.parametrize("case", WGRAD_CASES)
 def test_wgrad(case, dt):
-    """dY is a bf16 gradient plane, X a forward plane in `dt` (mixed-format MMA when dt = fp16)."""
+    """dY is a bf16 gradient plane, X a forward plane in `dt`; with dt = fp16 the kernel rewrites the X tiles to bf16 in
+    shared memory (the reference below therefore sees X rounded to fp16 and then to bf16)."""
     _setup()
     from scm_gan_b200 import kernels as K
     B, H, W, Ci, Co, wrap = case
@@ -235,6 +236,7 @@ def test_wgrad(case, dt):
     x = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
     dy = bf(torch.randn(B, Co, H, W, device=DEV))
     xp = make_plane(x, Ci, 0, wrap, dt)
+    x = bf(x)
     dyp = make_plane(dy, Co, 0, wrap)  # halo deliberately non-zero in wrap mode: must be ignored
     g = torch.zeros(Co, Ci, 3, 3, device=DEV)
     db = torch.zeros(Co, device=DEV)
