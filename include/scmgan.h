@@ -115,6 +115,9 @@ typedef struct {
     int bias_n; /* number of valid entries of `bias` (channels beyond it get 0); 0 = n.  Lets a layer with 3 or 12
                    real output channels pass its own bias vector although n is padded to 16. */
     int x_fmt, w_fmt, out_fmt; /* SCMGAN_FMT_* of the input plane, the packed weights and the output plane */
+    const float* sample_scale; /* [B] or NULL: y = acc*scale*sample_scale[b] + ...  Samples of several spectral-norm calls
+                                  (different sigma: the main rollout step and the counterfactual rollouts of reference
+                                  main.py:242-283) then share one GEMM with weights packed for the first call's sigma. */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
@@ -220,8 +223,15 @@ typedef struct {
     int rows, cols;
 } scmgan_sn_layer;
 int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers_host, scmgan_stream_t stream);
+/* `iters` successive power iterations in one launch; iteration i of a layer writes its sigma to sigma[i*sigma_stride].
+ * The iteration only reads the weights, which are constant between optimiser steps, so the 5T+3 per-call iterations of
+ * one training iteration (one per SpectralNorm.forward, spectral_normalization.py:66-68) can be run ahead of the
+ * rollout: u, v end in the same state and call i uses the sigma the reference would have computed in it. */
+int scmgan_spectral_norm_fwd_n(int count, const scmgan_sn_layer* layers_host, int iters, int sigma_stride,
+                               scmgan_stream_t stream);
 
-/* dWbar = G/sigma - (<G,Wbar>/sigma^2) u v^T  (autograd of `w / sigma.expand_as(w)`, sigma = u.(W v)).
+/* dWbar = G/sigma - (<G,Wbar>/sigma^2) u v^T  (autograd of `w / sigma.expand_as(w)`, sigma = u.(W v)); u, v as held by
+ * the module at backward time (the reference's autograd graph dereferences the Parameters then).
  * accumulate != 0: out += dWbar (what autograd's AccumulateGrad does for a weight shared by the unrolled steps of
  * main.py:162-215), else out = dWbar. */
 typedef struct {
@@ -234,6 +244,9 @@ typedef struct {
     float* out;
     int rows, cols;
     int accumulate;
+    const float* sigma2; /* optional.  g is the gradient w.r.t. Wbar/sigma accumulated over samples whose call used
+                            sigma2 (sample_scale of scmgan_conv_desc): dWbar = g/sigma - (<g,Wbar>/(sigma*sigma2)) u v^T.
+                            NULL = sigma (the plain formula above). */
 } scmgan_sn_bwd_layer;
 int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers_host, scmgan_stream_t stream);
 

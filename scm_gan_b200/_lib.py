@@ -33,7 +33,8 @@ class ConvDesc(C.Structure):
                 ("gate", C.c_void_p), ("gate_cs", C.c_int), ("gate_c_off", C.c_int),
                 ("out_f32", C.c_void_p), ("n_valid", C.c_int),
                 ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p),
-                ("bias_n", C.c_int), ("x_fmt", C.c_int), ("w_fmt", C.c_int), ("out_fmt", C.c_int)]
+                ("bias_n", C.c_int), ("x_fmt", C.c_int), ("w_fmt", C.c_int), ("out_fmt", C.c_int),
+                ("sample_scale", C.c_void_p)]
 
 
 class WgradReduceJob(C.Structure):
@@ -62,7 +63,7 @@ class SnLayer(C.Structure):
 class SnBwdLayer(C.Structure):
     _fields_ = [("g", C.c_void_p), ("wbar", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p),
                 ("sigma", C.c_void_p), ("dot", C.c_void_p), ("out", C.c_void_p),
-                ("rows", C.c_int), ("cols", C.c_int), ("accumulate", C.c_int)]
+                ("rows", C.c_int), ("cols", C.c_int), ("accumulate", C.c_int), ("sigma2", C.c_void_p)]
 
 
 class CsrnSweepDesc(C.Structure):
@@ -94,6 +95,7 @@ SIGNATURES = {
     "scmgan_plane_colsum": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_spectral_norm_fwd": (C.c_int, [C.c_int, C.POINTER(SnLayer), C.c_void_p]),
+    "scmgan_spectral_norm_fwd_n": (C.c_int, [C.c_int, C.POINTER(SnLayer), C.c_int, C.c_int, C.c_void_p]),
     "scmgan_spectral_norm_bwd": (C.c_int, [C.c_int, C.POINTER(SnBwdLayer), C.c_void_p]),
     "scmgan_action_bias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_void_p, C.c_void_p]),

@@ -348,6 +348,7 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
     P.a = reinterpret_cast<const __nv_bfloat16*>(d->x); P.a_cs = d->x_cs;
     P.bias_n = d->bias_n > 0 ? std::min(d->bias_n, d->n) : d->n;
     P.scale = d->scale; P.bias = d->bias; P.sample_bias = d->sample_bias; P.act = d->act; P.slope = d->slope;
+    P.sample_scale = d->sample_scale;
     P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
     P.wrap = d->wrap;
     P.add = reinterpret_cast<const __nv_bfloat16*>(d->add); P.add_cs = d->add_cs; P.add_c_off = d->add_c_off;
@@ -888,7 +889,13 @@ int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int 
 }
 
 int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_stream_t stream) {
+    return scmgan_spectral_norm_fwd_n(count, layers, 1, 0, stream);
+}
+
+int scmgan_spectral_norm_fwd_n(int count, const scmgan_sn_layer* layers, int iters, int sigma_stride,
+                               scmgan_stream_t stream) {
     SCM_REQUIRE(count > 0 && count <= kMaxSnLayers && layers, "spectral_norm_fwd: bad layer count %d", count);
+    SCM_REQUIRE(iters >= 1 && (iters == 1 || sigma_stride > 0), "spectral_norm_fwd: bad iteration count / sigma stride");
     SnLayers L;
     memset(&L, 0, sizeof(L));
     L.count = count;
@@ -921,7 +928,8 @@ int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_st
             const int smem = int(sizeof(float)) * (Gm.rows_max * (2 + kSnCluster) + Gm.cpc_max * (1 + gmax) +
                                                    kSnCluster + 33);
             if (smem <= 48 * 1024) {
-                sn_power_iter_cluster_kernel<<<count * kSnCluster, 1024, smem, (cudaStream_t)stream>>>(L, Gm);
+                sn_power_iter_cluster_kernel<<<count * kSnCluster, 1024, smem, (cudaStream_t)stream>>>(L, Gm, iters,
+                                                                                                      sigma_stride);
                 SCM_CUDA(cudaGetLastError());
                 ++g_launches;
                 return SCM_OK;
@@ -929,9 +937,13 @@ int scmgan_spectral_norm_fwd(int count, const scmgan_sn_layer* layers, scmgan_st
         }
     }
     SCM_REQUIRE(max_smem <= 48 * 1024, "spectral_norm_fwd: layer too large");
-    sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(L);
-    SCM_CUDA(cudaGetLastError());
-    ++g_launches;
+    for (int it = 0; it < iters; ++it) {  // single-CTA fallback: one launch per iteration
+        SnLayers Li = L;
+        for (int i = 0; i < count; ++i) Li.layer[i].sigma = L.layer[i].sigma + (long long)it * sigma_stride;
+        sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(Li);
+        SCM_CUDA(cudaGetLastError());
+        ++g_launches;
+    }
     return SCM_OK;
 }
 
@@ -943,7 +955,7 @@ int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmga
     for (int i = 0; i < count; ++i) {
         const scmgan_sn_bwd_layer& s = layers[i];
         SCM_REQUIRE(s.g && s.wbar && s.u && s.v && s.sigma && s.dot && s.out, "spectral_norm_bwd: bad layer %d", i);
-        L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols, s.accumulate};
+        L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols, s.accumulate, s.sigma2};
     }
     sn_bwd_dot_kernel<<<dim3(96, count), 256, 0, (cudaStream_t)stream>>>(L);
     SCM_CUDA(cudaGetLastError());

@@ -40,6 +40,8 @@ struct IgemmParams {
     const float* bias;         // [bias_n] or nullptr
     int bias_n;                // valid entries of bias (channels >= bias_n get 0)
     const float* sample_bias;  // [B][n] per-sample bias (folded action channels) or nullptr
+    const float* sample_scale; // [B] per-sample factor on the accumulator (on top of `scale`) or nullptr: lets samples
+                               // that belong to different spectral-norm calls (different sigma) share one GEMM
     int act;                   // ACT_*
     float slope;               // LeakyReLU negative slope
     // bf16 plane output (nullptr = none)
@@ -242,9 +244,10 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
                     for (int i = 0; i < 16; ++i) v[i] = float(i);
                 }
                 if (!valid || (P.debug & 1)) continue;
+                const float rs = P.sample_scale ? P.scale * __ldg(P.sample_scale + b) : P.scale;
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
-                    float x = v[i] * P.scale;
+                    float x = v[i] * rs;
                     if (P.bias && n0 + i < P.bias_n) x += __ldg(P.bias + n0 + i);
                     if (P.sample_bias) x += __ldg(P.sample_bias + size_t(b) * P.n + n0 + i);
                     v[i] = x;

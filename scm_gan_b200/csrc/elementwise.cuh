@@ -211,8 +211,12 @@ struct SnClusterGeom {
     int cpc_max, rows_max;
 };
 
+// `iters` successive power iterations in ONE launch (sigma of iteration i goes to sigma[i * sigma_stride]): the power
+// iteration depends only on the weights, which are constant within a training iteration, so all the per-call
+// iterations of one rollout (reference: one per SpectralNorm forward call, 5T+3 per iteration) can be run ahead.
 __global__ void __cluster_dims__(kSnCluster, 1, 1) __launch_bounds__(1024, 1)
-sn_power_iter_cluster_kernel(const __grid_constant__ SnLayers L, const __grid_constant__ SnClusterGeom Gm) {
+sn_power_iter_cluster_kernel(const __grid_constant__ SnLayers L, const __grid_constant__ SnClusterGeom Gm, int iters,
+                             int sigma_stride) {
     extern __shared__ float sn_smem[];
     const int li = blockIdx.x / kSnCluster;
     const uint32_t rank = cluster_ctarank();
@@ -234,70 +238,74 @@ sn_power_iter_cluster_kernel(const __grid_constant__ SnLayers L, const __grid_co
     const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
     for (int n = tid; n < R; n += nt) su[n] = Y.u[n];
     __syncthreads();
-    // phase 1: t = W^T u on the slice; thread (g, kk) sums the rows of group g for column k0 + kk
-    {
-        const int kk = tid % cpcp, g = tid / cpcp;
-        if (g < G && kk < nk) {
-            const int rpg = (R + G - 1) / G;
-            const int n1 = min(R, (g + 1) * rpg);
-            const float* wp = Y.w + k0 + kk;
-            float acc = 0.f;
+    for (int it = 0; it < iters; ++it) {
+        // phase 1: t = W^T u on the slice; thread (g, kk) sums the rows of group g for column k0 + kk
+        {
+            const int kk = tid % cpcp, g = tid / cpcp;
+            if (g < G && kk < nk) {
+                const int rpg = (R + G - 1) / G;
+                const int n1 = min(R, (g + 1) * rpg);
+                const float* wp = Y.w + k0 + kk;
+                float acc = 0.f;
 #pragma unroll 8
-            for (int n = g * rpg; n < n1; ++n) acc = fmaf(__ldg(wp + (long long)n * C), su[n], acc);
-            tpart[g * Gm.cpc_max + kk] = acc;
+                for (int n = g * rpg; n < n1; ++n) acc = fmaf(__ldg(wp + (long long)n * C), su[n], acc);
+                tpart[g * Gm.cpc_max + kk] = acc;
+            }
         }
-    }
-    __syncthreads();
-    float ss = 0.f;
-    if (tid < nk) {
-        float t = 0.f;
-        for (int g = 0; g < G; ++g) t += tpart[g * Gm.cpc_max + tid];
-        st[tid] = t;
-        ss = t * t;
-    }
-    ss = block_sum(ss, red);
-    if (tid < kSnCluster) {
-        const uint32_t remote = mapa_shared(smem_u32(ss_part + rank), uint32_t(tid));
-        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(ss) : "memory");
-    }
-    cluster_sync_all();
-    float tot = 0.f;
+        __syncthreads();
+        float ss = 0.f;
+        if (tid < nk) {
+            float t = 0.f;
+            for (int g = 0; g < G; ++g) t += tpart[g * Gm.cpc_max + tid];
+            st[tid] = t;
+            ss = t * t;
+        }
+        ss = block_sum(ss, red);
+        if (tid < kSnCluster) {
+            const uint32_t remote = mapa_shared(smem_u32(ss_part + rank), uint32_t(tid));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(ss) : "memory");
+        }
+        cluster_sync_all();
+        float tot = 0.f;
 #pragma unroll
-    for (int r = 0; r < kSnCluster; ++r) tot += ss_part[r];
-    const float inv_v = 1.f / (sqrtf(tot) + 1e-12f);
-    if (tid < nk) st[tid] *= inv_v;
-    __syncthreads();
-    // phase 2: partial s = W[:, slice] v[slice]  (warp per row)
-    for (int n = warp; n < R; n += nw) {
-        const float* wp = Y.w + (long long)n * C + k0;
-        float acc = 0.f;
-        for (int kk = lane; kk < nk; kk += 32) acc = fmaf(__ldg(wp + kk), st[kk], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) sp[n] = acc;
-    }
-    __syncthreads();
-    for (int i = tid; i < kSnCluster * R; i += nt) {
-        const int peer = i / R, n = i - peer * R;
-        const uint32_t remote = mapa_shared(smem_u32(s_part + int(rank) * Gm.rows_max + n), uint32_t(peer));
-        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(sp[n]) : "memory");
-    }
-    cluster_sync_all();
-    float s2 = 0.f;
-    for (int n = tid; n < R; n += nt) {
-        float s = 0.f;
-#pragma unroll
-        for (int r = 0; r < kSnCluster; ++r) s += s_part[r * Gm.rows_max + n];
-        su[n] = s;
-        s2 += s * s;
-    }
-    s2 = block_sum(s2, red);
-    const float inv_u = 1.f / (sqrtf(s2) + 1e-12f);
-    if (rank == 0) {
-        if (tid == 0) *Y.sigma = s2 * inv_u;  // sigma = u_new . (W v)
+        for (int r = 0; r < kSnCluster; ++r) tot += ss_part[r];
+        const float inv_v = 1.f / (sqrtf(tot) + 1e-12f);
+        if (tid < nk) st[tid] *= inv_v;
+        __syncthreads();
+        // phase 2: partial s = W[:, slice] v[slice]  (warp per row)
+        for (int n = warp; n < R; n += nw) {
+            const float* wp = Y.w + (long long)n * C + k0;
+            float acc = 0.f;
+            for (int kk = lane; kk < nk; kk += 32) acc = fmaf(__ldg(wp + kk), st[kk], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) sp[n] = acc;
+        }
+        __syncthreads();
+        for (int i = tid; i < kSnCluster * R; i += nt) {
+            const int peer = i / R, n = i - peer * R;
+            const uint32_t remote = mapa_shared(smem_u32(s_part + int(rank) * Gm.rows_max + n), uint32_t(peer));
+            asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(remote), "f"(sp[n]) : "memory");
+        }
+        cluster_sync_all();
+        float s2 = 0.f;
         for (int n = tid; n < R; n += nt) {
-            const float un = su[n] * inv_u;
-            Y.u[n] = un;
-            if (Y.u_save) Y.u_save[n] = un;
+            float s = 0.f;
+#pragma unroll
+            for (int r = 0; r < kSnCluster; ++r) s += s_part[r * Gm.rows_max + n];
+            su[n] = s;
+            s2 += s * s;
+        }
+        s2 = block_sum(s2, red);
+        const float inv_u = 1.f / (sqrtf(s2) + 1e-12f);
+        if (rank == 0 && tid == 0) Y.sigma[(long long)it * sigma_stride] = s2 * inv_u;  // sigma = u_new . (W v)
+        for (int n = tid; n < R; n += nt) su[n] *= inv_u;  // every CTA holds the full new u for the next iteration
+        if (it + 1 < iters) cluster_sync_all();  // peers are done reading ss_part / s_part before they are rewritten
+        else __syncthreads();
+    }
+    if (rank == 0) {
+        for (int n = tid; n < R; n += nt) {
+            Y.u[n] = su[n];
+            if (Y.u_save) Y.u_save[n] = su[n];
         }
     }
     if (tid < nk) {
@@ -317,6 +325,8 @@ struct SnBwdLayer {
     float* out;   // [rows][cols]
     int rows, cols;
     int accumulate;  // out += result instead of out = result
+    const float* sigma2;  // optional (see scmgan_sn_bwd_layer): g was taken with respect to Wbar/sigma, sigma2 is the
+                          // sigma of the call the samples belong to; nullptr = sigma
 };
 struct SnBwdLayers {
     SnBwdLayer layer[kMaxSnLayers];
@@ -340,7 +350,7 @@ __global__ void sn_bwd_apply_kernel(const __grid_constant__ SnBwdLayers L) {
     const long long total = (long long)Y.rows * Y.cols;
     const float sig = __ldg(Y.sigma);
     const float inv = 1.f / sig;
-    const float coef = __ldg(Y.dot) * inv * inv;
+    const float coef = __ldg(Y.dot) * inv / (Y.sigma2 ? __ldg(Y.sigma2) : sig);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
         const int n = int(i / Y.cols), k = int(i - (long long)n * Y.cols);

@@ -136,6 +136,7 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
     const float* sbp = (P.sample_bias && R.valid) ? P.sample_bias + size_t(R.b) * n_total + n0 : nullptr;
+    const float rs = (P.sample_scale && R.valid) ? P.scale * __ldg(P.sample_scale + R.b) : P.scale;
     const size_t hw = size_t(P.H) * P.W;
     const uint32_t s_bias_u32 = smem_u32(s_bias);
     __nv_bfloat16* const ob = P.out + (P.out_c_off + n0);
@@ -167,10 +168,10 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
                 asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
                              : "=f"(b4.x), "=f"(b4.y), "=f"(b4.z), "=f"(b4.w)
                              : "r"(s_bias_u32 + uint32_t(c0 + 4 * j) * 4u));
-                v[4 * j] = fmaf(v[4 * j], P.scale, b4.x);
-                v[4 * j + 1] = fmaf(v[4 * j + 1], P.scale, b4.y);
-                v[4 * j + 2] = fmaf(v[4 * j + 2], P.scale, b4.z);
-                v[4 * j + 3] = fmaf(v[4 * j + 3], P.scale, b4.w);
+                v[4 * j] = fmaf(v[4 * j], rs, b4.x);
+                v[4 * j + 1] = fmaf(v[4 * j + 1], rs, b4.y);
+                v[4 * j + 2] = fmaf(v[4 * j + 2], rs, b4.z);
+                v[4 * j + 3] = fmaf(v[4 * j + 3], rs, b4.w);
             }
         }
         if (sbp) {

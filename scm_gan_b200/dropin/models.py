@@ -80,11 +80,29 @@ class Transition(nn.Module):
                                                         dtype=torch.int64), persistent=False)
         _to_device(self)
 
-    def forward(self, s, a, return_all=False):
+    def power_iterations(self, calls):
+        """Run the power iterations of the next `calls` forward calls ahead of time, in one kernel launch: returns
+        sigma [calls, 5] (row i = what call i would compute, spectral_normalization.py:28-34) and leaves u, v advanced
+        `calls` times, exactly as `calls` forward calls would.  The iteration reads nothing but the weights, so this
+        is only valid while they do not change (within one training iteration).  Pass row i - or several rows, when
+        the batch folds the samples of several calls - as `sigma=` to forward()."""
+        wbar, _, u, v = _sn_params([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5])
+        sigma = torch.empty((calls, len(wbar)), dtype=torch.float32, device=wbar[0].device)
+        with torch.no_grad():
+            _ops.K.spectral_norm_fwd_n([w.detach() for w in wbar], [t.detach() for t in u], [t.detach() for t in v],
+                                       sigma)
+        return sigma
+
+    def forward(self, s, a, return_all=False, sigma=None):
+        """sigma (optional, not part of the reference signature): rows of power_iterations().  One row [5]: this call
+        uses it instead of running its own power iteration.  Several rows [S, 5]: the batch consists of S equal
+        segments belonging to S different calls of the reference (the main rollout step and the counterfactual
+        rollouts of main.py:242-283 folded into one batch); segment s is normalised with row s."""
         assert s.shape[0] == a.shape[0]
         wbar, bias, u, v = _sn_params([self.conv1, self.conv2, self.conv3, self.conv4, self.conv5])
-        with torch.no_grad():
-            sigma = torch.ops.scmgan.spectral_norm_update(wbar, u, v)
+        if sigma is None:
+            with torch.no_grad():
+                sigma = torch.ops.scmgan.spectral_norm_update(wbar, u, v)
         uniforms = None
         if self.training:
             uniforms, self._uniforms = self._uniforms, None

@@ -63,13 +63,30 @@ def spectral_norm_update(wbar, u, v):
     return sigma
 
 
+def _segment_ratio(sigma, B):
+    """sigma [S, n_layers] -> rho [n_layers, B] with rho[l, b] = sigma[0, l] / sigma[segment(b), l], or None for S = 1.
+    The batch is S equal segments whose spectral-norm calls differ (main rollout step + counterfactual rollouts folded
+    into one batch); the weights are packed for segment 0's sigma and rho rescales the other segments' rows."""
+    S = sigma.shape[0]
+    if S == 1:
+        return None
+    assert B % S == 0
+    return (sigma[0:1] / sigma).t().repeat_interleave(B // S, dim=1).contiguous()
+
+
 def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_state=None):
-    """z [B,L,H,W] fp32, a [B,A] fp32.  wbar/bias: lists for conv1..conv5; sigma [5] from spectral_norm_update.
-    Returns (z_next, p, saved) with saved = [zin, buf6, buf5, act3, wd...] for backward."""
+    """z [B,L,H,W] fp32, a [B,A] fp32.  wbar/bias: lists for conv1..conv5; sigma [5] from spectral_norm_update, or
+    [S, 5] when the batch consists of S equal segments that belong to S different calls of the reference (see
+    _segment_ratio).  Returns (z_next, p, saved) with saved = [zin, buf6, buf5, act3, wd..., rho] for backward."""
     dev = z.device
     B, L, H, W = z.shape
     Lp = _r16(L)
     A = a.shape[1]
+    sigma = sigma.view(-1, 5)
+    S = sigma.shape[0]
+    sig0 = sigma[0]
+    rho = _segment_ratio(sigma, B)
+    rs = (lambda l: None) if rho is None else (lambda l: rho[l])
 
     # packed operands: forward [9][Cout][Cin] and dgrad [9][Cin][Cout] (1/sigma folded in)
     wf = [K.packed_weight(HID, Lp, dev), K.packed_weight(HID, HID, dev), K.packed_weight(HID, HID, dev),
@@ -83,21 +100,24 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     wd = [K.packed_weight(Lp, HID, dev, G16), K.packed_weight(HID, HID + LS, dev, G16),
           K.packed_weight(HID, 2 * HID, dev, G16), K.packed_weight(HID, HID, dev, G16),
           K.packed_weight(HID, HID, dev, G16), K.packed_weight(HID, Lp, dev, G16)]
-    jobs = [_conv2d_fwd_job(wbar[0], wf[0], sigma[0:1], k_valid=L)]
-    jobs += [_conv2d_fwd_job(wbar[i], wf[i], sigma[i:i + 1]) for i in range(1, 5)]
+    jobs = [_conv2d_fwd_job(wbar[0], wf[0], sig0[0:1], k_valid=L)]
+    jobs += [_conv2d_fwd_job(wbar[i], wf[i], sig0[i:i + 1]) for i in range(1, 5)]
     jobs += [_conv2d_fwd_job(w6, wf[5])]
-    jobs += [_conv2d_dgrad_job(wbar[0], wd[0], sigma[0:1], 0, L)]
-    jobs += [_conv2d_dgrad_job(wbar[1], wd[1][:, :, :HID], sigma[1:2]),                       # conv2
+    jobs += [_conv2d_dgrad_job(wbar[0], wd[0], sig0[0:1], 0, L)]
+    jobs += [_conv2d_dgrad_job(wbar[1], wd[1][:, :, :HID], sig0[1:2]),                       # conv2
              _conv2d_dgrad_job(w6, wd[1][:, :, HID:], None, HID, HID, co_valid=L)]              # conv6, skip half
-    jobs += [_conv2d_dgrad_job(wbar[2], wd[2][:, :, :HID], sigma[2:3]),                       # conv3
-             _conv2d_dgrad_job(wbar[4], wd[2][:, :, HID:], sigma[4:5], HID, HID)]               # conv5, skip half
-    jobs += [_conv2d_dgrad_job(wbar[3], wd[3], sigma[3:4])]                                   # conv4
-    jobs += [_conv2d_dgrad_job(wbar[4], wd[4], sigma[4:5], 0, HID)]                           # conv5, act4 half
+    jobs += [_conv2d_dgrad_job(wbar[2], wd[2][:, :, :HID], sig0[2:3]),                       # conv3
+             _conv2d_dgrad_job(wbar[4], wd[2][:, :, HID:], sig0[4:5], HID, HID)]               # conv5, skip half
+    jobs += [_conv2d_dgrad_job(wbar[3], wd[3], sig0[3:4])]                                   # conv4
+    jobs += [_conv2d_dgrad_job(wbar[4], wd[4], sig0[4:5], 0, HID)]                           # conv5, act4 half
     jobs += [_conv2d_dgrad_job(w6, wd[5], None, 0, HID, co_valid=L)]                          # conv6, act5 half
     K.pack_weights(jobs)
 
+    # folded action channels: per-sample bias with the sigma of the sample's own segment
     sbias = torch.empty((B, HID), dtype=torch.float32, device=dev)
-    K.action_bias(wbar[0], sigma[0:1], bias[0], a, L, sbias)
+    Bs = B // S
+    for s in range(S):
+        K.action_bias(wbar[0], sigma[s, 0:1], bias[0], a[s * Bs:(s + 1) * Bs], L, sbias[s * Bs:(s + 1) * Bs])
 
     zin = K.fwd_plane(B, H, W, Lp, dev)
     K.pack_nchw(z, zin, wrap=True)
@@ -105,11 +125,11 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
     buf5 = K.fwd_plane(B, H, W, 2 * HID, dev)  # [act4 | act2]  = input of conv5 (models.py:95)
     act3 = K.fwd_plane(B, H, W, HID, dev)
     cv = dict(act=ACT_LRELU, wrap=True)
-    K.conv3x3(zin, wf[0], B, H, W, cin=Lp, sample_bias=sbias, out=buf6, out_c_off=HID, **cv)        # conv1 -> skip1
-    K.conv3x3(buf6, wf[1], B, H, W, cin=HID, x_c_off=HID, bias=bias[1], out=buf5, out_c_off=HID, **cv)  # conv2 -> skip2
-    K.conv3x3(buf5, wf[2], B, H, W, cin=HID, x_c_off=HID, bias=bias[2], out=act3, **cv)             # conv3
-    K.conv3x3(act3, wf[3], B, H, W, cin=HID, bias=bias[3], out=buf5, out_c_off=0, **cv)             # conv4
-    K.conv3x3(buf5, wf[4], B, H, W, cin=2 * HID, bias=bias[4], out=buf6, out_c_off=0, **cv)         # conv5
+    K.conv3x3(zin, wf[0], B, H, W, cin=Lp, sample_bias=sbias, sample_scale=rs(0), out=buf6, out_c_off=HID, **cv)  # conv1 -> skip1
+    K.conv3x3(buf6, wf[1], B, H, W, cin=HID, x_c_off=HID, bias=bias[1], sample_scale=rs(1), out=buf5, out_c_off=HID, **cv)  # conv2 -> skip2
+    K.conv3x3(buf5, wf[2], B, H, W, cin=HID, x_c_off=HID, bias=bias[2], sample_scale=rs(2), out=act3, **cv)  # conv3
+    K.conv3x3(act3, wf[3], B, H, W, cin=HID, bias=bias[3], sample_scale=rs(3), out=buf5, out_c_off=0, **cv)  # conv4
+    K.conv3x3(buf5, wf[4], B, H, W, cin=2 * HID, bias=bias[4], sample_scale=rs(4), out=buf6, out_c_off=0, **cv)  # conv5
     p = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     zn = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     if training and uniforms is None and rng_state is not None:
@@ -119,7 +139,7 @@ def transition_forward(z, a, wbar, bias, sigma, w6, b6, uniforms, training, rng_
         K.philox_uniform(uniforms, rng_state)
     K.conv3x3(buf6, wf[5], B, H, W, cin=2 * HID, bias=b6, act=ACT_SIGMOID, out_f32=p, n_valid=L, sample_out=zn,
               uniforms=uniforms if training else None)                                              # conv6 + head
-    return zn, p, [zin, buf6, buf5, act3] + wd
+    return zn, p, [zin, buf6, buf5, act3] + wd + ([rho] if rho is not None else [])
 
 
 def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
@@ -127,35 +147,57 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     reference models.py:38-40).  Returns (dz, [dWbar1..5], [db1..5], dW6, db6).
     sink = [gWbar1..5, gb1..5, gW6, gb6] (entries may be None): the kernels ADD that parameter's gradient into the
     given buffer (the parameter's .grad) and None is returned in its place; the weights are shared by every unrolled
-    step, so this replaces one AccumulateGrad add per parameter and step."""
+    step, so this replaces one AccumulateGrad add per parameter and step.
+
+    Segments (sigma [S, 5], S > 1): every gradient plane of a spectral-normalised layer l holds
+    rho_l[b] * d pre_l (the dgrad epilogue that writes it applies rho), so that the dgrad through layer l with the
+    weights packed for sigma[0] yields exactly d pre_l * (Wbar/sigma_s)^T for a sample of segment s.  The weight
+    gradients are taken per segment on those planes, G'_s = rho_s G_s, and
+        dWbar += G'_s/sigma_0 - (<G'_s, Wbar>/(sigma_0 sigma_s)) u v^T   ( = G_s/sigma_s - (<G_s,Wbar>/sigma_s^2) u v^T )
+    while bias gradients are rescaled by 1/rho_s."""
     zin, buf6, buf5, act3 = saved[:4]
-    wd = saved[4:]
+    wd = saved[4:10]
+    rho = saved[10] if len(saved) > 10 else None
+    rs = (lambda l: None) if rho is None else (lambda l: rho[l])
     dev = dz_next.device
     B, L, H, W = dz_next.shape
     Lp = zin.shape[3]
     A = a.shape[1]
-    # gradients w.r.t. the *normalised* weights / biases, one flat zeroed buffer (wgrad accumulates atomically)
-    shapes = [tuple(w.shape) for w in wbar] + [tuple(w6.shape)]
-    sizes = [w.numel() for w in wbar] + [w6.numel()]
-    nb = 5 * HID + Lp
-    flat = torch.zeros(sum(sizes) + nb + B * HID + 8, dtype=torch.float32, device=dev)
-    G, off = [], 0
-    for s, n in zip(shapes, sizes):
-        G.append(flat[off:off + n].view(s))
-        off += n
-    db = [flat[off + i * HID: off + (i + 1) * HID] for i in range(5)]
-    db6 = flat[off + 5 * HID: off + 5 * HID + Lp]
-    off += nb
-    S1 = flat[off: off + B * HID].view(B, HID)
-    off += B * HID
-    dots = flat[off: off + 8]
+    sigma = sigma.view(-1, 5)
+    S = sigma.shape[0]
+    Bs = B // S
+    # gradients w.r.t. the *normalised* weights / biases, one flat zeroed buffer
+    shapes = [tuple(w.shape) for w in wbar]
+    sizes = [w.numel() for w in wbar]
+    nb = 5 * HID
+    per_seg = sum(sizes) + nb + Bs * HID + 8
+    flat = torch.zeros(S * per_seg + w6.numel() + Lp, dtype=torch.float32, device=dev)
+    Gs, dbs, S1s, dots = [], [], [], []
+    for s in range(S):
+        off = s * per_seg
+        G = []
+        for sh, n in zip(shapes, sizes):
+            G.append(flat[off:off + n].view(sh))
+            off += n
+        Gs.append(G)
+        dbs.append([flat[off + i * HID: off + (i + 1) * HID] for i in range(5)])
+        off += nb
+        S1s.append(flat[off: off + Bs * HID].view(Bs, HID))
+        off += Bs * HID
+        dots.append(flat[off: off + 8])
+    G6 = flat[S * per_seg: S * per_seg + w6.numel()].view(w6.shape)
+    db6 = flat[S * per_seg + w6.numel():]
     sink = list(sink) if sink is not None else [None] * 12
     gw, gb, gw6, gb6 = sink[0:5], sink[5:10], sink[10], sink[11]
     if gw6 is not None:
-        G[5] = gw6
-    db = [db[i] if gb[i] is None else gb[i] for i in range(5)]
+        G6 = gw6
+    if S == 1:  # the bias sums go straight into the caller's buffers
+        dbs[0] = [dbs[0][i] if gb[i] is None else gb[i] for i in range(5)]
     if gb6 is not None and Lp == L:
         db6 = gb6
+
+    def seg(plane, s):
+        return plane if S == 1 else plane[s * Bs:(s + 1) * Bs]
 
     # Gradient planes.  DB = [d pre2 | d pre6 (Lp channels, zero-padded to LS)], DA = [d pre3 | d pre5]: each pair is
     # the K-concatenated input of one dgrad GEMM (see transition_forward), so the partial sums of the skip
@@ -167,37 +209,62 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     # d pre-activation of conv6: dz * p * (1 - p)
     K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
-    K.wgrad(DB, buf6, G[5], B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
+    K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
     with dr.side_section():
         K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
-    K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0, **dg)  # d pre5
-    K.wgrad(DA, buf5, G[4], B, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, db=db[4], defer=dr)
+    K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0,
+              sample_scale=rs(4), **dg)                                                                     # d pre5
+    for s in range(S):
+        K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][4], Bs, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9,
+                g_s_ci=9, db=dbs[s][4], defer=dr)
     d4 = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, **dg)              # d pre4
-    K.wgrad(d4, act3, G[3], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[3], defer=dr)
-    K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, **dg)                            # d pre3
-    K.wgrad(DA, buf5, G[2], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
-    K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, **dg)        # d pre2
-    K.wgrad(DB, buf6, G[1], B, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
+    K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, sample_scale=rs(3), **dg)  # d pre4
+    for s in range(S):
+        K.wgrad(seg(d4, s), seg(act3, s), Gs[s][3], Bs, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9,
+                db=dbs[s][3], defer=dr)
+    K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, sample_scale=rs(2), **dg)        # d pre3
+    for s in range(S):
+        K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][2], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
+                g_s_ci=9, db=dbs[s][2], defer=dr)
+    K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, sample_scale=rs(1),
+              **dg)                                                                                         # d pre2
+    for s in range(S):
+        K.wgrad(seg(DB, s), seg(buf6, s), Gs[s][1], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
+                g_s_ci=9, db=dbs[s][1], defer=dr)
     d1 = K.new_plane(B, H, W, HID, dev)
-    K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, **dg)                    # d pre1
+    K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, sample_scale=rs(0), **dg)  # d pre1
     c1 = L + A
-    K.wgrad(d1, zin, G[0], B, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L, defer=dr)
-    with dr.side_section():
-        K.plane_colsum(d1, 0, HID, B, H, W, S=S1, db=db[0])
-        K.action_wgrad(S1, a, L, G[0])
+    for s in range(S):
+        K.wgrad(seg(d1, s), seg(zin, s), Gs[s][0], Bs, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L,
+                defer=dr)
+        with dr.side_section():
+            K.plane_colsum(seg(d1, s), 0, HID, Bs, H, W, S=S1s[s], db=dbs[s][0])
+            K.action_wgrad(S1s[s], a[s * Bs:(s + 1) * Bs], L, Gs[s][0])
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
     # spectral norm backward with the u, v currently held by the module (= last forward call)
     dr.join()
     dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
-    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
-                          dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(5)])
+    for s in range(S):
+        K.spectral_norm_bwd([(Gs[s][i], wbar[i], u[i], v[i], sigma[0, i:i + 1], dots[s][i:i + 1],
+                              dwbar[i] if gw[i] is None else gw[i], gw[i] is not None or s > 0,
+                              sigma[s, i:i + 1]) for i in range(5)])
+    if S == 1:
+        db_out = [dbs[0][i].clone() if gb[i] is None else None for i in range(5)]
+    else:  # bias gradients: sum_s colsum_s / rho_s
+        inv_rho = (sigma / sigma[0:1])                                   # [S, 5] = 1 / rho_s
+        tot = (torch.stack([torch.stack(dbs[s]) for s in range(S)]) * inv_rho.unsqueeze(-1)).sum(0)   # [5, HID]
+        db_out = []
+        for i in range(5):
+            if gb[i] is None:
+                db_out.append(tot[i].clone())
+            else:
+                gb[i] += tot[i]
+                db_out.append(None)
     if gb6 is not None and Lp != L:
         gb6 += db6[:L]
-    return (dz, dwbar, [db[i].clone() if gb[i] is None else None for i in range(5)],
-            G[5].clone() if gw6 is None else None, db6[:L].clone() if gb6 is None else None)
+    return (dz, dwbar, db_out, G6.clone() if gw6 is None else None, db6[:L].clone() if gb6 is None else None)
 
 
 # ------------------------------------------------------------------------------------------------------------

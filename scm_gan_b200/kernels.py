@@ -87,7 +87,8 @@ def packed_weight(n_pad, k_pad, device, dtype=None):
     return torch.empty((9, n_pad, k_pad), dtype=dtype or FWD_DTYPE, device=device)
 
 
-def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, act=ACT_NONE,
+def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, sample_scale=None,
+            act=ACT_NONE,
             out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
             n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False):
     n = w_packed.shape[1]
@@ -97,6 +98,8 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     d.x, d.x_cs, d.x_c_off, d.cin = x_plane.data_ptr(), x_plane.shape[3], x_c_off, cin
     d.w, d.n = w_packed.data_ptr(), n
     d.scale, d.bias, d.sample_bias = scale, L.ptr(bias), L.ptr(sample_bias)
+    assert sample_scale is None or (sample_scale.numel() == B and sample_scale.is_contiguous())
+    d.sample_scale = L.ptr(sample_scale)
     d.bias_n = 0 if bias is None else min(int(bias.numel()), n)  # shorter than n: the padded channels get no bias
     d.act, d.slope = act, LRELU_SLOPE
     d.out = L.ptr(out)
@@ -230,14 +233,28 @@ def spectral_norm_fwd(layers):
     L.check(L.lib().scmgan_spectral_norm_fwd(len(layers), arr, _stream()), "scmgan_spectral_norm_fwd")
 
 
+def spectral_norm_fwd_n(wbar, u, v, sigma):
+    """sigma [iters, n_layers] (contiguous fp32): `iters` successive power iterations of every layer in one launch;
+    sigma[i, l] is what call i of layer l's SpectralNorm.forward would compute.  u, v end up advanced `iters` times."""
+    iters, n = sigma.shape
+    assert sigma.is_contiguous() and n == len(wbar)
+    arr = (L.SnLayer * n)()
+    for i, w in enumerate(wbar):
+        rows = w.shape[0]
+        arr[i] = L.SnLayer(w.data_ptr(), u[i].data_ptr(), v[i].data_ptr(), sigma[0, i:i + 1].data_ptr(), None, None, rows,
+                           w.numel() // rows)
+    L.check(L.lib().scmgan_spectral_norm_fwd_n(n, arr, iters, n, _stream()), "scmgan_spectral_norm_fwd_n")
+
+
 def spectral_norm_bwd(layers):
-    """layers: list of (g, wbar, u, v, sigma, dot, out[, accumulate])."""
+    """layers: list of (g, wbar, u, v, sigma, dot, out[, accumulate[, sigma2]])."""
     arr = (L.SnBwdLayer * len(layers))()
     for i, lay in enumerate(layers):
         g, w, u, v, s, dot, out = lay[:7]
         rows = w.shape[0]
         arr[i] = L.SnBwdLayer(g.data_ptr(), w.data_ptr(), u.data_ptr(), v.data_ptr(), s.data_ptr(), dot.data_ptr(),
-                              out.data_ptr(), rows, w.numel() // rows, int(bool(lay[7])) if len(lay) > 7 else 0)
+                              out.data_ptr(), rows, w.numel() // rows, int(bool(lay[7])) if len(lay) > 7 else 0,
+                              L.ptr(lay[8]) if len(lay) > 8 else None)
     L.check(L.lib().scmgan_spectral_norm_bwd(len(layers), arr, _stream()), "scmgan_spectral_norm_bwd")
 
 

@@ -317,7 +317,7 @@ bce_logits_seq.register_autograd(_bce_seq_backward, setup_context=_bce_seq_setup
 
 @torch.library.custom_op("scmgan::masked_mse_seq", mutates_args=())
 def masked_mse_seq(pred: Tensor, target_bt: Tensor, mask_bt: Tensor, scale: float,
-                   scale_dev: Optional[Tensor] = None) -> List[Tensor]:
+                   scale_dev: Optional[Tensor]) -> List[Tensor]:
     """pred [T*B, R] (t-major); target_bt [B, T, R], mask_bt [B, T] views.
     -> [scale * scale_dev * sum_t masked mean_t (0-dim), d / d pred, unscaled per-step means [T]]."""
     _require_cuda(pred, target_bt, mask_bt)
@@ -343,7 +343,7 @@ masked_mse_seq.register_autograd(lambda ctx, grads: _mse_backward(ctx, grads), s
 # ------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("scmgan::masked_mse", mutates_args=())
 def masked_mse(pred: Tensor, target: Tensor, mask: Tensor, scale: float,
-               scale_dev: Optional[Tensor] = None) -> List[Tensor]:
+               scale_dev: Optional[Tensor]) -> List[Tensor]:
     """-> [scale * scale_dev * masked mean, d loss / d pred, unscaled masked mean].  scale_dev is a 0-dim / 1-element
     device tensor (theta of main.py:143): no gradient flows to it."""
     _require_cuda(pred, target, mask)

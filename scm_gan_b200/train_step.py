@@ -85,16 +85,61 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
     lo_loss = torch.zeros((), dtype=torch.float32, device=states.device) if latent_overshooting else None
     lo_z = {}
     T = Hn - 2
+    do_dis = bool(enable_disentanglement and cf_now)
+    do_act = bool(enable_action_control and cf_now)
+    n_cf = counterfactual_horizon - 1   # extra Transition calls per counterfactual branch (main.py:255-257, 276-278)
+    L = z.shape[1]
+    unswapped = None
+    if do_dis:  # main.py:246-253
+        ar = torch.arange(B, device=z.device)
+        hit = torch.zeros((B, L), dtype=torch.float32, device=z.device)
+        hit.scatter_(1, cf_indices, 1.0)  # both intervened factors of every sample (graph-capturable)
+        unswapped = 1.0 - hit
     if T > 0 and not latent_overshooting and not SEQUENTIAL_HEADS:
-        # The reward predictor and the decoder are stateless (no spectral norm, no sampling) and nothing downstream of
-        # them feeds the rollout, so the T per-step calls of main.py:181-197 are evaluated as ONE batch of T*B
-        # latents after the rollout: same arithmetic per sample, 1/T of the launches, kernels large enough to be
-        # bandwidth- instead of latency-bound.  The Transition calls keep the reference's order (its spectral-norm
-        # state and random stream advance per call).
+        # ---- batched path ---------------------------------------------------------------------------------------
+        # (1) The reward predictor and the decoder are stateless (no spectral norm, no sampling) and nothing
+        #     downstream of them feeds the rollout, so the T per-step calls of main.py:181-197 are evaluated as ONE
+        #     batch of T*B latents after the rollout: same arithmetic per sample, 1/T of the launches.
+        # (2) Counterfactual step j of both branches (main.py:255-257, 276-278) starts from z_orig and needs nothing
+        #     from the main rollout, so it is folded into the batch of main step j: one Transition call on up to 3B
+        #     samples.  Each segment keeps the spectral-norm sigma of ITS call in the reference's order (all main
+        #     calls, then the disentanglement branch, then the action-control branch): the power iterations only
+        #     depend on the weights, so all of them run ahead in one launch (Transition.power_iterations) and u, v end
+        #     in the same state.
+        if do_dis:
+            # main.py:253 assigns through views: net effect z[i, idx_a] <- z[i, idx_b], in place on
+            # z_orig, hence also seen by the action-control branch (main.py:272)
+            z_orig[ar, cf_indices[:, 0]] = z_orig[ar, cf_indices[:, 1]]
+        sig = tr.power_iterations(T + n_cf * (int(do_dis) + int(do_act)))
+        row_d, row_a = T, T + (n_cf if do_dis else 0)
+        zd = z_orig if do_dis else None
+        za = z_orig if do_act else None
+        cf_onehots = onehots[:, cf_perm] if do_act else None  # actions of another trajectory of the batch (main.py:275)
+        ulist = list(uniforms) if uniforms is not None else None
         zs = []
-        for t in range(1, Hn - 1):
-            zs.append(z)
-            z = step(z.detach() if (truncate_bptt and t > 1) else z, onehots[t])   # main.py:192-193, 206-207
+        for t in range(1, max(T, n_cf if (do_dis or do_act) else 0) + 1):
+            segs, acts, rows = [], [], []
+            if t <= T:
+                zs.append(z)
+                segs.append(z.detach() if (truncate_bptt and t > 1) else z)   # main.py:192-193
+                acts.append(onehots[t])
+                rows.append(t - 1)
+            if do_dis and t <= n_cf:
+                segs.append(zd); acts.append(onehots[t]); rows.append(row_d + t - 1)
+            if do_act and t <= n_cf:
+                segs.append(za); acts.append(cf_onehots[t]); rows.append(row_a + t - 1)
+            if ulist is not None:
+                tr._uniforms = ulist[rows[0]] if len(rows) == 1 else torch.cat([ulist[r] for r in rows], dim=0)
+            if len(segs) == 1:
+                outs = [tr(segs[0], acts[0], sigma=sig[rows[0]])]
+            else:
+                outs = list(tr(torch.cat(segs, dim=0), torch.cat(acts, dim=0), sigma=sig[rows]).chunk(len(segs), dim=0))
+            if t <= T:
+                z = outs.pop(0)
+            if do_dis and t <= n_cf:
+                zd = outs.pop(0)
+            if do_act and t <= n_cf:
+                za = outs.pop(0)
         zcat = torch.cat(zs, dim=0)                                # [T*B, L, H, W], t-major
         mask_bt = masks[:, :T]
         rd = torch.ops.scmgan.masked_mse_seq(rew(zcat), rewards[:, 1:Hn - 1], mask_bt, reward_coef, theta)
@@ -104,58 +149,65 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
             for t in range(1, Hn - 1):
                 collect[f"Rd Loss t={t}"] = rd[2][t - 1]
                 collect[f"Reconstruction t={t}"] = rec[t - 1]
-    else:
-        for t in range(1, Hn - 1):
-            mask = masks[:, t - 1]
-            expected = rew(z)
-            rd = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, reward_coef, theta)
-            terms.append(rd[0])
-            rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
-            if truncate_bptt and t > 1:
-                z = z.detach()
-            terms.append(rec)
+        mask = masks[:, Hn - 3]
+        if do_dis:   # main.py:258-262
+            cf = torch.ops.scmgan.cf_loss(z, zd, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
+            terms.append(cf)
             if collect is not None:
-                collect[f"Rd Loss t={t}"] = rd[2]
-                collect[f"Reconstruction t={t}"] = rec
-            z = step(z, onehots[t])
+                collect["CF Disentanglement Loss"] = cf
+        if do_act:   # main.py:279-283
+            cf = torch.ops.scmgan.cf_loss(z, za, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
+            terms.append(cf)
+            if collect is not None:
+                collect["CF Control Bias Loss"] = cf
+        loss = torch.cat([t_.reshape(-1) for t_ in terms]).sum()
+        return loss, z
 
-            if latent_overshooting:  # Hafner et al., reference main.py:217-230
-                lo_z[t] = enc(states[:, t - 1:t + 2])
-                for t_left in range(1, t):
-                    lo_z[t_left] = step(lo_z[t_left], onehots[t - 1])
-                for t_a in range(2, t - 1):
-                    lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
-                    lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
+    # ---- sequential path: main.py's own order, call by call (latent overshooting, horizon 2, A/B measurements) ------
+    for t in range(1, Hn - 1):
+        mask = masks[:, t - 1]
+        expected = rew(z)
+        rd = torch.ops.scmgan.masked_mse(expected, rewards[:, t], mask, reward_coef, theta)
+        terms.append(rd[0])
+        rec = torch.ops.scmgan.bce_logits(dec(z), states[:, t], mask)[0]
+        if truncate_bptt and t > 1:
+            z = z.detach()
+        terms.append(rec)
+        if collect is not None:
+            collect[f"Rd Loss t={t}"] = rd[2]
+            collect[f"Reconstruction t={t}"] = rec
+        z = step(z, onehots[t])
+
+        if latent_overshooting:  # Hafner et al., reference main.py:217-230
+            lo_z[t] = enc(states[:, t - 1:t + 2])
+            for t_left in range(1, t):
+                lo_z[t_left] = step(lo_z[t_left], onehots[t - 1])
+            for t_a in range(2, t - 1):
+                lo_batch = ((lo_z[t].detach() - lo_z[t_a]) ** 2).mean(-1).mean(-1).mean(-1)
+                lo_loss = lo_loss + td_lambda * torch.mean(lo_batch * mask)
     mask = masks[:, Hn - 3] if Hn > 2 else torch.ones(B, device=states.device)
     if latent_overshooting:  # main.py:232-234
         terms.append(theta * lo_loss)
         if collect is not None:
             collect["LO total"] = lo_loss
 
-    if enable_disentanglement and cf_now:  # main.py:242-262
-        z_cf_a = z.clone()
+    if do_dis:  # main.py:242-262
         z_cf_b = z_orig
-        L = z.shape[1]
-        ar = torch.arange(B, device=z.device)
-        hit = torch.zeros((B, L), dtype=torch.float32, device=z.device)
-        hit.scatter_(1, cf_indices, 1.0)  # both intervened factors of every sample (graph-capturable)
-        unswapped = 1.0 - hit
         # main.py:253 assigns through views: net effect z[i, idx_a] <- z[i, idx_b], in place on z_orig
         z_cf_b[ar, cf_indices[:, 0]] = z_cf_b[ar, cf_indices[:, 1]]
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, onehots[t])
-        cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
+        cf = torch.ops.scmgan.cf_loss(z, z_cf_b, unswapped, mask, 0, CF_REGULARIZATION_LAMBDA)[0]
         terms.append(cf)
         if collect is not None:
             collect["CF Disentanglement Loss"] = cf
 
-    if enable_action_control and cf_now:  # main.py:268-283
-        z_cf_a = z.clone()
+    if do_act:  # main.py:268-283
         z_cf_b = z_orig
         cf_onehots = onehots[:, cf_perm]  # actions of another trajectory of the batch (main.py:275)
         for t in range(1, counterfactual_horizon):
             z_cf_b = step(z_cf_b, cf_onehots[t])
-        cf = torch.ops.scmgan.cf_loss(z_cf_a, z_cf_b, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
+        cf = torch.ops.scmgan.cf_loss(z, z_cf_b, None, mask, 1, CF_REGULARIZATION_LAMBDA)[0]
         terms.append(cf)
         if collect is not None:
             collect["CF Control Bias Loss"] = cf

@@ -59,12 +59,30 @@ def test_version_and_error_reporting_without_gpu(lib):
     assert l.scmgan_spectral_norm_fwd(0, None, None) == -1
 
 
-def test_struct_layouts_match_header_sizes(lib):
-    # pointer/int/float/long long packing as a C compiler lays out the structs of scmgan.h (x86-64 SysV)
-    assert C.sizeof(lib.PackJob) == 72
-    assert C.sizeof(lib.SnLayer) == 56
-    assert C.sizeof(lib.SnBwdLayer) == 72
-    assert C.sizeof(lib.AdamChunk) == 48
+def test_struct_layouts_match_header_sizes(lib, tmp_path):
+    """Every ctypes.Structure of the binding has the size (and the offset of its last field) the C compiler gives
+    the corresponding struct of include/scmgan.h."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    pairs = {"PackJob": "scmgan_pack_job", "ConvDesc": "scmgan_conv_desc", "WgradReduceJob": "scmgan_wgrad_reduce_job",
+             "WgradDesc": "scmgan_wgrad_desc", "SnLayer": "scmgan_sn_layer", "SnBwdLayer": "scmgan_sn_bwd_layer",
+             "CsrnSweepDesc": "scmgan_csrn_sweep_desc", "AdamChunk": "scmgan_adam_chunk"}
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    body = "".join(f'  printf("{py} %zu %zu\\n", sizeof({c}), offsetof({c}, {getattr(lib, py)._fields_[-1][0]}));\n'
+                   for py, c in pairs.items())
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "scmgan.h"\nint main(void) {\n' + body +
+                   "  return 0; }\n")
+    exe = tmp_path / "sizes"
+    subprocess.run(["gcc", "-std=c99", "-I", os.path.join(root, "include"), "-o", str(exe), str(src)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    got = {out[i]: (int(out[i + 1]), int(out[i + 2])) for i in range(0, len(out), 3)}
+    for py in pairs:
+        st = getattr(lib, py)
+        last = getattr(st, st._fields_[-1][0])
+        assert got[py] == (C.sizeof(st), last.offset), (py, got[py], C.sizeof(st), last.offset)
 
 
 def test_header_is_plain_c(tmp_path):

@@ -325,6 +325,19 @@ def test_colsum_action_bce_adam():
     rl.backward()
     assert abs(loss.item() - rl.item()) <= 1e-5 * abs(rl.item())
     assert report("bce dx", dx, lg.grad, 1e-5)
+    # sequence form: the decodes of T rollout steps as one batch (t-major logits, [B, T] windows of states / masks)
+    import scm_gan_b200.ops  # noqa: F401
+    Tn = 3
+    lt = (torch.randn(Tn * B, 3, H, W, device=DEV) * 3).requires_grad_(True)
+    mbt = (torch.rand(B, 4, device=DEV) > 0.3).float()
+    refs = [(F.binary_cross_entropy(torch.sigmoid(lt[t * B:(t + 1) * B]), states[:, 1 + t], reduction="none")
+             .mean(-1).mean(-1).mean(-1) * mbt[:, t]).mean() for t in range(Tn)]
+    wts = torch.tensor([1.0, 2.0, 0.5], device=DEV)
+    (gr,) = torch.autograd.grad((torch.stack(refs) * wts).sum(), lt)
+    terms = torch.ops.scmgan.bce_logits_seq(lt, states[:, 1:1 + Tn], mbt[:, :Tn])[0]
+    (gg,) = torch.autograd.grad((terms * wts).sum(), lt)
+    assert report("bce seq terms", terms, torch.stack(refs).detach(), 1e-5)
+    assert report("bce seq grad", gg, gr, 1e-5)
 
     # fused clip + Adam vs torch.optim.Adam after clip_grad_value_
     ps = [torch.randn(1000, device=DEV), torch.randn(77, 3, device=DEV)]
@@ -502,7 +515,7 @@ def test_masked_mse():
     ref = 0.37 * torch.mean(torch.mean((pred - rewards[:, 4]) ** 2, dim=1) * masks[:, 3])
     (gref,) = torch.autograd.grad(ref, pred)
     p2 = pred.detach().clone().requires_grad_(True)
-    got = torch.ops.scmgan.masked_mse(p2, rewards[:, 4], masks[:, 3], 0.37)[0]
+    got = torch.ops.scmgan.masked_mse(p2, rewards[:, 4], masks[:, 3], 0.37, None)[0]
     (ggot,) = torch.autograd.grad(got * 2.0, p2)
     assert report("masked mse", got, ref, 1e-6)
     assert report("masked mse grad", ggot, 2.0 * gref, 1e-6)
@@ -514,6 +527,18 @@ def test_masked_mse():
     assert report("masked mse (device theta)", out[0], 0.25 * ref, 1e-6)
     assert report("masked mse grad (device theta)", g3, 0.25 * gref, 1e-6)
     assert report("masked mse raw", out[2], ref / 0.37, 1e-6)
+    # sequence form: T steps in one launch, targets / masks addressed as [B, T] windows of the batch tensors
+    T = 5
+    pt = torch.randn(T * B, R, device=DEV, requires_grad=True)
+    refs = [torch.mean(torch.mean((pt[t * B:(t + 1) * B] - rewards[:, 2 + t]) ** 2, dim=1) * masks[:, 1 + t])
+            for t in range(T)]
+    ref_tot = 0.37 * 0.25 * sum(refs)
+    (gref,) = torch.autograd.grad(ref_tot, pt)
+    out = torch.ops.scmgan.masked_mse_seq(pt, rewards[:, 2:2 + T], masks[:, 1:1 + T], 0.37, theta)
+    (gg,) = torch.autograd.grad(out[0], pt)
+    assert report("masked mse seq", out[0], ref_tot, 1e-6)
+    assert report("masked mse seq raw", out[2], torch.stack(refs), 1e-6)
+    assert report("masked mse seq grad", gg, gref, 1e-6)
 
 
 @pytest.mark.parametrize("shape", [(2, 8, 6, 7), (3, 16, 12, 9), (2, 32, 16, 16)])
