@@ -10,8 +10,9 @@ reads `max()`/`argmax` of python floats, i.e. one transfer per candidate).  Call
 reference exactly by default, because every Transition call advances the spectral-norm power iteration
 (spectral_normalization.py:28-31) and, in train mode, draws Bernoulli noise.  `fold_actions=True` simulates the A
 candidates as one batch of A * A^lookahead trajectories (A x fewer Transition calls of A x the batch - the shape the
-tcgen05 kernels like); it performs fewer power iterations per decision, so it matches the sequential planner only up
-to the (converged) spectral-norm state.
+tcgen05 kernels like).  It is the same computation: the power iterations of all 13 A calls of the sequential order
+run ahead in one launch (Transition.power_iterations) and every candidate's segment of the batch is normalised with
+the sigma of ITS call, so scores agree with the sequential planner to rounding and u, v end in the same state.
 """
 import numpy as np
 import torch
@@ -44,9 +45,11 @@ def beam_actions(num_actions, lookahead=2, rollout_depth=12, rollout_policy="noo
 
 @torch.no_grad()
 def rollout_scores(z, transition, reward_predictor, num_actions, lookahead=2, rollout_depth=12,
-                   rollout_policy="noop", negative_positive_tradeoff=10.0, actions=None):
+                   rollout_policy="noop", negative_positive_tradeoff=10.0, actions=None, sigma_for_step=None):
     """Score of every plan of the beam started at each row of z: [Bz * A^lookahead] (plans of one start state are
-    contiguous).  With Bz = 1 this is the `cumulative_reward.sum(dim=1)` of main.py:476-486."""
+    contiguous).  With Bz = 1 this is the `cumulative_reward.sum(dim=1)` of main.py:476-486.
+    sigma_for_step(t) (optional) -> the `sigma=` rows of Transition.forward for rollout step t (one row per start
+    state: the folded planner)."""
     width = num_actions ** lookahead
     if actions is None:
         actions = beam_actions(num_actions, lookahead, rollout_depth, rollout_policy)
@@ -56,7 +59,8 @@ def rollout_scores(z, transition, reward_predictor, num_actions, lookahead=2, ro
     plan = actions.repeat(bz, 1)
     cumulative = reward_predictor(z).clone()
     for t in range(rollout_depth):
-        z = transition(z.detach(), onehot(plan[:, t], num_actions, z.device))
+        z = transition(z.detach(), onehot(plan[:, t], num_actions, z.device),
+                       sigma=None if sigma_for_step is None else sigma_for_step(t))
         cumulative += reward_predictor(z)
     cumulative[:, 0] *= negative_positive_tradeoff  # "caution" about the first (negative) reward channel
     return cumulative.sum(dim=1)
@@ -77,9 +81,17 @@ def choose_action(z, transition, reward_predictor, num_actions, rollout_depth=12
     """One decision of play() (main.py:356-368).  Returns (best action, [score of every action] as a CPU tensor)."""
     dev = z.device
     if fold_actions:
+        # sequential order: for every action a: 1 call on z, then rollout_depth calls on its beam -> call index
+        # a * (1 + rollout_depth) + k.  Folded call k serves all actions, one segment each.
+        per = 1 + rollout_depth
+        sig = transition.power_iterations(num_actions * per)
+
+        def rows(k):
+            return torch.stack([sig[a * per + k] for a in range(num_actions)])
         z_all = transition(z.repeat(num_actions, 1, 1, 1),
-                           onehot(torch.arange(num_actions, device=dev), num_actions, dev))
-        scores = rollout_scores(z_all, transition, reward_predictor, num_actions, 2, rollout_depth, rollout_policy)
+                           onehot(torch.arange(num_actions, device=dev), num_actions, dev), sigma=rows(0))
+        scores = rollout_scores(z_all, transition, reward_predictor, num_actions, 2, rollout_depth, rollout_policy,
+                                sigma_for_step=lambda t: rows(1 + t))
         rewards = scores.view(num_actions, -1).max(dim=1)[0]
     else:
         per_action = []

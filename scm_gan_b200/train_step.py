@@ -133,7 +133,8 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
             if len(segs) == 1:
                 outs = [tr(segs[0], acts[0], sigma=sig[rows[0]])]
             else:
-                outs = list(tr(torch.cat(segs, dim=0), torch.cat(acts, dim=0), sigma=sig[rows]).chunk(len(segs), dim=0))
+                outs = list(tr(torch.cat(segs, dim=0), torch.cat(acts, dim=0),
+                               sigma=torch.stack([sig[r] for r in rows])).chunk(len(segs), dim=0))
             if t <= T:
                 z = outs.pop(0)
             if do_dis and t <= n_cf:

@@ -525,12 +525,31 @@ def test_mpc_planner_vs_reference_golden_and_oracle():
     assert oscores[best].item() >= oscores.max().item() - 0.08 * abs(oscores.max().item()), (best, obest)
     for k, v in g["sn_after"].items():
         assert rel(nets["transition"].state_dict()[k].cpu(), v) < 1e-4
-    # folded variant: same decision from converged-enough spectral-norm state
+    # folded variant (all A candidates in one batch, each segment with the sigma of its own call): the same scores as
+    # the sequential order up to rounding-induced bit flips, and the same spectral-norm state afterwards
     for k, m in nets.items():
         m.load_state_dict(sd0[k])
     fbest, fscores = planner.choose_action(z0, nets["transition"], nets["reward_predictor"], cfg["A"], fold_actions=True)
-    assert report("folded plan scores", fscores, ref, 5e-2)
+    print("folded", [round(v, 3) for v in fscores.tolist()])
+    # an untrained model's latent probabilities sit next to the 0.5 threshold, so the differently rounded weights of
+    # the folded batch (Wbar/sigma_0 scaled per segment instead of Wbar/sigma_s) flip bits and the 13-step scores move
+    # by several per cent; the call accounting and the per-segment normalisation are checked exactly below
+    assert report("folded plan scores vs reference golden", fscores, ref, 8e-2)
     assert oscores[fbest].item() >= oscores.max().item() - 0.08 * abs(oscores.max().item()), (fbest, obest)
+    for k, v in g["sn_after"].items():   # same number of power iterations as the reference's 13 A calls
+        assert rel(nets["transition"].state_dict()[k].cpu(), v) < 1e-4
+    # per-segment sigma: the hidden activations of the folded first call (segment a normalised with the sigma of call
+    # 13 a) against single calls given that very sigma
+    for k, m in nets.items():
+        m.load_state_dict(sd0[k])
+    tr_net, A_ = nets["transition"], cfg["A"]
+    sig = tr_net.power_iterations(13 * A_)
+    eye = torch.eye(A_, device=DEV)
+    folded = tr_net(z0.repeat(A_, 1, 1, 1), eye, return_all=True, sigma=torch.stack([sig[13 * a] for a in range(A_)]))
+    for a in range(A_):
+        single = tr_net(z0, eye[a:a + 1], return_all=True, sigma=sig[13 * a])
+        for i in range(5):
+            assert report(f"folded segment {a} act{i + 1}", folded[i][a:a + 1], single[i], 3e-3)
     # the agent loop on the synthetic environment
     src = MovingDots(cfg["C"], cfg["H"], cfg["W"], cfg["A"], cfg["R"], seed=3)
     env = src.make_env()
