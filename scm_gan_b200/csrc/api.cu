@@ -4,6 +4,7 @@
 #include "conv_igemm.cuh"
 #include "conv_igemm_v2.cuh"
 #include "conv_igemm_v3.cuh"
+#include "conv_expand.cuh"
 #include "conv_wgrad.cuh"
 #include "conv_wgrad_v2.cuh"
 #include "conv_wgrad_narrow.cuh"
@@ -300,6 +301,70 @@ static int launch_igemm_v2(const scmgan_conv_desc* d, const IgemmParams& P, long
 
 static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st);
 
+// 16-input-channel layers writing a 64/128-channel plane (conv_expand.cuh).  Returns 1 when the shape does not qualify.
+static int launch_expand(const scmgan_conv_desc* d, cudaStream_t st) {
+    static const char* off = getenv("SCMGAN_NO_EXPAND");
+    if (off && atoi(off)) return 1;
+    if (d->cin != 16 || (d->n != 64 && d->n != 128) || !d->out || d->out_f32 || d->add) return 1;
+    if (d->W > 128 || d->W < 2 || d->H < 2) return 1;
+    ExpandParams P;
+    memset(&P, 0, sizeof(P));
+    P.B = d->B; P.H = d->H; P.W = d->W; P.Hp = d->H + 2; P.Wp = d->W + 2;
+    P.k = std::max(1, std::min(128 / d->W, d->H));
+    P.tiles_per_img = (d->H + P.k - 1) / P.k;
+    P.num_tiles = d->B * P.tiles_per_img;
+    P.n = d->n;
+    P.a = reinterpret_cast<const __nv_bfloat16*>(d->x); P.a_cs = d->x_cs; P.a_c_off = d->x_c_off;
+    P.copy_rows = (P.k + 2) * d->W;
+    P.copy_bytes = (P.copy_rows * 32 + 1023) & ~1023;
+    P.scale = d->scale; P.bias = d->bias; P.bias_n = d->bias_n > 0 ? std::min(d->bias_n, d->n) : d->n;
+    P.sample_bias = d->sample_bias; P.sample_scale = d->sample_scale;
+    P.act = d->act; P.slope = d->slope;
+    P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
+    P.wrap = d->wrap; P.gated = d->gate ? 1 : 0; P.gate_c_off = d->gate_c_off;
+    P.a_fmt = d->x_fmt; P.b_fmt = d->w_fmt; P.out_fmt = d->out_fmt;
+    if (d->act == SCMGAN_ACT_SIGMOID) return 1;
+    const int halves = d->n / 64;
+    const int b_bytes = (9 * d->n * 32 + 1023) & ~1023;
+    const int fixed = b_bytes + halves * 2 * 16384 * (P.gated ? 2 : 1) + kExpEpiWarps * 64 * 4 + 256 + 1024;
+    const int stages = std::min(4, (kSmemMax - fixed) / (3 * P.copy_bytes));
+    if (stages < 2) return 1;
+    P.num_a_stages = stages;
+    // the MMA of a tile reads 128 rows from row 2 W of a copy at most: keep that inside the A region
+    if ((2 * d->W + 128) * 32 > 3 * P.copy_bytes) return 1;
+    const int Hp = P.Hp, Wp = P.Wp;
+    CUtensorMap tb, tout, tgate;
+    {
+        uint64_t dims[2] = {16, uint64_t(9 * d->n)};
+        uint64_t str[1] = {32};
+        uint32_t box[2] = {16, uint32_t(d->n)};
+        int rc = encode_tmap_bf16(&tb, d->w, 2, dims, str, box, 32);
+        if (rc) return rc;
+    }
+    auto interior = [&](CUtensorMap* t, const void* base, int cs) -> int {
+        const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(base) + (size_t(Wp) + 1) * cs;
+        uint64_t dims[4] = {uint64_t(cs), uint64_t(d->W), uint64_t(d->H), uint64_t(d->B)};
+        uint64_t str[3] = {uint64_t(cs) * 2, uint64_t(Wp) * cs * 2, uint64_t(Hp) * Wp * cs * 2};
+        uint32_t box[4] = {64, uint32_t(d->W), uint32_t(P.k), 1};
+        return encode_tmap_bf16(t, bp, 4, dims, str, box, 128);
+    };
+    int rc = interior(&tout, d->out, d->out_cs);
+    if (rc) return rc;
+    if (P.gated) {
+        rc = interior(&tgate, d->gate, d->gate_cs);
+        if (rc) return rc;
+    } else {
+        tgate = tout;
+    }
+    const int smem = fixed + stages * 3 * P.copy_bytes;
+    SCM_OPT_IN_SMEM(conv3x3_expand_kernel, kSmemMax);
+    const int grid = std::min(P.num_tiles, num_sms());
+    conv3x3_expand_kernel<<<grid, kExpThreads, smem, st>>>(tb, tout, tgate, P);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     const int rc = conv_impl_inner(d, st);
     if (rc == SCM_OK && d->sample_out && d->rng_state && !d->uniforms) {
@@ -371,6 +436,9 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
             if (CK == 64) {
                 const int rc3 = launch_igemm_v3(d, P, rows, st);
                 if (rc3 <= 0) return rc3;
+            } else {
+                const int rce = launch_expand(d, st);
+                if (rce <= 0) return rce;
             }
             const int rc = CK == 64 ? launch_igemm_v2<64>(d, P, rows, st) : launch_igemm_v2<16>(d, P, rows, st);
             if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape does not fit -> first-generation kernel

@@ -436,10 +436,12 @@ def reward_forward(z, w1, b1, w2, b2, want_map):
     R = co // 3
     assert w1.shape[0] == RHID and co <= 16
     # hidden plane 128 channels wide for wgrad, only RHID computed (see decoder_forward)
-    wf1 = K.packed_weight(RHID, Lp, dev)
+    # the hidden layer is computed 64 channels wide (32 real + 32 zero weight rows): the 16-channel-input kernel
+    # (conv_expand.cuh) stores 64-channel halves
+    wf1 = K.packed_weight(2 * RHID, Lp, dev)
     wf2 = K.packed_weight(16, RHID, dev)
     wd1 = K.packed_weight(Lp, RHID, dev, K.GRAD_DTYPE)
-    wd2 = K.packed_weight(RHID, 16, dev, K.GRAD_DTYPE)
+    wd2 = K.packed_weight(2 * RHID, 16, dev, K.GRAD_DTYPE)
     K.pack_weights([_conv2d_fwd_job(w1, wf1), _conv2d_fwd_job(w2, wf2),
                     _conv2d_dgrad_job(w1, wd1), _conv2d_dgrad_job(w2, wd2)])
     zin = K.fwd_plane(B, H, W, Lp, dev)

@@ -118,6 +118,13 @@ CONV_CASES = [
     (2, 9, 11, 32, 16, False, 0),      # two 16-channel chunks (reward head)
     (2, 64, 64, 256, 128, True, 1),    # Cin = 256: CTA-pair kernel with streamed weights
     (2, 64, 64, 64, 128, False, 1),
+    # 16 input channels: image-aligned tiles + TMA-store epilogue (conv_expand.cuh)
+    (3, 64, 64, 16, 128, True, 1),
+    (2, 64, 64, 16, 64, False, 0),
+    (5, 15, 19, 16, 128, True, 1),     # k = 6 rows per tile, last tile of every image clipped (15 = 6 + 6 + 3)
+    (3, 15, 19, 16, 64, False, 1),
+    (2, 5, 128, 16, 128, True, 0),     # one image row per tile
+    (40, 16, 16, 16, 128, False, 1),   # more tiles than CTAs x pipeline depth
 ]
 
 
@@ -203,6 +210,51 @@ def test_conv_dgrad_epilogue(dt):
         ref = (gx + resid) * torch.where(actv > 0, 1.0, 0.01)
         got = plane_interior(out, 0, Ci)
         assert report(f"dgrad wrap={wrap}", got, ref, 4e-3)
+
+
+@pytest.mark.parametrize("dt", FWD_DTYPES)
+@pytest.mark.parametrize("shape", [(3, 64, 64, 128), (4, 15, 19, 64), (2, 16, 16, 128)])
+def test_expand_conv_sample_bias_scale_and_gated_dgrad(shape, dt):
+    """conv_expand.cuh beyond the plain cases: per-sample bias + per-sample scale (Transition conv1 with the batch
+    folded over several spectral-norm calls), and the gated data gradient (16-channel gradient plane -> 64/128
+    channels times lrelu'(saved activation), gate tile loaded by TMA)."""
+    _setup()
+    from scm_gan_b200 import kernels as K
+    B, H, W, Co = shape
+    Ci = 16
+    torch.manual_seed(21)
+    x = rnd(torch.randn(B, Ci, H, W, device=DEV), dt)
+    w = rnd(torch.randn(Co, Ci, 3, 3, device=DEV) / 12.0, dt)
+    sb = torch.randn(B, Co, device=DEV)
+    ss = torch.rand(B, device=DEV) + 0.5
+    for wrap in (True, False):
+        xp = make_plane(x, Ci, 0, wrap, dt)
+        wp = pack_conv_weight(w, Co, Ci, dtype=dt)
+        out = torch.full((B, H + 2, W + 2, 2 * Co), float("nan"), dtype=dt, device=DEV)
+        K.conv3x3(xp, wp, B, H, W, cin=Ci, sample_bias=sb, sample_scale=ss, act=1, out=out, out_c_off=Co, wrap=wrap)
+        ref = F.leaky_relu(ref_conv(x, w, wrap) * ss.view(B, 1, 1, 1) + sb.view(B, Co, 1, 1))
+        got = plane_interior(out, Co, Co)
+        assert report(f"expand fwd {shape} wrap={wrap} {dt}", got, ref, OUT_TOL[dt])
+        full = out[:, :, :, Co:].permute(0, 3, 1, 2).float()
+        assert torch.equal(full, ref_plane(got, wrap)), "halo mismatch"
+        assert torch.isnan(out[:, :, :, :Co].float()).all()
+    # gated dgrad: bf16 gradient plane and weights, gate read from a forward plane in `dt`
+    dy = bf(torch.randn(B, Ci, H, W, device=DEV))
+    wg = bf(torch.randn(Ci, Co, 3, 3, device=DEV) / 12.0)     # Conv2d weight [co=16][ci=Co]
+    actv = rnd(torch.randn(B, Co, H, W, device=DEV), dt)
+    for wrap in (True, False):
+        dyp = make_plane(dy, Ci, 0, wrap)
+        ap = make_plane(actv, Co + 16, 16, wrap, dt)
+        wd = pack_conv_weight(wg, Co, Ci, dgrad=True)
+        out = K.new_plane(B, H, W, Co, DEV)
+        K.conv3x3(dyp, wd, B, H, W, cin=Ci, out=out, wrap=wrap, gate=ap, gate_c_off=16, sample_scale=ss, dgrad=True)
+        xin = torch.zeros(B, Co, H, W, device=DEV, requires_grad=True)
+        (gx,) = torch.autograd.grad(ref_conv(xin, wg, wrap), xin, dy)
+        ref = gx * ss.view(B, 1, 1, 1) * torch.where(actv > 0, 1.0, 0.01)
+        got = plane_interior(out, 0, Co)
+        assert report(f"expand gated dgrad {shape} wrap={wrap} {dt}", got, ref, 4e-3)
+        full = out.permute(0, 3, 1, 2).float()
+        assert torch.equal(full, ref_plane(got, wrap)), "halo mismatch"
 
 
 WGRAD_CASES = [
