@@ -323,10 +323,14 @@ static int launch_expand(const scmgan_conv_desc* d, cudaStream_t st) {
     P.out = reinterpret_cast<__nv_bfloat16*>(d->out); P.out_cs = d->out_cs; P.out_c_off = d->out_c_off;
     P.wrap = d->wrap; P.gated = d->gate ? 1 : 0; P.gate_c_off = d->gate_c_off;
     P.a_fmt = d->x_fmt; P.b_fmt = d->w_fmt; P.out_fmt = d->out_fmt;
+    {
+        const char* dbg = getenv("SCMGAN_DEBUG");
+        P.debug = dbg ? atoi(dbg) : 0;
+    }
     if (d->act == SCMGAN_ACT_SIGMOID) return 1;
     const int halves = d->n / 64;
     const int b_bytes = (9 * d->n * 32 + 1023) & ~1023;
-    const int fixed = b_bytes + halves * 2 * 16384 * (P.gated ? 2 : 1) + kExpEpiWarps * 64 * 4 + 256 + 1024;
+    const int fixed = b_bytes + halves * 2 * 16384 * (P.gated ? 2 : 1) + kExpEpiWarps * 32 * 4 + 256 + 1024;
     const int stages = std::min(4, (kSmemMax - fixed) / (3 * P.copy_bytes));
     if (stages < 2) return 1;
     P.num_a_stages = stages;
@@ -930,6 +934,13 @@ static int wgrad_dispatch(const scmgan_wgrad_desc* d, scmgan_stream_t stream) {
     }
     set_error("wgrad: one of cout (%d) / cin (%d) must be a multiple of 128", d->cout, d->cin);
     return SCM_EUNSUPPORTED;
+}
+
+/* profiling aid (not part of the documented ABI): copies the in-kernel timeline of conv_expand.cuh to the host */
+int scmgan_debug_expand_timeline(unsigned long long* out_host, int n) {
+    SCM_CUDA(cudaDeviceSynchronize());
+    SCM_CUDA(cudaMemcpyFromSymbol(out_host, g_exp_dbg, sizeof(unsigned long long) * std::min(n, 3 * 16 * 8)));
+    return SCM_OK;
 }
 
 long long scmgan_wgrad_workspace_bytes(void) {
