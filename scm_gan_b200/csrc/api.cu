@@ -13,6 +13,7 @@
 #include "host_util.cuh"
 
 #include <algorithm>
+#include <utility>
 #include <atomic>
 #include <mutex>
 #include <stdlib.h>
@@ -111,6 +112,30 @@ static cudaError_t opt_in_smem(Kernel kernel, std::atomic<unsigned long long>& d
         SCM_CUDA(opt_in_smem(kernel, _done, bytes));                     \
     } while (0)
 
+
+// Every kernel of this library is launched with programmatic dependent launch (PDL) enabled and starts with
+// griddepcontrol.wait (pdl_sync() in ptx.cuh) before its first access to global memory: the next kernel of the
+// stream is scheduled while the previous one drains, its prologue (barrier init, TMEM allocation, tensor-map
+// prefetch) and the launch latency overlap the predecessor's tail, and it proceeds the moment the predecessor's
+// memory operations are visible.  Inside a captured CUDA graph the launches become programmatic dependency edges.
+// SCMGAN_NO_PDL=1 switches the attribute off (plain stream order).
+static bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("SCMGAN_NO_PDL"); return !(e && atoi(e)); }();
+    return on;
+}
+template <typename... KArgs, typename... Args>
+static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors are picked up by cudaGetLastError()
+}
+
 constexpr int kSmemBudget = 200 * 1024;  // tiles; barriers/alignment slack on top (<= 227 KB per CTA)
 
 template <int CK>
@@ -124,7 +149,7 @@ static int launch_igemm(const CUtensorMap& ta, const CUtensorMap& tb, const Igem
     const int smem = stages * stage_bytes + 1024 + 256;
     SCM_OPT_IN_SMEM(conv3x3_igemm_kernel<CK>, 227 * 1024);
     const int grid = std::min(P.num_tiles, num_sms());
-    conv3x3_igemm_kernel<CK><<<grid, kIgemmThreads, smem, st>>>(ta, tb, P, stages);
+    launch_k(conv3x3_igemm_kernel<CK>, dim3(grid), dim3(kIgemmThreads), size_t(smem), st, ta, tb, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -137,7 +162,7 @@ template <int CK, int TPG>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& P, const IgemmV2Geom& G,
                           int gx, int nsplit, int smem, cudaStream_t st) {
     SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG>), kSmemMax);
-    conv3x3_igemm_v2_kernel<CK, TPG><<<dim3(gx, nsplit), v2_threads<CK>(), smem, st>>>(ta, tb, P, G);
+    launch_k(conv3x3_igemm_v2_kernel<CK, TPG>, dim3(dim3(gx, nsplit)), dim3(v2_threads<CK>()), size_t(smem), st, ta, tb, P, G);
     SCM_CUDA(cudaGetLastError());
     return SCM_OK;
 }
@@ -202,10 +227,10 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
     const int smem = fixed + G.num_stages * G.a_stage_bytes;
     if (tpg == 9) {
         SCM_OPT_IN_SMEM((conv3x3_igemm_v3_kernel<64, 9>), kSmemMax);
-        conv3x3_igemm_v3_kernel<64, 9><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
+        launch_k(conv3x3_igemm_v3_kernel<64, 9>, dim3(2 * pairs), dim3(kV2Threads), size_t(smem), st, ta, tb, P, G);
     } else {
         SCM_OPT_IN_SMEM((conv3x3_igemm_v3_kernel<64, 3>), kSmemMax);
-        conv3x3_igemm_v3_kernel<64, 3><<<2 * pairs, kV2Threads, smem, st>>>(ta, tb, P, G);
+        launch_k(conv3x3_igemm_v3_kernel<64, 3>, dim3(2 * pairs), dim3(kV2Threads), size_t(smem), st, ta, tb, P, G);
     }
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
@@ -363,7 +388,7 @@ static int launch_expand(const scmgan_conv_desc* d, cudaStream_t st) {
     const int smem = fixed + stages * 3 * P.copy_bytes;
     SCM_OPT_IN_SMEM(conv3x3_expand_kernel, kSmemMax);
     const int grid = std::min(P.num_tiles, num_sms());
-    conv3x3_expand_kernel<<<grid, kExpThreads, smem, st>>>(tb, tout, tgate, P);
+    launch_k(conv3x3_expand_kernel, dim3(grid), dim3(kExpThreads), size_t(smem), st, tb, tout, tgate, P);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -374,7 +399,7 @@ static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     if (rc == SCM_OK && d->sample_out && d->rng_state && !d->uniforms) {
         // one Philox counter per 4 elements
         const unsigned long long n = ((unsigned long long)d->B * d->n_valid * d->H * d->W + 3) / 4;
-        rng_advance_kernel<<<1, 1, 0, st>>>(d->rng_state, n);
+        launch_k(rng_advance_kernel, dim3(1), dim3(1), size_t(0), st, d->rng_state, n);
         SCM_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -488,11 +513,9 @@ static int launch_reduce(const scmgan_wgrad_reduce_job& j, cudaStream_t st) {
     const int total = 9 * j.n * 32;
     const int blocks = (total + 31) / 32 + (j.ws_bias && j.db ? 1 : 0);
     if (j.lanes == 32)
-        wgrad_reduce_kernel<32><<<blocks, dim3(32, 32), 0, st>>>(j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip,
-                                                                 j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
+        launch_k(wgrad_reduce_kernel<32>, dim3(blocks), dim3(dim3(32, 32)), size_t(0), st, j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip, j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
     else
-        wgrad_reduce_kernel<8><<<blocks, dim3(32, 8), 0, st>>>(j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip,
-                                                               j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
+        launch_k(wgrad_reduce_kernel<8>, dim3(blocks), dim3(dim3(32, 8)), size_t(0), st, j.ws, j.splits, j.n, j.g, j.g_sm, j.g_sn, j.g_st, j.flip, j.m_valid, j.n_valid, j.scale, j.ws_bias, j.db);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -565,7 +588,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     }
     SCM_OPT_IN_SMEM(conv3x3_wgrad_v2_kernel, kSmemMax);
     const int smem = stages * stage_bytes + 1024 + 1024;
-    conv3x3_wgrad_v2_kernel<<<dim3(splits, 3), kWgradThreads, smem, st>>>(tp, tq, P, stages);
+    launch_k(conv3x3_wgrad_v2_kernel, dim3(dim3(splits, 3)), dim3(kWgradThreads), size_t(smem), st, tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return emit_reduce(ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, P.ws_bias, db,
@@ -640,9 +663,9 @@ static int wgrad_launch_narrow(bool x_is_wide, int B, int H, int W, const void* 
     SCM_OPT_IN_SMEM(conv3x3_wgrad_narrow_kernel, kSmemMax);
     const int smem = stages * stage_bytes + 1024 + 1024;
     if (x_is_wide)
-        conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tx, tdy, P, stages);
+        launch_k(conv3x3_wgrad_narrow_kernel, dim3(dim3(splits, m_blocks)), dim3(kWgradThreads), size_t(smem), st, tx, tdy, P, stages);
     else
-        conv3x3_wgrad_narrow_kernel<<<dim3(splits, m_blocks), kWgradThreads, smem, st>>>(tdy, tx, P, stages);
+        launch_k(conv3x3_wgrad_narrow_kernel, dim3(dim3(splits, m_blocks)), dim3(kWgradThreads), size_t(smem), st, tdy, tx, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     for (int mb = 0; mb < m_blocks; ++mb) {
@@ -737,7 +760,7 @@ static int wgrad_launch(int B, int H, int W, const void* pp, int p_cs, int p_c_o
 
     SCM_OPT_IN_SMEM(conv3x3_wgrad_kernel, 227 * 1024);
     const int smem = stages * stage_bytes + 1024 + 256;
-    conv3x3_wgrad_kernel<<<dim3(splits, groups), kWgradThreads, smem, st>>>(tp, tq, P, stages);
+    launch_k(conv3x3_wgrad_kernel, dim3(dim3(splits, groups)), dim3(kWgradThreads), size_t(smem), st, tp, tq, P, stages);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     if (P.ws) return emit_reduce(P.ws, splits, n, g, g_sm, g_sn, g_st, flip, m_valid, n_valid, scale, nullptr, nullptr, 8, st);
@@ -765,8 +788,7 @@ int scmgan_pack_nchw(const float* src, long long src_bstride, int C, int B, int 
     const long long rows = (long long)B * (H + 2) * (W + 2);
     const int threads = 128;
     const long long blocks = (rows + threads - 1) / threads;
-    pack_nchw_to_plane_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-        src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap, sig, fmt);
+    launch_k(pack_nchw_to_plane_kernel, dim3((unsigned)blocks), dim3(threads), size_t(0), (cudaStream_t)stream, src, src_bstride, C, B, H, W, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, c_pad, wrap, sig, fmt);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -777,8 +799,7 @@ int scmgan_pack_coords(void* dst_plane, int Cs, int c_off, int B, int H, int W, 
     SCM_REQUIRE(dst_plane && B > 0 && H > 0 && W > 0, "pack_coords: bad arguments");
     SCM_REQUIRE(c_off % 2 == 0 && c_off + 2 <= Cs, "pack_coords: bad channel window (Cs=%d off=%d)", Cs, c_off);
     const long long total = (long long)B * H * W;
-    pack_coords_kernel<<<unsigned((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, B, H, W, fmt);
+    launch_k(pack_coords_kernel, dim3(unsigned((total + 255) / 256)), dim3(256), size_t(0), (cudaStream_t)stream, reinterpret_cast<__nv_bfloat16*>(dst_plane), Cs, c_off, B, H, W, fmt);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -807,7 +828,7 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t 
         }
         const int threads = 256;
         const int bx = int(std::min<long long>((max_total + threads - 1) / threads, 296));
-        pack_weights_kernel<<<dim3(bx, J.count), threads, 0, (cudaStream_t)stream>>>(J);
+        launch_k(pack_weights_kernel, dim3(dim3(bx, J.count)), dim3(threads), size_t(0), (cudaStream_t)stream, J);
         SCM_CUDA(cudaGetLastError());
     ++g_launches;
     }
@@ -960,8 +981,7 @@ int scmgan_plane_colsum(const void* plane, int Cs, int c_off, int n, int B, int 
     int chunks = std::max(1, std::min((hw + 255) / 256, std::max(1, 4 * num_sms() / B)));
     const int rows_per_block = (hw + chunks - 1) / chunks;
     chunks = (hw + rows_per_block - 1) / rows_per_block;
-    plane_colsum_kernel<<<dim3(chunks, B), threads, lanes * n * sizeof(float), (cudaStream_t)stream>>>(
-        reinterpret_cast<const __nv_bfloat16*>(plane), Cs, c_off, n, B, H, W, S, db, rows_per_block);
+    launch_k(plane_colsum_kernel, dim3(dim3(chunks, B)), dim3(threads), size_t(lanes * n * sizeof(float)), (cudaStream_t)stream, reinterpret_cast<const __nv_bfloat16*>(plane), Cs, c_off, n, B, H, W, S, db, rows_per_block);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1007,8 +1027,7 @@ int scmgan_spectral_norm_fwd_n(int count, const scmgan_sn_layer* layers, int ite
             const int smem = int(sizeof(float)) * (Gm.rows_max * (2 + kSnCluster) + Gm.cpc_max * (1 + gmax) +
                                                    kSnCluster + 33);
             if (smem <= 48 * 1024) {
-                sn_power_iter_cluster_kernel<<<count * kSnCluster, 1024, smem, (cudaStream_t)stream>>>(L, Gm, iters,
-                                                                                                      sigma_stride);
+                launch_k(sn_power_iter_cluster_kernel, dim3(count * kSnCluster), dim3(1024), size_t(smem), (cudaStream_t)stream, L, Gm, iters, sigma_stride);
                 SCM_CUDA(cudaGetLastError());
                 ++g_launches;
                 return SCM_OK;
@@ -1019,7 +1038,7 @@ int scmgan_spectral_norm_fwd_n(int count, const scmgan_sn_layer* layers, int ite
     for (int it = 0; it < iters; ++it) {  // single-CTA fallback: one launch per iteration
         SnLayers Li = L;
         for (int i = 0; i < count; ++i) Li.layer[i].sigma = L.layer[i].sigma + (long long)it * sigma_stride;
-        sn_power_iter_kernel<<<count, 1024, max_smem, (cudaStream_t)stream>>>(Li);
+        launch_k(sn_power_iter_kernel, dim3(count), dim3(1024), size_t(max_smem), (cudaStream_t)stream, Li);
         SCM_CUDA(cudaGetLastError());
         ++g_launches;
     }
@@ -1036,10 +1055,10 @@ int scmgan_spectral_norm_bwd(int count, const scmgan_sn_bwd_layer* layers, scmga
         SCM_REQUIRE(s.g && s.wbar && s.u && s.v && s.sigma && s.dot && s.out, "spectral_norm_bwd: bad layer %d", i);
         L.layer[i] = SnBwdLayer{s.g, s.wbar, s.u, s.v, s.sigma, s.dot, s.out, s.rows, s.cols, s.accumulate, s.sigma2};
     }
-    sn_bwd_dot_kernel<<<dim3(96, count), 256, 0, (cudaStream_t)stream>>>(L);
+    launch_k(sn_bwd_dot_kernel, dim3(dim3(96, count)), dim3(256), size_t(0), (cudaStream_t)stream, L);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    sn_bwd_apply_kernel<<<dim3(256, count), 256, 0, (cudaStream_t)stream>>>(L);
+    launch_k(sn_bwd_apply_kernel, dim3(dim3(256, count)), dim3(256), size_t(0), (cudaStream_t)stream, L);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1049,8 +1068,7 @@ int scmgan_action_bias(const float* wbar, const float* sigma, const float* bias,
                        int L, int A, float* out, scmgan_stream_t stream) {
     SCM_REQUIRE(wbar && act && out && B > 0 && Cout > 0 && A > 0, "action_bias: bad arguments");
     const int total = B * Cout;
-    action_bias_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(wbar, sigma, bias, act, B, Cout, L, A,
-                                                                             out);
+    launch_k(action_bias_kernel, dim3((total + 127) / 128), dim3(128), size_t(0), (cudaStream_t)stream, wbar, sigma, bias, act, B, Cout, L, A, out);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1060,7 +1078,7 @@ int scmgan_action_wgrad(const float* S, const float* act, int B, int Cout, int L
                         scmgan_stream_t stream) {
     SCM_REQUIRE(S && act && g && B > 0 && Cout > 0 && A > 0, "action_wgrad: bad arguments");
     const int total = Cout * A;
-    action_wgrad_kernel<<<(total + 127) / 128, 128, 0, (cudaStream_t)stream>>>(S, act, B, Cout, L, A, g);
+    launch_k(action_wgrad_kernel, dim3((total + 127) / 128), dim3(128), size_t(0), (cudaStream_t)stream, S, act, B, Cout, L, A, g);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1071,9 +1089,7 @@ int scmgan_masked_mse_seq(const float* pred, const float* target, long long targ
                           float scale, const float* scale_dev, float* loss, float* loss_raw, float* dpred,
                           scmgan_stream_t stream) {
     SCM_REQUIRE(pred && target && loss && T > 0 && B > 0 && R > 0, "masked_mse: bad arguments");
-    masked_mse_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, target_bstride, target_tstride, mask,
-                                                          mask_bstride, mask_tstride, T, B, R, scale, scale_dev, loss,
-                                                          loss_raw, dpred);
+    launch_k(masked_mse_kernel, dim3(1), dim3(256), size_t(0), (cudaStream_t)stream, pred, target, target_bstride, target_tstride, mask, mask_bstride, mask_tstride, T, B, R, scale, scale_dev, loss, loss_raw, dpred);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1094,9 +1110,7 @@ int scmgan_bce_logits_seq(const float* x, const float* y, long long y_bstride, l
     const int threads = 256;
     int bx = int(std::min<long long>((per + threads * 4 - 1) / (threads * 4), std::max(1, 8 * num_sms() / (T * B))));
     bx = std::max(bx, 1);
-    bce_logits_kernel<<<dim3(bx, T * B), threads, 0, (cudaStream_t)stream>>>(x, y, y_bstride, y_tstride, mask,
-                                                                            mask_bstride, mask_tstride, T, B, per,
-                                                                            loss_t, dx);
+    launch_k(bce_logits_kernel, dim3(dim3(bx, T * B)), dim3(threads), size_t(0), (cudaStream_t)stream, x, y, y_bstride, y_tstride, mask, mask_bstride, mask_tstride, T, B, per, loss_t, dx);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1111,7 +1125,7 @@ int scmgan_reward_head_fwd(const float* y2, int B, int R, int H, int W, float* r
                            scmgan_stream_t stream) {
     SCM_REQUIRE(y2 && r && B > 0 && R > 0 && 3 * R <= 16 && H >= 5 && W >= 5, "reward_head_fwd: bad arguments");
     const int h2 = (H - 5) / 2 + 1, w2 = (W - 5) / 2 + 1;
-    reward_head_fwd_kernel<<<dim3(B, R), 128, 0, (cudaStream_t)stream>>>(y2, B, R, H, W, h2, w2, r, map);
+    launch_k(reward_head_fwd_kernel, dim3(dim3(B, R)), dim3(128), size_t(0), (cudaStream_t)stream, y2, B, R, H, W, h2, w2, r, map);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1123,8 +1137,7 @@ int scmgan_reward_head_bwd(const float* y2, const float* dr, int B, int R, int H
                 "reward_head_bwd: bad arguments");
     const int h2 = (H - 5) / 2 + 1, w2 = (W - 5) / 2 + 1;
     const long long rows = (long long)B * (H + 2) * (W + 2);
-    reward_head_bwd_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        y2, dr, B, R, H, W, h2, w2, reinterpret_cast<__nv_bfloat16*>(d2_plane));
+    launch_k(reward_head_bwd_kernel, dim3((unsigned)((rows + 127) / 128)), dim3(128), size_t(0), (cudaStream_t)stream, y2, dr, B, R, H, W, h2, w2, reinterpret_cast<__nv_bfloat16*>(d2_plane));
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1134,10 +1147,10 @@ int scmgan_cf_loss_fwd(const float* za, const float* zb, const float* unswapped,
                        int HW, int mode, float lambda, float* rowmean, float* loss, scmgan_stream_t stream) {
     SCM_REQUIRE(za && zb && mask && rowmean && loss && B > 0 && L > 0 && L <= 64 && HW > 0, "cf_loss_fwd: bad arguments");
     SCM_REQUIRE(mode == 1 || (mode == 0 && unswapped), "cf_loss_fwd: mode 0 needs the unswapped-factor map");
-    cf_rowmean_kernel<<<B * L, 256, 0, (cudaStream_t)stream>>>(za, zb, HW, rowmean);
+    launch_k(cf_rowmean_kernel, dim3(B * L), dim3(256), size_t(0), (cudaStream_t)stream, za, zb, HW, rowmean);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    cf_loss_fwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(rowmean, unswapped, mask, B, L, mode, lambda, loss);
+    launch_k(cf_loss_fwd_kernel, dim3(1), dim3(256), size_t(0), (cudaStream_t)stream, rowmean, unswapped, mask, B, L, mode, lambda, loss);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1149,8 +1162,7 @@ int scmgan_cf_loss_bwd(const float* za, const float* zb, const float* unswapped,
     SCM_REQUIRE(za && zb && mask && rowmean && gscale && (dza || dzb) && B > 0 && L > 0 && HW > 0,
                 "cf_loss_bwd: bad arguments");
     const int bx = std::max(1, std::min((HW + 255) / 256, 8));
-    cf_loss_bwd_kernel<<<dim3(bx, B, L), 256, 0, (cudaStream_t)stream>>>(za, zb, unswapped, mask, rowmean, gscale, B, L,
-                                                                        HW, mode, lambda, dza, dzb);
+    launch_k(cf_loss_bwd_kernel, dim3(dim3(bx, B, L)), dim3(256), size_t(0), (cudaStream_t)stream, za, zb, unswapped, mask, rowmean, gscale, B, L, HW, mode, lambda, dza, dzb);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1160,7 +1172,7 @@ int scmgan_transition_tail(const float* x, const float* uniforms, long long n, f
                            scmgan_stream_t stream) {
     SCM_REQUIRE(x && z && n > 0, "transition_tail: bad arguments");
     const int blocks = int(std::min<long long>((n + 255) / 256, 4LL * num_sms()));
-    transition_tail_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, uniforms, n, p, z);
+    launch_k(transition_tail_kernel, dim3(blocks), dim3(256), size_t(0), (cudaStream_t)stream, x, uniforms, n, p, z);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1205,7 +1217,7 @@ int scmgan_gru_conv_sweep_fwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t s
         return SCM_EUNSUPPORTED;
     }
     SCM_OPT_IN_SMEM(csrn_sweep_fwd_kernel, kSmemMax);
-    csrn_sweep_fwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
+    launch_k(csrn_sweep_fwd_kernel, dim3(P.B), dim3(256), size_t(smem), (cudaStream_t)stream, P);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1221,7 +1233,7 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t s
         return SCM_EUNSUPPORTED;
     }
     SCM_OPT_IN_SMEM(csrn_sweep_bwd_kernel, kSmemMax);
-    csrn_sweep_bwd_kernel<<<P.B, 256, smem, (cudaStream_t)stream>>>(P);
+    launch_k(csrn_sweep_bwd_kernel, dim3(P.B), dim3(256), size_t(smem), (cudaStream_t)stream, P);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1230,10 +1242,10 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* d, scmgan_stream_t s
 int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream) {
     SCM_REQUIRE(out && rng_state && n > 0, "philox_uniform: bad arguments");
     const long long blocks4 = (n + 3) / 4;
-    philox_fill_kernel<<<unsigned((blocks4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, rng_state);
+    launch_k(philox_fill_kernel, dim3(unsigned((blocks4 + 255) / 256)), dim3(256), size_t(0), (cudaStream_t)stream, out, n, rng_state);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
-    rng_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(rng_state, (unsigned long long)blocks4);
+    launch_k(rng_advance_kernel, dim3(1), dim3(1), size_t(0), (cudaStream_t)stream, rng_state, (unsigned long long)blocks4);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;
@@ -1260,7 +1272,7 @@ int scmgan_clip_adam(int count, const scmgan_adam_chunk* chunks, float lr, float
             A.bc2_sqrt = sqrtf(1.f - powf(beta2, float(step)));
         }
         const int bx = std::max(1, std::min((max_n + 1023) / 1024, 64));
-        clip_adam_kernel<<<dim3(bx, A.count), 256, 0, (cudaStream_t)stream>>>(A);
+        launch_k(clip_adam_kernel, dim3(dim3(bx, A.count)), dim3(256), size_t(0), (cudaStream_t)stream, A);
         SCM_CUDA(cudaGetLastError());
     ++g_launches;
     }

@@ -159,6 +159,7 @@ conv3x3_expand_kernel(const __grid_constant__ CUtensorMap tmap_b, const __grid_c
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

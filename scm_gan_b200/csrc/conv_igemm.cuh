@@ -144,6 +144,7 @@ conv3x3_igemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_co
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

@@ -93,6 +93,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kEpiWarps) s_bias[i] = (P.bias && n0 + i < P.bias_n) ? P.bias[n0 + i] : 0.f;
     }

@@ -65,6 +65,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_alloc_pair(tmem_slot, 512);
         tmem_relinquish_pair();
     }
+    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
     if (warp >= 2) {
         for (int i = threadIdx.x - 64; i < n_full; i += 32 * kV2EpiWarps) s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
     }

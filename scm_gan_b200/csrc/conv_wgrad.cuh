@@ -116,6 +116,7 @@ conv3x3_wgrad_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid_co
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_sync();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -244,6 +245,7 @@ __global__ void __launch_bounds__(32 * LANES) wgrad_reduce_kernel(const float* _
                                                             long long g_st, int flip, int m_valid, int n_valid,
                                                             float scale, const float* __restrict__ ws_bias,
                                                             float* __restrict__ db) {
+    pdl_sync();
     __shared__ float4 part[LANES][32];
     constexpr int lanes = LANES;
     const int total4 = 9 * n * 32;  // float4 groups per split
@@ -288,6 +290,7 @@ __global__ void __launch_bounds__(32 * LANES) wgrad_reduce_kernel(const float* _
 // db[m] += scale * sum_split ws_bias[split][m]   (bias gradient partials of conv_wgrad_v2.cuh)
 __global__ void wgrad_bias_reduce_kernel(const float* __restrict__ ws_bias, int splits, float* __restrict__ db,
                                          int m_valid, float scale) {
+    pdl_sync();
     const int m = threadIdx.x;
     if (m >= m_valid) return;
     float acc = 0.f;

@@ -85,6 +85,7 @@ conv3x3_wgrad_narrow_kernel(const __grid_constant__ CUtensorMap tmap_x, const __
         tmem_alloc(tmem_slot, 256);
         tmem_relinquish();
     }
+    pdl_sync();
     if (P.with_ones) {  // tile 9 of every stage: bf16 1.0 (never touched by TMA)
         for (int s = 0; s < num_stages; ++s) {
             uint32_t* ones = reinterpret_cast<uint32_t*>(smem + size_t(s) * stage_bytes + a_bytes + 9 * b_tile_bytes);

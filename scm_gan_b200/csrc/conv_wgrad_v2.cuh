@@ -80,6 +80,7 @@ conv3x3_wgrad_v2_kernel(const __grid_constant__ CUtensorMap tmap_p, const __grid
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
+    pdl_sync();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();

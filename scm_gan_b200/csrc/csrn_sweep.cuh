@@ -35,6 +35,7 @@ struct CsrnSweepParams {
 __device__ __forceinline__ float csrn_sigmoid(float v) { return 1.f / (1.f + expf(-v)); }
 
 __global__ void __launch_bounds__(256) csrn_sweep_fwd_kernel(const CsrnSweepParams P) {
+    pdl_sync();
     extern __shared__ float sm[];
     const int C = P.C, n = P.n, nC = n * C;
     float* xs = sm;            // [n][C]
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(256) csrn_sweep_fwd_kernel(const CsrnSweepPara
 }
 
 __global__ void __launch_bounds__(256) csrn_sweep_bwd_kernel(const CsrnSweepParams P) {
+    pdl_sync();
     extern __shared__ float sm[];
     const int C = P.C, n = P.n, nC = n * C;
     float* xs = sm;             // x_i

@@ -14,6 +14,7 @@ namespace scm {
 __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long long src_bstride, int C, int B, int H,
                                           int W, __nv_bfloat16* __restrict__ dst, int Cs, int c_off, int c_pad,
                                           int wrap, const float* __restrict__ sig, int fmt) {
+    pdl_sync();
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,6 +59,7 @@ __global__ void pack_nchw_to_plane_kernel(const float* __restrict__ src, long lo
 // CoordConv coordinate channels: x coordinate -1 + 2w/W at channel c_off, y coordinate -1 + 2h/H at c_off + 1 of every
 // interior pixel (reference coordconv.py:10-14).
 __global__ void pack_coords_kernel(__nv_bfloat16* __restrict__ dst, int Cs, int c_off, int B, int H, int W, int fmt) {
+    pdl_sync();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * H * W) return;
     const int w = int(i % W), h = int((i / W) % H), b = int(i / ((long long)W * H));
@@ -89,6 +91,7 @@ struct PackJobs {
 };
 
 __global__ void pack_weights_kernel(const __grid_constant__ PackJobs jobs) {
+    pdl_sync();
     const PackJob& J = jobs.job[blockIdx.y];
     const long long total = 9LL * J.n_pad * J.k_pad;
     const float inv = J.sigma ? 1.f / __ldg(J.sigma) : 1.f;
@@ -152,6 +155,7 @@ __device__ __forceinline__ float block_sum(float x, float* red /*[33]*/) {
 }
 
 __global__ void __launch_bounds__(1024, 1) sn_power_iter_kernel(const __grid_constant__ SnLayers L) {
+    pdl_sync();
     extern __shared__ float sn_smem[];  // [cols] t/v  + [rows] s/u + 33
     const SnLayer& Y = L.layer[blockIdx.x];
     const int R = Y.rows, C = Y.cols;
@@ -217,6 +221,7 @@ struct SnClusterGeom {
 __global__ void __cluster_dims__(kSnCluster, 1, 1) __launch_bounds__(1024, 1)
 sn_power_iter_cluster_kernel(const __grid_constant__ SnLayers L, const __grid_constant__ SnClusterGeom Gm, int iters,
                              int sigma_stride) {
+    pdl_sync();
     extern __shared__ float sn_smem[];
     const int li = blockIdx.x / kSnCluster;
     const uint32_t rank = cluster_ctarank();
@@ -334,6 +339,7 @@ struct SnBwdLayers {
 };
 
 __global__ void sn_bwd_dot_kernel(const __grid_constant__ SnBwdLayers L) {
+    pdl_sync();
     __shared__ float red[33];
     const SnBwdLayer& Y = L.layer[blockIdx.y];
     const long long total = (long long)Y.rows * Y.cols;
@@ -346,6 +352,7 @@ __global__ void sn_bwd_dot_kernel(const __grid_constant__ SnBwdLayers L) {
 }
 
 __global__ void sn_bwd_apply_kernel(const __grid_constant__ SnBwdLayers L) {
+    pdl_sync();
     const SnBwdLayer& Y = L.layer[blockIdx.y];
     const long long total = (long long)Y.rows * Y.cols;
     const float sig = __ldg(Y.sigma);
@@ -366,6 +373,7 @@ __global__ void sn_bwd_apply_kernel(const __grid_constant__ SnBwdLayers L) {
 // ----------------------------------------------------------------------------------------------
 __global__ void plane_colsum_kernel(const __nv_bfloat16* __restrict__ plane, int Cs, int c_off, int n, int B, int H,
                                     int W, float* __restrict__ S, float* __restrict__ db, int rows_per_block) {
+    pdl_sync();
     extern __shared__ float cs_smem[];  // [row lanes][n]
     const int Hp = H + 2, Wp = W + 2;
     const int groups = n >> 3;
@@ -405,6 +413,7 @@ __global__ void plane_colsum_kernel(const __nv_bfloat16* __restrict__ plane, int
 __global__ void action_bias_kernel(const float* __restrict__ wbar, const float* __restrict__ sigma,
                                    const float* __restrict__ bias, const float* __restrict__ act, int B, int Cout,
                                    int L, int A, float* __restrict__ out) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Cout) return;
     const int b = i / Cout, n = i - b * Cout;
@@ -425,6 +434,7 @@ __global__ void action_bias_kernel(const float* __restrict__ wbar, const float* 
 
 __global__ void action_wgrad_kernel(const float* __restrict__ S, const float* __restrict__ act, int B, int Cout,
                                     int L, int A, float* __restrict__ g) {
+    pdl_sync();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= Cout * A) return;
     const int n = i / A, a = i - n * A;
@@ -449,6 +459,7 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
                                   long long y_tstride, const float* __restrict__ mask, long long m_bstride,
                                   long long m_tstride, int T, int B, long long per, float* __restrict__ loss_t,
                                   float* __restrict__ dx) {
+    pdl_sync();
     __shared__ float red[33];
     const int row = blockIdx.y;  // t * B + b
     const int t = row / B, b = row - t * B;
@@ -484,6 +495,7 @@ __global__ void masked_mse_kernel(const float* __restrict__ pred, const float* _
                                   long long m_bstride, long long m_tstride, int T, int B, int R, float scale,
                                   const float* __restrict__ scale_dev, float* __restrict__ loss,
                                   float* __restrict__ loss_raw, float* __restrict__ dpred) {
+    pdl_sync();
     __shared__ float red[33];
     const float k0 = 1.f / (float(B) * float(R));
     const float k = scale * (scale_dev ? __ldg(scale_dev) : 1.f) * k0;
@@ -529,6 +541,7 @@ struct AdamArgs {
 };
 
 __global__ void clip_adam_kernel(const __grid_constant__ AdamArgs A) {
+    pdl_sync();
     const AdamChunk& C = A.chunk[blockIdx.y];
     float bc1 = A.bc1, bc2s = A.bc2_sqrt;
     const float* sp = C.step ? C.step : A.step_ptr;
@@ -563,6 +576,7 @@ namespace scm {
 // ----------------------------------------------------------------------------------------------
 __global__ void reward_head_fwd_kernel(const float* __restrict__ y2, int B, int R, int H, int W, int h2, int w2,
                                        float* __restrict__ r, float* __restrict__ map) {
+    pdl_sync();
     __shared__ float red[33];
     const int b = blockIdx.x, j = blockIdx.y;
     const size_t hw = size_t(H) * W;
@@ -587,6 +601,7 @@ __global__ void reward_head_fwd_kernel(const float* __restrict__ y2, int B, int 
 //   d logit_k = dr[b][j] * p_k * ((k==0) - (k==2) - (p_0 - p_2))
 __global__ void reward_head_bwd_kernel(const float* __restrict__ y2, const float* __restrict__ dr, int B, int R, int H,
                                        int W, int h2, int w2, __nv_bfloat16* __restrict__ d2) {
+    pdl_sync();
     const int Hp = H + 2, Wp = W + 2;
     const long long rows = (long long)B * Hp * Wp;
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -642,6 +657,7 @@ namespace scm {
 // ----------------------------------------------------------------------------------------------
 __global__ void cf_rowmean_kernel(const float* __restrict__ za, const float* __restrict__ zb, int HW,
                                   float* __restrict__ rowmean) {
+    pdl_sync();
     __shared__ float red[33];
     const size_t row = blockIdx.x;  // b * L + l
     const float4* pa = reinterpret_cast<const float4*>(za + row * HW);
@@ -664,6 +680,7 @@ __global__ void cf_rowmean_kernel(const float* __restrict__ za, const float* __r
 __global__ void cf_loss_fwd_kernel(const float* __restrict__ rowmean, const float* __restrict__ unswapped,
                                    const float* __restrict__ mask, int B, int L, int mode, float lambda,
                                    float* __restrict__ loss) {
+    pdl_sync();
     __shared__ float red[33];
     float acc = 0.f;
     for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -684,6 +701,7 @@ __global__ void cf_loss_bwd_kernel(const float* __restrict__ za, const float* __
                                    const float* __restrict__ unswapped, const float* __restrict__ mask,
                                    const float* __restrict__ rowmean, const float* __restrict__ gscale, int B, int L,
                                    int HW, int mode, float lambda, float* __restrict__ dza, float* __restrict__ dzb) {
+    pdl_sync();
     const int b = blockIdx.y, l = blockIdx.z;
     float coef;
     if (mode == 0) {
@@ -710,6 +728,7 @@ __global__ void cf_loss_bwd_kernel(const float* __restrict__ za, const float* __
 // ----------------------------------------------------------------------------------------------
 __global__ void transition_tail_kernel(const float* __restrict__ x, const float* __restrict__ u, long long n,
                                        float* __restrict__ p, float* __restrict__ z) {
+    pdl_sync();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float pv = 1.f / (1.f + __expf(-__ldg(x + i)));
         if (p) p[i] = pv;
@@ -719,6 +738,7 @@ __global__ void transition_tail_kernel(const float* __restrict__ x, const float*
 
 // uniforms of the Philox stream as a tensor: thread t evaluates block (offset + t) once and writes its four outputs
 __global__ void philox_fill_kernel(float* __restrict__ out, long long n, const unsigned long long* __restrict__ rng) {
+    pdl_sync();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long i0 = t * 4;
     if (i0 >= n) return;
@@ -745,6 +765,7 @@ __global__ void philox_fill_kernel(float* __restrict__ out, long long n, const u
 }
 
 // advance the device-side Philox offset after a sampling launch (keeps the whole step CUDA-graph replayable)
-__global__ void rng_advance_kernel(unsigned long long* rng, unsigned long long n) { rng[1] += n; }
+__global__ void rng_advance_kernel(unsigned long long* rng, unsigned long long n) {
+    pdl_sync(); rng[1] += n; }
 
 }  // namespace scm

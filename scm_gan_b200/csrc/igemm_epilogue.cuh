@@ -133,11 +133,27 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             gb[(k * GROUP) >> 5] |= m << ((k * GROUP) & 31);
         }
     }
+    // Bernoulli head: the uniforms of this warp's first column group are fetched before the accumulator wait as well.
+    // Inside the store loop every load sat behind the previous (possibly aliasing) store and its own ~700-cycle
+    // latency: measured 40 us of a 61 us conv6 launch.
+    const size_t hw = size_t(P.H) * P.W;
+    float upre[GROUP];
+    bool have_upre = false;
+    if constexpr (F32) {
+        if (P.sample_out && P.uniforms && R.interior) {
+            const size_t base = (size_t(R.b) * P.n_valid) * hw + size_t(R.hp - 1) * P.W + (R.wp - 1);
+#pragma unroll
+            for (int i = 0; i < GROUP; ++i) {
+                const int n = n0 + half * GROUP + i;
+                upre[i] = n < P.n_valid ? __ldg(P.uniforms + base + size_t(n) * hw) : 0.f;
+            }
+            have_upre = true;
+        }
+    }
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
     const float* sbp = (P.sample_bias && R.valid) ? P.sample_bias + size_t(R.b) * n_total + n0 : nullptr;
     const float rs = (P.sample_scale && R.valid) ? P.scale * __ldg(P.sample_scale + R.b) : P.scale;
-    const size_t hw = size_t(P.H) * P.W;
     const uint32_t s_bias_u32 = smem_u32(s_bias);
     __nv_bfloat16* const ob = P.out + (P.out_c_off + n0);
     __nv_bfloat16* const ob0 = ob + size_t(d0 < 0 ? 0 : d0) * P.out_cs;
@@ -237,13 +253,15 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
         }
         if (F32 && P.out_f32 && R.interior) {
             const size_t base = (size_t(R.b) * P.n_valid) * hw + size_t(R.hp - 1) * P.W + (R.wp - 1);
+            const bool pre = have_upre && c0 == half * GROUP;
 #pragma unroll
             for (int i = 0; i < GROUP; ++i) {
                 const int n = n0 + c0 + i;
                 if (n < P.n_valid) {
                     const size_t idx = base + size_t(n) * hw;
                     P.out_f32[idx] = v[i];
-                    if (P.sample_out) P.sample_out[idx] = bernoulli_head(P, idx, v[i]);
+                    if (P.sample_out)
+                        P.sample_out[idx] = pre ? (upre[i] < v[i] ? 1.f : 0.f) : bernoulli_head(P, idx, v[i]);
                 }
             }
         }

@@ -13,6 +13,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Programmatic dependent launch (see launch_k() in api.cu): every kernel calls pdl_sync() before its first access to
+// global memory.  griddepcontrol.wait returns once the preceding kernel of the stream has completed and its memory
+// operations are visible; launch_dependents then lets the runtime schedule the NEXT kernel early (it will block in
+// its own griddepcontrol.wait until this grid is done).
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
