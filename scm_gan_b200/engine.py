@@ -296,8 +296,23 @@ def encoder_forward(x, wbar, bias, sigma, w4, b4):
     return z, [xin, a1, a2, a3] + wd
 
 
+# Called by encoder_backward with the indices (into [Wbar1..3, b1..3, W4, b4]) of the parameters whose gradient has just
+# become final in stream order.  The data-parallel launcher hangs its per-layer all-reduce on it (scm_gan_b200/dp.py):
+# the encoder's backward is the tail of every iteration, so its gradients are exchanged layer by layer while the layers
+# below are still being differentiated.  Set through ops._encoder_backward; None = nobody listens.
+LAYER_READY_HOOK = None
+
+
+def _ready(idxs):
+    if LAYER_READY_HOOK is not None:
+        LAYER_READY_HOOK(idxs)
+
+
 def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
-    """sink = [gWbar1..3, gb1..3, gW4, gb4] (entries may be None): see transition_backward."""
+    """sink = [gWbar1..3, gb1..3, gW4, gb4] (entries may be None): see transition_backward.
+    Layer order: every layer's weight-gradient reduction runs on the side stream under the NEXT layer's data-gradient
+    conv; it is joined, spectrally back-normalised and announced (LAYER_READY_HOOK) before the next weight gradient is
+    issued, so that a data-parallel run can exchange it while the remaining layers are computed."""
     xin, a1, a2, a3 = saved[:4]
     wd = saved[4:]
     dev = dz.device
@@ -321,6 +336,13 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
     db = [db[i] if gb[i] is None else gb[i] for i in range(3)]
     if gb4 is not None and Lp == L:
         db4 = gb4
+    dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
+
+    def finish_layer(i):  # spectral norm backward with the u, v currently held by the module (= last forward call)
+        K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
+                              dwbar[i] if gw[i] is None else gw[i], gw[i] is not None)])
+        _ready([i, 3 + i])
+
     dr = K.DeferredReduces(dev)
     d4 = K.new_plane(B, H, W, Lp, dev)
     K.pack_nchw(dz, d4, wrap=False, sig=z)
@@ -329,17 +351,21 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
         K.plane_colsum(d4, 0, Lp, B, H, W, db=db4)
     d3, d2, d1 = (K.new_plane(B, H, W, HID, dev) for _ in range(3))
     K.conv3x3(d4, wd[2], B, H, W, cin=Lp, out=d3, gate=a3, dgrad=True)
-    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
-    K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
-    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
-    K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
-    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0], defer=dr)
-    dr.join()
-    dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
-    K.spectral_norm_bwd([(G[i], wbar[i], u[i], v[i], sigma[i:i + 1], dots[i:i + 1],
-                          dwbar[i] if gw[i] is None else gw[i], gw[i] is not None) for i in range(3)])
+    dr.join()                                                   # conv4: no spectral norm
     if gb4 is not None and Lp != L:
         gb4 += db4[:L]
+    _ready([6, 7])
+    K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
+    K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
+    dr.join()
+    finish_layer(2)
+    K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
+    K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
+    dr.join()
+    finish_layer(1)
+    K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0], defer=dr)
+    dr.join()
+    finish_layer(0)
     return (dwbar, [db[i].clone() if gb[i] is None else None for i in range(3)],
             G[3].clone() if gw4 is None else None, db4[:L].clone() if gb4 is None else None)
 

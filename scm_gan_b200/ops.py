@@ -198,9 +198,24 @@ def _encoder_backward(ctx, grads):
     u, v = ctx.uv
     params = ctx.wbar + ctx.bias + [ctx.w4, ctx.b4]
     sinks, mask = _sinks_of(params)
-    out = torch.ops.scmgan.encoder_bwd(grads[0], z, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w4, sinks, mask)
+    told = set()
+
+    def layer_ready(idxs):  # engine.encoder_backward: these gradients are final in stream order - announce them now
+        for i in idxs:
+            if (mask >> i) & 1 and i not in told:
+                told.add(i)
+                _notify([params[i]], 1)
+    E.LAYER_READY_HOOK = layer_ready
+    try:
+        out = torch.ops.scmgan.encoder_bwd(grads[0], z, rest, ctx.wbar, ctx.sigma, list(u), list(v), ctx.w4, sinks,
+                                           mask)
+    finally:
+        E.LAYER_READY_HOOK = None
     g = _merge(out, mask, 2 * n + 2)
-    _notify(params, mask)
+    rest_mask = mask
+    for i in told:
+        rest_mask &= ~(1 << i)
+    _notify(params, rest_mask)
     return None, g[:n], g[n:2 * n], None, g[2 * n], g[2 * n + 1]
 
 

@@ -1,0 +1,162 @@
+"""Data-parallel training step on two GPUs over NCCL (-m gpu; skipped with fewer than two devices).
+
+Two ranks (one process per GPU, torch.distributed NCCL, scm_gan_b200.dp.BucketedGradSync) each take half of a global
+batch and run three iterations through the path bench.py times (Trainer.step with CUDA-graph replay, the gradient
+all-reduces captured inside the graph on a side stream).  Checked:
+  * the replicated state stays replicated: after three iterations every weight, the Adam moments and the spectral-norm
+    vectors are BIT-IDENTICAL on the two ranks;
+  * the result is the single-GPU result: the same three iterations on one GPU with the concatenated batch (same weights,
+    same injected Bernoulli uniforms, the counterfactual action shuffle acting inside each half) give the same loss and
+    the same weights up to fp32 summation order.
+"""
+import json
+import os
+import socket
+import sys
+import tempfile
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_problem(Bg, Hn, C, H, W, A, Rw, cf_h, n_steps, dev):
+    """Global batch + per-iteration uniforms (identical on every rank: seeded CPU generator)."""
+    from oracle import restated as R   # synthetic batch generator only (test infrastructure)
+    st, rw, dn, ac = R.synthetic_batch(Bg, Hn, C, H, W, A, Rw, seed=77, p_done=0.05)
+    g = torch.Generator().manual_seed(5)
+    cf_indices = torch.randint(16, (Bg, 2), generator=g)
+    half = Bg // 2
+    # the action shuffle of main.py:275 permutes rows of the LOCAL batch in a data-parallel run (scm_gan_b200/dp.py): for
+    # the single-GPU comparison the global permutation is the two local ones side by side
+    perm_local = [torch.randperm(half, generator=g) for _ in range(2)]
+    cf_perm_global = torch.cat([perm_local[0], perm_local[1] + half])
+    calls = (Hn - 2) + 2 * (cf_h - 1)
+    uniforms = [torch.rand((calls, Bg, 16, H, W), generator=g) for _ in range(n_steps)]
+    batch = {"states": st, "rewards": rw, "dones": dn, "actions": torch.as_tensor(ac), "cf_indices": cf_indices}
+    return batch, perm_local, cf_perm_global, uniforms
+
+
+def _state_of(trainer, nets):
+    out = {}
+    for name, m in nets.items():
+        for k, v in m.state_dict().items():
+            out[f"{name}.{k}"] = v.detach().float().cpu().clone()
+    for i, (m_, v_) in enumerate(zip(trainer.m, trainer.v)):
+        out[f"adam.m{i}"] = m_.detach().cpu().clone()
+        out[f"adam.v{i}"] = v_.detach().cpu().clone()
+    return out
+
+
+def _worker(rank, world, port, cfg, out_path):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dev = torch.device("cuda", rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from scm_gan_b200.dp import BucketedGradSync
+    from scm_gan_b200.train_step import Trainer, build_nets
+    C, H, W, A, Rw, Bg, Hn, cf_h, n_steps = cfg
+    batch, perm_local, cf_perm_global, uniforms = _make_problem(Bg, Hn, C, H, W, A, Rw, cf_h, n_steps, dev)
+    half = Bg // world
+    kw = dict(enable_disentanglement=True, enable_action_control=True, counterfactual_horizon=cf_h)
+    theta = 0.6
+
+    def run(nets, trainer, lo, hi, perm):
+        b = {k: v[lo:hi].to(dev) for k, v in batch.items()}
+        b["cf_perm"] = perm.to(dev)
+        losses = []
+        for it in range(n_steps):
+            b["uniforms"] = uniforms[it][:, lo:hi].contiguous().to(dev)
+            loss = trainer.step(b, theta, cf_now=True, use_graph=True)
+            torch.cuda.synchronize()
+            losses.append(loss.item())
+        return losses
+
+    # ---- data-parallel run: rank r takes rows [r*half, (r+1)*half) ----
+    nets = build_nets(C, A, Rw, seed=0)
+    for n in nets.values():
+        n.train()
+    tr = Trainer(nets, loss_kwargs=kw)
+    sync = BucketedGradSync(tr)
+    losses = run(nets, tr, rank * half, (rank + 1) * half, perm_local[rank])
+    mine = _state_of(tr, nets)
+    # global loss = mean of the shard losses (every term is a batch mean with denominator = local batch)
+    lt = torch.tensor(losses, dtype=torch.float64, device=dev)
+    dist.all_reduce(lt)
+    lt /= world
+    # bit-identical replicas: compare a checksum-free way - gather everything on rank 0
+    gathered = [None] * world
+    dist.gather_object({k: v for k, v in mine.items()}, gathered if rank == 0 else None, dst=0)
+    result = {"n_buckets": len(sync.buckets)}
+    if rank == 0:
+        mismatched = [k for k in gathered[0] if not torch.equal(gathered[0][k], gathered[1][k])]
+        result["replicas_bit_identical"] = not mismatched
+        result["mismatched"] = mismatched[:8]
+        # ---- single-GPU run on the whole batch ----
+        nets1 = build_nets(C, A, Rw, seed=0)
+        for n in nets1.values():
+            n.train()
+        tr1 = Trainer(nets1, loss_kwargs=kw)
+        losses1 = run(nets1, tr1, 0, Bg, cf_perm_global)
+        one = _state_of(tr1, nets1)
+        worst, worst_key = 0.0, ""
+        for k, v in one.items():
+            if k.startswith("adam.v"):
+                continue  # second moments are squares of tiny numbers: compared through the weights they produce
+            d = ((gathered[0][k] - v).norm() / (v.norm() + 1e-30)).item()
+            if d > worst:
+                worst, worst_key = d, k
+        result.update(loss_dp=lt.tolist(), loss_single=losses1, worst_rel=worst, worst_key=worst_key)
+        with open(out_path, "w") as f:
+            json.dump(result, f)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sys.stdout.flush()
+    os._exit(0)  # captured graphs hold references into the communicator: leave without running destructors
+
+
+@pytest.mark.parametrize("workload", ["minipacman", "pong64"])
+def test_two_gpu_step_matches_single_gpu(workload):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    import torch.multiprocessing as mp
+    shapes = {"minipacman": (3, 15, 19, 5, 2, 8, 6, 3, 3), "pong64": (3, 64, 64, 4, 1, 8, 6, 2, 3)}
+    cfg = shapes[workload]
+    with tempfile.TemporaryDirectory() as d:
+        out = os.path.join(d, "result.json")
+        ctx = mp.get_context("spawn")
+        port = _free_port()
+        procs = [ctx.Process(target=_worker, args=(r, 2, port, cfg, out)) for r in range(2)]
+        for p in procs:
+            p.start()
+        for p in procs:
+            p.join(timeout=600)
+            assert p.exitcode == 0, f"worker exited with {p.exitcode}"
+        with open(out) as f:
+            res = json.load(f)
+    print(json.dumps(res))
+    keep = os.environ.get("SCMGAN_DP_TEST_ARTEFACT")
+    if keep:
+        with open(keep, "a") as f:
+            f.write(json.dumps({"workload": workload, **res}) + "\n")
+    assert res["replicas_bit_identical"], res["mismatched"]
+    assert res["n_buckets"] >= 5   # reward+decoder+transition, then the encoder layer by layer
+    for a, b in zip(res["loss_dp"], res["loss_single"]):
+        assert abs(a - b) <= 1e-5 * abs(b), (res["loss_dp"], res["loss_single"])
+    # same gradients up to the fp32 summation order of the split-K / cross-rank reductions; Adam turns a gradient into
+    # a step of ~lr whatever its size, so weights may differ by a few 1e-6 relative after three steps
+    assert res["worst_rel"] <= 1e-4, (res["worst_key"], res["worst_rel"])
