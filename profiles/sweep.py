@@ -119,7 +119,7 @@ def main():
                            "horizon": Hn, "T": T, "cf": cf, "counterfactual_horizon": CF_HORIZON, "note": note},
                 "step_tflops_per_gpu": flops / (ms * 1e-3) / 1e12,
                 "frac_of_sustained_bf16_peak": flops / (ms * 1e-3) / 1e12 / peaks["bf16_sustained"],
-                "launches_per_step": trainer.launches_per_step, "peak_mem_gib": round(mem, 2)}), flush=True)
+                "launches_per_step": {f"Hn={k[0]},cf={int(k[1])}": v for k, v in trainer.launches_per_step.items()}, "peak_mem_gib": round(mem, 2)}), flush=True)
         # free everything (graphs hold the pools) before the next configuration
         del trainer, nets, batch
         gc.collect()
