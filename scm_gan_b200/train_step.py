@@ -352,7 +352,7 @@ class Trainer:
 
     # -- loss-term log (reference main.py:184,196,233,262,283 ts.collect + 297 ts.print_every(10)) ---------------------
     LOG_RING = 16    # iterations kept on the device between two read-backs
-    LOG_WIDTH = 64   # named terms per iteration (2 per rollout step + LO + 2 CF + total)
+    LOG_WIDTH = 128  # named terms per iteration (2 per rollout step + LO + 2 CF + total): horizons up to 62
 
     def _log_terms(self, key, terms, loss):
         """Append this iteration's named loss terms to a device-side ring (graph-capturable: the slot index lives on
