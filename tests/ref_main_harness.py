@@ -110,10 +110,38 @@ def _install_environment():
         legacy._scm_legacy = True
         clip_mod.clip_grad_value_ = legacy
         torch.nn.utils.clip_grad_value_ = legacy
+    if USE_REFERENCE_MODELS:
+        _reference_model_shims()
+
+
+def _reference_model_shims():
+    """Control arm only: the reference's own models.py needs shim 2 (legacy circular pad-1 on every Transition) and,
+    without a GPU, shim 4 (.cuda() no-op)."""
+    import torch
+    from oracle import shims
+    if not torch.cuda.is_available():
+        torch.nn.Module.cuda = lambda self, *a, **k: self
+        torch.Tensor.cuda = lambda self, *a, **k: self
+    import models
+    if not getattr(models.Transition, "_scm_legacy_pad", False):
+        orig_init = models.Transition.__init__
+
+        def init(self, *a, **k):
+            orig_init(self, *a, **k)
+            shims.apply_legacy_circular(self)
+        models.Transition.__init__ = init
+        models.Transition._scm_legacy_pad = True
+
+
+# SCMGAN_HARNESS_MODELS=reference: main.py imports the reference's OWN models.py / layer modules (stock torch ops, with
+# the legacy-circular-padding shim) instead of the drop-ins - the control arm of the comparison, and the way to check the
+# harness itself on a machine without a GPU.
+USE_REFERENCE_MODELS = os.environ.get("SCMGAN_HARNESS_MODELS", "dropin") == "reference"
 
 
 def _paths():
-    for p in (REF_COPY, ROOT, DROPIN):   # final order: dropin, repo root, reference copy
+    order = (DROPIN, ROOT, REF_COPY) if USE_REFERENCE_MODELS else (REF_COPY, ROOT, DROPIN)
+    for p in order:   # final order (default): dropin, repo root, reference copy
         if p in sys.path:
             sys.path.remove(p)
         sys.path.insert(0, p)
@@ -134,7 +162,8 @@ def run_main(argv, iters_per_video=None, stub_evaluate=True, spy=None):
         mod = importlib.util.module_from_spec(spec)
         spec.loader.exec_module(mod)
         import models
-        assert os.path.abspath(models.__file__).startswith(DROPIN), f"main.py imported {models.__file__}"
+        want = REF_COPY if USE_REFERENCE_MODELS else DROPIN
+        assert os.path.abspath(models.__file__).startswith(want), f"main.py imported {models.__file__}"
         if iters_per_video is not None:
             mod.ITERS_PER_VIDEO = iters_per_video
         if stub_evaluate:
@@ -152,14 +181,53 @@ def run_main(argv, iters_per_video=None, stub_evaluate=True, spy=None):
         sys.argv = old_argv
 
 
-if __name__ == "__main__":
-    if not prepare_ref_copy():
-        sys.exit("reference copy not available (baseline/_ref missing and /root/reference absent)")
-    _paths()
-    _install_environment()
-    sys.argv = [os.path.join(REF_COPY, "main.py")] + sys.argv[1:]
-    runpy.run_path(os.path.join(REF_COPY, "main.py"), run_name="__main__")
+def _dump_state_spy(path):
+    """spy for run_main(): saves the state_dicts train() was entered with (after --load-from, main.py:79-90)."""
+    def spy(latent_dim, datasource, num_actions, num_rewards, encoder, decoder, reward_predictor, discriminator,
+            transition):
+        import torch
+        torch.save({"encoder": encoder.state_dict(), "decoder": decoder.state_dict(),
+                    "transition": transition.state_dict(), "discriminator": discriminator.state_dict(),
+                    "reward_predictor": reward_predictor.state_dict()}, path)
+    return spy
+
+
+def _report():
+    import json
     ts = RecordingTimeSeries.instances[-1] if RecordingTimeSeries.instances else None
     if ts is not None:
-        import json
         print("HARNESS_SERIES " + json.dumps({k: [v[0], v[-1], len(v)] for k, v in ts.series.items()}))
+        print("HARNESS_FULL " + json.dumps(ts.series))
+    print("HARNESS_MODELS " + os.path.abspath(sys.modules["models"].__file__))
+    try:
+        from scm_gan_b200 import kernels
+        print("HARNESS_LAUNCHES %d" % kernels.launch_count())
+    except Exception as e:  # control arm on a machine without the library
+        print("HARNESS_LAUNCHES -1 (%s)" % type(e).__name__)
+
+
+if __name__ == "__main__":
+    # environment knobs (the command line belongs to main.py's own argparse):
+    #   SCMGAN_HARNESS_MODELS=reference        control arm, see above
+    #   SCMGAN_HARNESS_ITERS_PER_VIDEO=N       module mode with main.ITERS_PER_VIDEO lowered to N (checkpoint branch)
+    #   SCMGAN_HARNESS_DUMP_STATE=file.pt      save the state_dicts train() starts from (checks --load-from)
+    #   SCMGAN_HARNESS_SEED=S                  seed torch / numpy / random before main() (main.py itself never seeds)
+    if not prepare_ref_copy():
+        sys.exit("reference copy not available (baseline/_ref missing and /root/reference absent)")
+    seed = os.environ.get("SCMGAN_HARNESS_SEED")
+    if seed is not None:
+        import random
+        import numpy
+        import torch
+        torch.manual_seed(int(seed)); numpy.random.seed(int(seed)); random.seed(int(seed))
+    ipv = os.environ.get("SCMGAN_HARNESS_ITERS_PER_VIDEO")
+    dump = os.environ.get("SCMGAN_HARNESS_DUMP_STATE")
+    if ipv is not None or dump is not None:
+        run_main(sys.argv[1:], iters_per_video=int(ipv) if ipv else None,
+                 spy=_dump_state_spy(dump) if dump else None)
+    else:
+        _paths()
+        _install_environment()
+        sys.argv = [os.path.join(REF_COPY, "main.py")] + sys.argv[1:]
+        runpy.run_path(os.path.join(REF_COPY, "main.py"), run_name="__main__")
+    _report()
