@@ -156,6 +156,32 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* desc_host, scmgan_st
  * conv epilogue.  Replaces torch.rand_like of DifferentiableBernoulliSampler, reference models.py:27-31. */
 int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream);
 
+/* Device-side replay buffer sampler: the reference's get_trajectories (envs/minipacman.py:122-164; same contract in
+ * envs/betterpong.py, gridworld.py, ...) without leaving the GPU.  Episodes occupy fixed slots in HBM; the first
+ * *n_filled slots are valid, ep_len[slot] (>= 4) is the episode length.  Each batch row concatenates clips
+ * (random episode, random start in [0, len-4] or 0, up to len-1) until Hn timesteps are filled; the last step of every
+ * clip - also of the final, truncated one - is flagged done, as in the reference.  Randomness: Philox4x32-10 stream
+ * {seed, offset} in rng_state; clip k of row b uses counter offset + b*Hn + k (lanes 0, 1); offset += B*Hn afterwards
+ * (second launch), so the call is CUDA-graph replayable.  plan (optional, [B][Hn][3] int32) receives
+ * (slot, start, duration) per clip, -1 beyond the last clip. */
+typedef struct {
+    const float* frames;     /* [slots][max_len][per_frame] */
+    const float* rewards;    /* [slots][max_len][R] */
+    const int* actions;      /* [slots][max_len] */
+    const int* ep_len;       /* [slots] */
+    const int* n_filled;     /* device scalar */
+    int slots, max_len, R;
+    long long per_frame;
+    int B, Hn, random_start;
+    unsigned long long* rng_state;
+    float* states;           /* out [B][Hn][per_frame] */
+    float* rewards_out;      /* out [B][Hn][R] */
+    float* dones;            /* out [B][Hn] (0 / 1) */
+    long long* actions_out;  /* out [B][Hn] */
+    int* plan;               /* out, optional */
+} scmgan_replay_desc;
+int scmgan_replay_sample(const scmgan_replay_desc* desc_host, scmgan_stream_t stream);
+
 struct scmgan_wgrad_reduce_job;
 
 /* Weight gradient: g[co*g_s_co + ci*g_s_ci + tap'*g_s_tap] += scale * sum_interior dy[p][co] * x[p+tap][ci],
@@ -286,6 +312,19 @@ int scmgan_masked_mse_seq(const float* pred, const float* target, long long targ
  * Fuses torch.sigmoid + F.binary_cross_entropy + means (reference main.py:188-197, 310-312). */
 int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const float* mask, int B, long long per,
                       float* loss, float* dx, scmgan_stream_t stream);
+
+/* Rollout-MSE evaluation (reference measure_prediction_mse, main.py:784-836) without per-step host reads.
+ * x: logits of T decoded steps, t-major [T][B][per]; step t of sample b of the frame / reward / done tensors is found at
+ * base + b*bstride + t*tstride.
+ *   eval_sqerr: out[t*B+b] = mean_chw (y[b,t] - sigmoid(x[t,b]))^2                                  (main.py:812-815)
+ *   eval_stats: table[t] = { mean(d)*B/live, std(d)*B/live, mean(r)*B/live, std(r)*B/live, live } with
+ *               mask_t = prod_{s<=t}(1-done_s), d = mask*sqerr, r = mask*(sum_r rewards - sum_r rpred)^2, live = sum mask
+ *               (main.py:806-829; std is torch.std's unbiased estimate).  rpred is [T][B][R] dense. */
+int scmgan_eval_sqerr(const float* x, const float* y, long long y_bstride, long long y_tstride, int T, int B,
+                      long long per, float* out, scmgan_stream_t stream);
+int scmgan_eval_stats(const float* sqerr, const float* rpred, const float* rewards, long long r_bstride,
+                      long long r_tstride, const float* dones, long long d_bstride, long long d_tstride, int T, int B,
+                      int R, float* table, scmgan_stream_t stream);
 
 /* Separate forward / backward entry points of the same fused kernel (the names SURVEY.md section 8b lists). */
 int scmgan_decoder_bce_fwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,

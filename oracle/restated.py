@@ -326,7 +326,8 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
     cf_perm: batch permutation replacing np.random.shuffle(cf_actions) (main.py:275).
     Returns (loss, dict of named loss terms, final z).
     """
-    actions = torch.as_tensor(np.asarray(actions)).long()
+    # a device tensor stays where it is (graph-captured stock-torch baseline); numpy / lists as in main.py:206
+    actions = actions.long() if torch.is_tensor(actions) else torch.as_tensor(np.asarray(actions)).long()
     bsz = states.shape[0]
     hn = states.shape[1]
     eye = torch.eye(num_actions, dtype=states.dtype, device=states.device)
@@ -390,7 +391,7 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
     if enable_action_control and cf_now:  # main.py:268-283
         z_cf_a = z.clone()
         z_cf_b = z_orig
-        cf_actions = actions[torch.as_tensor(np.asarray(cf_perm)).long()]
+        cf_actions = actions[cf_perm.long() if torch.is_tensor(cf_perm) else torch.as_tensor(np.asarray(cf_perm)).long()]
         for t in range(1, counterfactual_horizon):
             z_cf_b = trans(z_cf_b, eye[cf_actions[:, t]])
         eps = 0.001
@@ -537,3 +538,38 @@ def synthetic_batch(batch, horizon, channels, height, width, num_actions, num_re
     dones = (torch.rand(batch, horizon, generator=g) < p_done).float()
     actions = torch.randint(num_actions, (batch, horizon), generator=g)
     return states, rewards, dones, actions.numpy()
+
+
+# --------------------------------------------------------------------------------------------------------------
+# envs/minipacman.py:122-164 (same sampler in the other environments): replay-buffer clip sampling
+# --------------------------------------------------------------------------------------------------------------
+def get_trajectories_from_uniforms(episodes, uniforms, batch_size, timesteps, random_start=True):
+    """reference envs/minipacman.py:137-163 with the two random draws of every clip taken from `uniforms`:
+    uniforms[b, k] = (u0, u1), u0 -> random.choice(replay_buffer) (line 144), u1 -> np.random.randint(0, len - 3)
+    (line 146).  A uniform u selects index min(int(float32(u) * float32(n)), n - 1) of n choices.
+    episodes: list of (states [n,...], rewards [n,R], actions [n]).
+    Returns (states, rewards, dones, actions, plan) with plan[b] = [(episode, start, duration), ...]."""
+    f32 = np.float32
+
+    def pick(u, n):
+        return min(int(f32(u) * f32(n)), n - 1)
+    states_b, rewards_b, dones_b, actions_b, plans = [], [], [], [], []
+    for b in range(batch_size):
+        states, rewards, actions, dones, plan = [], [], [], [], []
+        remaining, k = timesteps, 0
+        while remaining > 0:
+            e = pick(uniforms[b][k][0], len(episodes))
+            sel_s, sel_r, sel_a = episodes[e]
+            start = pick(uniforms[b][k][1], len(sel_s) - 3) if random_start else 0
+            end = min(start + remaining, len(sel_s) - 1)
+            duration = end - start
+            states.extend(sel_s[start:end])
+            rewards.extend(sel_r[start:end])
+            actions.extend(sel_a[start:end])
+            dones.extend([False for _ in range(duration - 1)] + [True])
+            remaining -= duration
+            plan.append((e, start, duration))
+            k += 1
+        states_b.append(np.array(states)); rewards_b.append(np.array(rewards))
+        dones_b.append(np.array(dones)); actions_b.append(np.array(actions)); plans.append(plan)
+    return np.array(states_b), np.array(rewards_b), np.array(dones_b), np.array(actions_b), plans

@@ -74,6 +74,14 @@ class CsrnSweepDesc(C.Structure):
                 ("dx", C.c_void_p), ("dparams", C.c_void_p)]
 
 
+class ReplayDesc(C.Structure):
+    _fields_ = [("frames", C.c_void_p), ("rewards", C.c_void_p), ("actions", C.c_void_p), ("ep_len", C.c_void_p),
+                ("n_filled", C.c_void_p), ("slots", C.c_int), ("max_len", C.c_int), ("R", C.c_int),
+                ("per_frame", C.c_longlong), ("B", C.c_int), ("Hn", C.c_int), ("random_start", C.c_int),
+                ("rng_state", C.c_void_p), ("states", C.c_void_p), ("rewards_out", C.c_void_p), ("dones", C.c_void_p),
+                ("actions_out", C.c_void_p), ("plan", C.c_void_p)]
+
+
 class AdamChunk(C.Structure):
     _fields_ = [("p", C.c_void_p), ("g", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p),
                 ("n", C.c_int), ("clip", C.c_float), ("step", C.c_void_p)]
@@ -103,6 +111,11 @@ SIGNATURES = {
                                       C.c_void_p]),
     "scmgan_bce_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), C.c_void_p]),
+    "scmgan_eval_sqerr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_longlong,
+                                    C.c_void_p, C.c_void_p]),
+    "scmgan_eval_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_void_p,
+                                    C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "scmgan_reward_head_fwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
     "scmgan_reward_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -1121,6 +1121,27 @@ int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const
     return scmgan_bce_logits_seq(x, y, y_bstride, 0, mask, 1, 0, 1, B, per, loss, dx, stream);
 }
 
+int scmgan_eval_sqerr(const float* x, const float* y, long long y_bstride, long long y_tstride, int T, int B,
+                      long long per, float* out, scmgan_stream_t stream) {
+    SCM_REQUIRE(x && y && out && T > 0 && B > 0 && per > 0, "eval_sqerr: bad arguments");
+    launch_k(eval_sqerr_kernel, dim3((unsigned)((long long)T * B)), dim3(256), size_t(0), (cudaStream_t)stream, x, y, y_bstride, y_tstride, B, per, out);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_eval_stats(const float* sqerr, const float* rpred, const float* rewards, long long r_bstride,
+                      long long r_tstride, const float* dones, long long d_bstride, long long d_tstride, int T, int B,
+                      int R, float* table, scmgan_stream_t stream) {
+    SCM_REQUIRE(sqerr && rpred && rewards && dones && table && T > 0 && B > 0 && R > 0, "eval_stats: bad arguments");
+    const size_t smem = (size_t(3) * B + 33) * sizeof(float);
+    SCM_REQUIRE(smem <= 48 * 1024, "eval_stats: batch %d exceeds the single-block limit", B);
+    launch_k(eval_stats_kernel, dim3(1), dim3(256), smem, (cudaStream_t)stream, sqerr, rpred, rewards, r_bstride, r_tstride, dones, d_bstride, d_tstride, T, B, R, table);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 int scmgan_reward_head_fwd(const float* y2, int B, int R, int H, int W, float* r, float* map,
                            scmgan_stream_t stream) {
     SCM_REQUIRE(y2 && r && B > 0 && R > 0 && 3 * R <= 16 && H >= 5 && W >= 5, "reward_head_fwd: bad arguments");
@@ -1246,6 +1267,29 @@ int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     launch_k(rng_advance_kernel, dim3(1), dim3(1), size_t(0), (cudaStream_t)stream, rng_state, (unsigned long long)blocks4);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
+int scmgan_replay_sample(const scmgan_replay_desc* d, scmgan_stream_t stream) {
+    SCM_REQUIRE(d != nullptr, "replay_sample: null descriptor");
+    SCM_REQUIRE(d->frames && d->rewards && d->actions && d->ep_len && d->n_filled && d->rng_state,
+                "replay_sample: null buffer pointer");
+    SCM_REQUIRE(d->states && d->rewards_out && d->dones && d->actions_out, "replay_sample: null output pointer");
+    SCM_REQUIRE(d->slots > 0 && d->max_len >= 4 && d->per_frame > 0 && d->R > 0 && d->B > 0 && d->Hn > 0,
+                "replay_sample: bad geometry");
+    SCM_REQUIRE(size_t(3) * d->Hn * sizeof(int) <= 48 * 1024, "replay_sample: %d timesteps exceed the row buffer", d->Hn);
+    ReplayParams P;
+    P.frames = d->frames; P.rewards = d->rewards; P.actions = d->actions; P.ep_len = d->ep_len;
+    P.n_filled = d->n_filled; P.slots = d->slots; P.max_len = d->max_len; P.R = d->R; P.per_frame = d->per_frame;
+    P.B = d->B; P.Hn = d->Hn; P.random_start = d->random_start; P.rng = d->rng_state;
+    P.states = d->states; P.rewards_out = d->rewards_out; P.dones = d->dones; P.actions_out = d->actions_out;
+    P.plan = d->plan;
+    launch_k(replay_sample_kernel, dim3(d->B), dim3(256), size_t(3) * d->Hn * sizeof(int), (cudaStream_t)stream, P);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    launch_k(rng_advance_kernel, dim3(1), dim3(1), size_t(0), (cudaStream_t)stream, d->rng_state, (unsigned long long)d->B * d->Hn);
     SCM_CUDA(cudaGetLastError());
     ++g_launches;
     return SCM_OK;

@@ -481,6 +481,81 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ----------------------------------------------------------------------------------------------
+// Rollout-MSE evaluation (reference measure_prediction_mse, main.py:784-836).  The decoder / reward predictor are
+// stateless, so all steps of the evaluation rollout are decoded as one batch; these two kernels turn the logits into the
+// four per-step curves without a single host round trip (the reference reads four scalars back per step).
+//   eval_sqerr_kernel: out[t*B + b] = mean_chw (y[b,t] - sigmoid(x[t,b]))^2     (main.py:812-815, before the mask)
+//   eval_stats_kernel: one block walks the steps in order; mask_t = prod_{s<=t} (1 - done_s) (main.py:806),
+//       d = mask * sqerr, r = mask * (sum_r reward - sum_r predicted)^2 (main.py:822-824),
+//       table[t] = { mean(d) B/live, std(d) B/live, mean(r) B/live, std(r) B/live, live }   (std unbiased: torch.std)
+// One block per row / one block in total: fixed summation order, deterministic.
+// ----------------------------------------------------------------------------------------------
+__global__ void eval_sqerr_kernel(const float* __restrict__ x, const float* __restrict__ y, long long y_bstride,
+                                  long long y_tstride, int B, long long per, float* __restrict__ out) {
+    pdl_sync();
+    __shared__ float red[33];
+    const long long row = blockIdx.x;  // t * B + b
+    const int t = int(row / B), b = int(row - (long long)t * B);
+    const float* xb = x + row * per;
+    const float* yb = y + (long long)b * y_bstride + (long long)t * y_tstride;
+    float acc = 0.f;
+    for (long long i = threadIdx.x; i < per; i += blockDim.x) {
+        const float d = __ldg(yb + i) - 1.f / (1.f + __expf(-__ldg(xb + i)));
+        acc = fmaf(d, d, acc);
+    }
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) out[row] = acc / float(per);
+}
+
+__global__ void eval_stats_kernel(const float* __restrict__ sqerr, const float* __restrict__ rpred,
+                                  const float* __restrict__ rewards, long long r_bstride, long long r_tstride,
+                                  const float* __restrict__ dones, long long d_bstride, long long d_tstride, int T,
+                                  int B, int R, float* __restrict__ table) {
+    pdl_sync();
+    extern __shared__ float ev_smem[];  // [B] running mask, [B] d, [B] r, 33 reduction slots
+    float* mask = ev_smem;
+    float* dv = mask + B;
+    float* rv = dv + B;
+    float* red = rv + B;
+    for (int b = threadIdx.x; b < B; b += blockDim.x) mask[b] = 1.f;
+    __syncthreads();
+    for (int t = 0; t < T; ++t) {
+        float live = 0.f, sd = 0.f, sr = 0.f;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            const float m = mask[b] * (1.f - __ldg(dones + (long long)b * d_bstride + (long long)t * d_tstride));
+            mask[b] = m;
+            float re = 0.f, rp = 0.f;
+            for (int r = 0; r < R; ++r) {
+                re += __ldg(rewards + (long long)b * r_bstride + (long long)t * r_tstride + r);
+                rp += rpred[((long long)t * B + b) * R + r];
+            }
+            const float d = m * sqerr[(long long)t * B + b];
+            const float q = m * (re - rp) * (re - rp);
+            dv[b] = d; rv[b] = q;
+            live += m; sd += d; sr += q;
+        }
+        live = block_sum(live, red);
+        const float md = block_sum(sd, red) / float(B);
+        const float mr = block_sum(sr, red) / float(B);
+        float vd = 0.f, vr = 0.f;
+        for (int b = threadIdx.x; b < B; b += blockDim.x) {
+            vd = fmaf(dv[b] - md, dv[b] - md, vd);
+            vr = fmaf(rv[b] - mr, rv[b] - mr, vr);
+        }
+        vd = block_sum(vd, red);
+        vr = block_sum(vr, red);
+        if (threadIdx.x == 0) {
+            const float scale = float(B) / live;  // live == 0: inf / nan rows, dropped by the caller (main.py:807-809)
+            const float den = float(B > 1 ? B - 1 : 1);
+            float* o = table + (long long)t * 5;
+            o[0] = md * scale; o[1] = sqrtf(vd / den) * scale; o[2] = mr * scale; o[3] = sqrtf(vr / den) * scale;
+            o[4] = live;
+        }
+        __syncthreads();
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Masked mean-squared error of the reward predictions (reference main.py:182-186), forward and gradient in one
 // single-block launch:  loss = scale * (*scale_dev) / (B*R) * sum_b mask[b] * sum_r (pred - target)^2
 // scale_dev (optional device scalar) carries the training-progress factor theta = iter/iters of main.py:143,185 so
@@ -761,6 +836,96 @@ __global__ void philox_fill_kernel(float* __restrict__ out, long long n, const u
     } else {
         const float v[4] = {u.x, u.y, u.z, u.w};
         for (int j = 0; j < 4 && i0 + j < n; ++j) out[i0 + j] = v[j];
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Device-side replay buffer: the sampler of the reference's get_trajectories (envs/minipacman.py:122-164) as one
+// kernel.  Episodes live in HBM in fixed slots ([slots][max_len] frames / rewards / actions, ep_len[slot] valid steps;
+// the first *n_filled slots hold an episode).  Row b of the batch is a concatenation of clips:
+//     while remaining > 0:  ep = random.choice(buffer); start = randint(0, len - 3) (or 0); end = min(start + remaining,
+//                           len - 1); take ep[start:end]; dones = [False]*(duration-1) + [True]; remaining -= duration
+// Clip k of row b draws its two uniforms from Philox counter (offset + b*Hn + k), lanes 0 / 1 - i.e. elements
+// 4*(b*Hn+k) and 4*(b*Hn+k)+1 of the scmgan_philox_uniform stream of the same state - so the plan can be re-derived
+// outside (tests) and does not depend on the launch geometry.  One block per batch row: thread 0 lays out the row
+// (which slot / source step every timestep comes from), then the block copies the frames with 128-bit accesses.
+// ----------------------------------------------------------------------------------------------
+struct ReplayParams {
+    const float* frames;   // [slots][max_len][per_frame]
+    const float* rewards;  // [slots][max_len][R]
+    const int* actions;    // [slots][max_len]
+    const int* ep_len;     // [slots]
+    const int* n_filled;   // device scalar
+    int slots, max_len, R;
+    long long per_frame;
+    int B, Hn, random_start;
+    const unsigned long long* rng;  // {seed, offset}
+    float* states;         // [B][Hn][per_frame]
+    float* rewards_out;    // [B][Hn][R]
+    float* dones;          // [B][Hn]
+    long long* actions_out;  // [B][Hn]
+    int* plan;             // optional [B][Hn][3]: (slot, start, duration) of clip k, -1 past the last clip
+};
+
+__global__ void replay_sample_kernel(const ReplayParams P) {
+    pdl_sync();
+    extern __shared__ int rp_smem[];  // [Hn] source slot, [Hn] source step, [Hn] done flag
+    int* src_slot = rp_smem;
+    int* src_step = src_slot + P.Hn;
+    int* src_done = src_step + P.Hn;
+    const int b = blockIdx.x;
+    if (threadIdx.x == 0) {
+        const unsigned long long seed = __ldg(P.rng), off = __ldg(P.rng + 1);
+        const int nf = max(1, min(__ldg(P.n_filled), P.slots));
+        int remaining = P.Hn, pos = 0, k = 0;
+        while (remaining > 0) {
+            const unsigned long long ctr = off + (unsigned long long)b * P.Hn + k;
+            const float u0 = philox_uniform(seed, ctr, 0), u1 = philox_uniform(seed, ctr, 1);
+            const int slot = min(int(u0 * float(nf)), nf - 1);
+            const int len = __ldg(P.ep_len + slot);
+            int start = 0;
+            if (P.random_start) start = min(int(u1 * float(len - 3)), len - 4);  // np.random.randint(0, len - 3)
+            start = max(start, 0);
+            const int end = min(start + remaining, len - 1);
+            const int dur = max(end - start, 1);  // an episode shorter than 2 steps would never terminate the loop
+            for (int i = 0; i < dur && pos < P.Hn; ++i, ++pos) {
+                src_slot[pos] = slot;
+                src_step[pos] = min(start + i, len - 1);
+                src_done[pos] = (i == dur - 1);
+            }
+            if (P.plan) {
+                int* q = P.plan + ((long long)b * P.Hn + k) * 3;
+                q[0] = slot; q[1] = start; q[2] = dur;
+            }
+            remaining -= dur;
+            ++k;
+        }
+        if (P.plan)
+            for (; k < P.Hn; ++k) {
+                int* q = P.plan + ((long long)b * P.Hn + k) * 3;
+                q[0] = -1; q[1] = -1; q[2] = -1;
+            }
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < P.Hn; t += blockDim.x) {
+        const long long src = (long long)src_slot[t] * P.max_len + src_step[t];
+        const long long dst = (long long)b * P.Hn + t;
+        P.dones[dst] = src_done[t] ? 1.f : 0.f;
+        P.actions_out[dst] = (long long)__ldg(P.actions + src);
+        for (int r = 0; r < P.R; ++r) P.rewards_out[dst * P.R + r] = __ldg(P.rewards + src * P.R + r);
+    }
+    const bool vec = (P.per_frame % 4 == 0) && ((reinterpret_cast<uintptr_t>(P.frames) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(P.states) & 15) == 0);
+    for (int t = 0; t < P.Hn; ++t) {
+        const float* s = P.frames + ((long long)src_slot[t] * P.max_len + src_step[t]) * P.per_frame;
+        float* d = P.states + ((long long)b * P.Hn + t) * P.per_frame;
+        if (vec) {
+            const float4* s4 = reinterpret_cast<const float4*>(s);
+            float4* d4 = reinterpret_cast<float4*>(d);
+            for (long long i = threadIdx.x; i < P.per_frame / 4; i += blockDim.x) d4[i] = __ldg(s4 + i);
+        } else {
+            for (long long i = threadIdx.x; i < P.per_frame; i += blockDim.x) d[i] = __ldg(s + i);
+        }
     }
 }
 

@@ -327,6 +327,45 @@ def bce_logits_seq(x, y_bt, mask_bt, loss_t, dx=None):
                                           loss_t.data_ptr(), L.ptr(dx), _stream()), "scmgan_bce_logits_seq")
 
 
+def replay_sample(frames, rewards, actions, ep_len, n_filled, rng_state, states, rewards_out, dones, actions_out,
+                  random_start=True, plan=None):
+    """Device-side get_trajectories (include/scmgan.h: scmgan_replay_sample).  frames [slots, max_len, ...] f32,
+    rewards [slots, max_len, R] f32, actions [slots, max_len] i32, ep_len [slots] i32, n_filled i32 scalar tensor,
+    rng_state i64 [2]; outputs states [B, Hn, ...] f32, rewards_out [B, Hn, R], dones [B, Hn], actions_out i64."""
+    slots, max_len = frames.shape[0], frames.shape[1]
+    B, Hn = states.shape[0], states.shape[1]
+    per = frames[0, 0].numel()
+    for t in (frames, rewards, actions, ep_len, states, rewards_out, dones, actions_out):
+        assert t.is_contiguous()
+    assert actions.dtype == torch.int32 and ep_len.dtype == torch.int32 and n_filled.dtype == torch.int32
+    assert actions_out.dtype == torch.int64 and states[0, 0].numel() == per
+    d = L.ReplayDesc(frames.data_ptr(), rewards.data_ptr(), actions.data_ptr(), ep_len.data_ptr(), n_filled.data_ptr(),
+                     slots, max_len, rewards.shape[2], per, B, Hn, int(bool(random_start)), rng_state.data_ptr(),
+                     states.data_ptr(), rewards_out.data_ptr(), dones.data_ptr(), actions_out.data_ptr(), L.ptr(plan))
+    L.check(L.lib().scmgan_replay_sample(C.byref(d), _stream()), "scmgan_replay_sample")
+
+
+def eval_sqerr(x, y_bt, out):
+    """x [T*B, ...] dense fp32 logits (t-major); y_bt [B, T, ...] view (dense per frame); out [T*B] per-sample MSE of
+    sigmoid(x) against y (reference main.py:812-815)."""
+    B, T = y_bt.shape[0], y_bt.shape[1]
+    per = x.numel() // (T * B)
+    assert x.is_contiguous() and x.shape[0] == T * B and y_bt[0, 0].is_contiguous() and y_bt[0, 0].numel() == per
+    assert out.is_contiguous() and out.numel() == T * B
+    L.check(L.lib().scmgan_eval_sqerr(x.data_ptr(), y_bt.data_ptr(), y_bt.stride(0), y_bt.stride(1), T, B, per,
+                                      out.data_ptr(), _stream()), "scmgan_eval_sqerr")
+
+
+def eval_stats(sqerr, rpred, rewards_bt, dones_bt, table):
+    """sqerr [T*B], rpred [T*B, R] (t-major, dense); rewards_bt [B, T, R], dones_bt [B, T] views; table [T, 5]."""
+    B, T, R = rewards_bt.shape
+    assert sqerr.is_contiguous() and rpred.is_contiguous() and rpred.shape == (T * B, R) and table.is_contiguous()
+    assert R == 1 or rewards_bt.stride(2) == 1
+    L.check(L.lib().scmgan_eval_stats(sqerr.data_ptr(), rpred.data_ptr(), rewards_bt.data_ptr(), rewards_bt.stride(0),
+                                      rewards_bt.stride(1), dones_bt.data_ptr(), dones_bt.stride(0), dones_bt.stride(1),
+                                      T, B, R, table.data_ptr(), _stream()), "scmgan_eval_stats")
+
+
 def masked_mse_seq(pred, target_bt, mask_bt, scale, loss, loss_raw, dpred=None, scale_dev=None):
     """pred [T*B, R] contiguous (t-major); target_bt [B, T, R], mask_bt [B, T] views; loss [1], loss_raw [T]."""
     B, T, R = target_bt.shape

@@ -138,3 +138,85 @@ def play(env, convert_frame, nets, num_actions, no_op=3, max_steps=300, fold_act
         if t > max_steps:
             break
     return total, chosen
+
+
+class GraphedPlanner:
+    """One decision of play() (main.py:356-368) - and the state re-estimate that precedes it (main.py:389-391) - as ONE
+    CUDA graph: encoder + Transition on the three latest frames, then the folded beam (1 + rollout_depth Transition calls
+    and 1 + rollout_depth RewardPredictor calls at batch A * A^2), the "caution" weighting, the max over plans and the
+    argmax over actions, all on the device.  Per decision the host uploads three frames and one action index and reads
+    back A + 1 floats (the scores and the chosen action).
+
+    Spectral-norm bookkeeping is the reference's: 1 + A * (1 + rollout_depth) Transition calls per decision advance
+    u, v that many times (one multi-iteration launch each for the re-estimate and the beam).
+    Bernoulli noise (train-mode modules, the way main.py's play() runs them) comes from the Transition's device-side
+    Philox state, so replays draw fresh noise.
+    """
+
+    def __init__(self, nets, num_actions, rollout_depth=12, rollout_policy="noop", negative_positive_tradeoff=10.0):
+        assert rollout_policy == "noop", "the captured plan table is fixed: only the deterministic roll-out policy"
+        self.nets = nets
+        self.A = num_actions
+        self.depth = rollout_depth
+        self.tradeoff = negative_positive_tradeoff
+        self._graph = None
+        self._plan = None   # device copy of the plan table (uploaded before capture: no host copies inside the graph)
+        self.launches = None
+
+    @torch.no_grad()
+    def _decide(self, frames, prev_action):
+        enc, tr, rew = self.nets["encoder"], self.nets["transition"], self.nets["reward_predictor"]
+        dev, A = frames.device, self.A
+        eye = torch.eye(A, dtype=torch.float32, device=dev)
+        z = tr(enc(frames), eye[prev_action])                      # main.py:389-391 (prev_action: int64 [1])
+        per = 1 + self.depth
+        sig = tr.power_iterations(A * per)
+
+        def rows(k):
+            return torch.stack([sig[a * per + k] for a in range(A)])
+        z_all = tr(z.repeat(A, 1, 1, 1), eye, sigma=rows(0))
+        scores = rollout_scores(z_all, tr, rew, A, 2, self.depth, "noop", self.tradeoff, actions=self._plan,
+                                sigma_for_step=lambda t: rows(1 + t))
+        per_action = scores.view(A, -1).max(dim=1)[0]
+        best = torch.argmax(per_action).to(torch.float32).reshape(1)
+        return torch.cat([per_action, best]), z
+
+    def decide(self, frames, prev_action, use_graph=True):
+        """frames [1, 3, C, H, W] f32 device tensor (the three latest frames), prev_action: int or int64 tensor [1].
+        Returns (best action, per-action scores as a CPU tensor, z of the current state)."""
+        dev = frames.device
+        if not torch.is_tensor(prev_action):
+            prev_action = torch.tensor([int(prev_action)], dtype=torch.int64, device=dev)
+        if self._plan is None:
+            self._plan = beam_actions(self.A, 2, self.depth, "noop").to(dev)
+        if not use_graph:
+            out, z = self._decide(frames, prev_action)
+        else:
+            if self._graph is None:
+                from . import kernels as K
+                static = {"frames": frames.clone(), "prev_action": prev_action.clone()}
+                tr = self.nets["transition"]
+                snap = [(p, p.detach().clone()) for net in self.nets.values() for n_, p in net.named_parameters()
+                        if n_.endswith("weight_u") or n_.endswith("weight_v")]
+                rng = tr._rng_state.clone()
+                s = torch.cuda.Stream()
+                s.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(s):
+                    self._decide(**static)
+                torch.cuda.current_stream().wait_stream(s)
+                with torch.no_grad():
+                    for p, val in snap:
+                        p.copy_(val)
+                    tr._rng_state.copy_(rng)
+                n0 = K.launch_count()
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    out, z = self._decide(**static)
+                self.launches = K.launch_count() - n0
+                self._graph = (graph, static, out, z)
+            graph, static, out, z = self._graph
+            static["frames"].copy_(frames, non_blocking=True)
+            static["prev_action"].copy_(prev_action, non_blocking=True)
+            graph.replay()
+        host = out.cpu()   # the only device->host transfer of the decision
+        return int(host[-1].item()), host[:-1], z

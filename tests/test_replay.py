@@ -1,0 +1,146 @@
+"""Device-side replay buffer (VERDICT r1 missing item 9): scmgan_replay_sample against the
+restated sampler of the reference's get_trajectories (envs/minipacman.py:122-164), bit-exact, and the restatement
+against the reference's own function (CPU, random draws injected)."""
+import os
+import random
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import restated as R  # noqa: E402
+from oracle import shims  # noqa: E402
+
+
+def _episodes(n, C, H, W, Rw, A, seed, lo=6, hi=40):
+    rng = np.random.RandomState(seed)
+    eps = []
+    for _ in range(n):
+        ln = int(rng.randint(lo, hi))
+        eps.append((rng.rand(ln, C, H, W).astype(np.float32), rng.randn(ln, Rw).astype(np.float32),
+                    rng.randint(A, size=ln)))
+    return eps
+
+
+@pytest.mark.skipif(not (shims.reference_available() or os.path.isfile(os.path.join(ROOT, "baseline/_ref/envs/minipacman.py"))),
+                    reason="reference sources not available")
+def test_restated_sampler_matches_reference_get_trajectories(monkeypatch):
+    """The reference's real get_trajectories with random.choice / np.random.randint fed from a recorded uniform stream."""
+    shims.install_stub_modules()
+    import importlib.util
+    src = "/root/reference" if shims.reference_available() else os.path.join(ROOT, "baseline", "_ref")
+    gm = sys.modules["gym_minipacman.envs.minipacman_env"]
+    for name in ("MiniPacman", "ALE"):
+        if not hasattr(gm, name):
+            setattr(gm, name, type(name, (), {"__init__": lambda self, *a, **k: None}))
+    spec = importlib.util.spec_from_file_location("ref_minipacman_env", os.path.join(src, "envs", "minipacman.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    eps = _episodes(9, 3, 5, 4, 2, 5, seed=1)
+    B, T = 6, 17
+    u = np.random.RandomState(2).rand(B, T, 2).astype(np.float32)
+    stream = iter(u.reshape(-1, 2))
+    cur = {}
+
+    def choice(seq):
+        cur["u"] = next(stream)
+        return seq[min(int(np.float32(cur["u"][0]) * np.float32(len(seq))), len(seq) - 1)]
+
+    def randint(lo, hi=None, *a, **k):
+        return min(int(np.float32(cur["u"][1]) * np.float32(hi)), hi - 1)
+
+    class Alive:
+        def is_alive(self):
+            return True
+    mod.initialized, mod.sim_thread = True, Alive()
+    mod.replay_buffer_training[:] = eps
+    monkeypatch.setattr(mod.random, "choice", choice)
+    monkeypatch.setattr(mod.np.random, "randint", randint)
+    ref = mod.get_trajectories(batch_size=B, timesteps=T, random_start=True, training=True)
+    monkeypatch.undo()
+    # the reference consumes one (u0, u1) pair per clip, row after row; hand the restatement the same pairs per row
+    per_row, it = [], iter(u.reshape(-1, 2))
+    for b in range(B):
+        row, remaining = [], T
+        while remaining > 0:
+            uu = next(it)
+            e = min(int(np.float32(uu[0]) * np.float32(len(eps))), len(eps) - 1)
+            ln = len(eps[e][0])
+            start = min(int(np.float32(uu[1]) * np.float32(ln - 3)), ln - 4)
+            remaining -= min(start + remaining, ln - 1) - start
+            row.append(uu)
+        per_row.append(row)
+    got = R.get_trajectories_from_uniforms(eps, per_row, B, T, True)
+    for a, b_ in zip(got[:4], ref):
+        assert a.shape == b_.shape and np.array_equal(a, b_)
+    assert got[2][:, -1].all()   # the last step of every row is flagged done (quirk of the reference, line 153)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("random_start", [True, False])
+def test_device_replay_sampler_bit_exact(random_start):
+    from scm_gan_b200 import kernels as K
+    from scm_gan_b200.data import DeviceReplayBuffer
+    C, H, W, Rw, A = 3, 15, 19, 2, 5
+    buf = DeviceReplayBuffer((C, H, W), Rw, capacity=12, max_len=48, seed=5)
+    eps = _episodes(9, C, H, W, Rw, A, seed=3, lo=6, hi=60)   # some longer than max_len: cut at 48
+    for e in eps:
+        buf.add_episode(*e, training=True)
+    eps = [(s[:48], r[:48], a[:48]) for s, r, a in eps]
+    B, T = 32, 21
+    for rep in range(2):   # second call: the Philox offset has advanced
+        st0 = buf.rng_state.clone()
+        plan = torch.full((B, T, 3), -7, dtype=torch.int32, device="cuda")
+        states, rewards, dones, actions = buf.get_trajectories(B, T, random_start=random_start, plan=plan)
+        assert buf.rng_state[1].item() == st0[1].item() + B * T
+        # the uniforms the kernel drew: elements 4*(b*T+k) + {0, 1} of the same Philox stream
+        u = torch.empty(4 * B * T, device="cuda")
+        K.philox_uniform(u, st0)
+        u = u.view(B, T, 4)[:, :, :2].cpu().numpy()
+        ref = R.get_trajectories_from_uniforms(eps, u, B, T, random_start)
+        assert np.array_equal(states.cpu().numpy(), ref[0])
+        assert np.array_equal(rewards.cpu().numpy(), ref[1])
+        assert np.array_equal(dones.cpu().numpy() > 0.5, ref[2])
+        assert np.array_equal(actions.cpu().numpy(), ref[3])
+        p = plan.cpu().numpy()
+        for b in range(B):
+            for k, clip in enumerate(ref[4][b]):
+                assert tuple(p[b, k]) == clip
+            assert (p[b, len(ref[4][b]):] == -1).all()
+        if random_start:
+            assert len({c[0] for row in ref[4] for c in row}) > 4   # episodes are actually mixed
+
+
+@pytest.mark.gpu
+def test_device_replay_feeds_captured_training_graph():
+    """The sampler as a node of the captured training iteration: zero host->device bytes per step."""
+    from scm_gan_b200.data import DeviceReplayBuffer
+    from scm_gan_b200.synthetic import MovingDotsEnv
+    from scm_gan_b200.train_step import Trainer, build_nets
+    C, H, W, A, Rw, B, Hn = 3, 15, 19, 5, 2, 8, 6
+    buf = DeviceReplayBuffer((C, H, W), Rw, capacity=16, max_len=40, seed=1)
+    env = MovingDotsEnv(C, H, W, A, Rw, seed=2, episode_length=30)
+    rng = np.random.RandomState(0)
+    for _ in range(10):
+        frames, rews, acts = [env.reset()], [np.zeros(Rw, np.float32)], [0]
+        done = False
+        while not done:
+            a = int(rng.randint(A))
+            f, r, done, info = env.step(a)
+            frames.append(f); rews.append(np.array([max(0, r), min(0, r)], np.float32)); acts.append(a)
+        buf.add_episode(np.stack(frames), np.stack(rews), np.array(acts), training=True)
+    nets = build_nets(C, A, Rw, seed=0)
+    tr = Trainer(nets)
+    st, rw, dn, ac = buf.get_trajectories(B, Hn)
+    batch = {"states": st, "rewards": rw, "dones": dn, "actions": ac}
+    static = tr.static_inputs(batch, 0.5, False)
+    losses = []
+    for i in range(6):
+        buf.get_trajectories(B, Hn, out=static)   # device -> device, straight into the graph's inputs
+        losses.append(tr.step(static, 0.5, use_graph=True))
+    vals = [float(v) for v in torch.stack(losses).cpu()]
+    assert all(v == v and v > 0 for v in vals) and len(set(round(v, 6) for v in vals)) > 1   # new batch each step
+    assert tr.captures == 1
