@@ -343,7 +343,11 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device=dev)
+    rank_ms = None
     if world > 1:
+        gathered = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(gathered, t)
+        rank_ms = [round(g[0].item() / args.steps, 4) for g in gathered]   # per-rank device time per step
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
     frames = B * world * T * args.steps
@@ -386,6 +390,12 @@ def main():
                             "note": "algorithmic FLOPs/iter (BASELINE.md section 3) per GPU over the whole step"},
             "use_cuda_graph": use_graph,
         }
+        if rank_ms is not None:
+            out["rank_ms_per_step"] = rank_ms
+            if os.environ.get("SCMGAN_DP_NOSYNC") == "1":
+                # diagnostic run: gradient exchange switched off, so every rank's time is its own compute time; the
+                # spread is the rank skew an exchange has to wait for (NOT a valid training / bench number)
+                out["diagnostic"] = "SCMGAN_DP_NOSYNC=1: no gradient exchange, ranks uncoupled; not a bench value"
         if not args.no_cpu_baseline and world == 1:
             sb = args.cpu_sample_batch or 8
             n_it = 8

@@ -377,8 +377,8 @@ def train_step_loss(nets, states, rewards, dones, actions, *, num_actions, theta
         unswapped = torch.ones((bsz, latent_dim), dtype=states.dtype, device=states.device)
         for i in range(bsz):
             idx_a, idx_b = int(cf_indices[i][0]), int(cf_indices[i][1])
-            unswapped[i, idx_a] = 0
-            unswapped[i, idx_b] = 0
+            unswapped[i, idx_a].zero_()   # (= 0; written as a device-side fill so that a CUDA-graph capture of the
+            unswapped[i, idx_b].zero_()   #  stock-torch baseline does not need a host scalar upload)
             # main.py:253: tuple assignment on views => net effect z[i,idx_a] <- z[i,idx_b]
             z_cf_b[i, idx_a], z_cf_b[i, idx_b] = z_cf_b[i, idx_b], z_cf_b[i, idx_a]
         for t in range(1, counterfactual_horizon):

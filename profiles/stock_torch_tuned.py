@@ -41,6 +41,24 @@ def sn_copy(sd, prefix):
     return w / sigma.expand_as(w)
 
 
+_orig_conv2d, _orig_convT2d = torch.nn.functional.conv2d, torch.nn.functional.conv_transpose2d
+
+
+def _conv2d(x, *a, **k):
+    if _conv2d.nhwc:
+        x = x.contiguous(memory_format=torch.channels_last)
+    return _orig_conv2d(x, *a, **k)
+
+
+def _convT2d(x, *a, **k):
+    if _convT2d.nhwc:
+        x = x.contiguous(memory_format=torch.channels_last)
+    return _orig_convT2d(x, *a, **k)
+
+
+_conv2d.nhwc = _convT2d.nhwc = False
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=10)
@@ -57,6 +75,13 @@ def main():
     torch.backends.cuda.matmul.allow_tf32 = True
     torch.backends.cudnn.allow_tf32 = True
     R.spectral_norm_weight = sn_copy
+    R.F.conv2d, R.F.conv_transpose2d = _conv2d, _convT2d
+
+    def pixel_loss_fp32(target, predicted):   # torch refuses F.binary_cross_entropy under autocast: evaluate it in fp32
+        with torch.autocast("cuda", enabled=False):
+            return _orig_bce(predicted.float(), target.float(), reduction="none").mean(-1).mean(-1).mean(-1)
+    _orig_bce = torch.nn.functional.binary_cross_entropy
+    R.decoder_pixel_loss = pixel_loss_fp32
 
     for variant in args.variants.split(","):
         bf16 = "bf16" in variant
@@ -69,8 +94,6 @@ def main():
         for sd in nets.values():
             for k in list(sd):
                 v = sd[k].to(dev)
-                if nhwc and v.dim() == 4:
-                    v = v.contiguous(memory_format=torch.channels_last)
                 sd[k] = v
                 if v.dtype.is_floating_point and not (k.endswith("_u") or k.endswith("_v") or "bn_conv1" in k):
                     v.requires_grad_(True)
@@ -79,8 +102,9 @@ def main():
         st, rw, dn, ac = R.synthetic_batch(B, Hn, C, H, W, A, Rw, seed=1234)
         st, rw, dn = st.to(dev), rw.to(dev), dn.to(dev)
         ac = torch.as_tensor(ac).to(dev)
-        # (channels_last weights are enough for cuDNN to run NHWC kernels; the frame tensor keeps the layout whose
-        # [B,3,C,H,W] -> [B,3C,H,W] view the algorithm needs, main.py:162 / models.py:141)
+        # NHWC: every convolution receives a channels_last input (no-op once activations are channels_last; the
+        # parameters stay contiguous because the spectral norm views them as matrices, cuDNN re-lays them per call)
+        _conv2d.nhwc = _convT2d.nhwc = nhwc
         g = torch.Generator().manual_seed(1)
         cf_idx, cf_perm = torch.randint(16, (B, 2), generator=g), torch.randperm(B, generator=g).to(dev)
 
@@ -124,7 +148,9 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.iters
             out = {"variant": variant, "ms_per_step": ms, "frames_per_s": B * T / ms * 1e3}
-        except Exception as e:  # a variant torch cannot run (e.g. an op that is not capturable) is reported, not hidden
+        except Exception as e:  # noqa: BLE001 - a variant torch cannot run (e.g. an op that is not capturable) is reported, not hidden
+            import traceback
+            traceback.print_exc()
             out = {"variant": variant, "error": f"{type(e).__name__}: {str(e)[:300]}"}
         out.update({"workload": args.workload, "batch": B, "horizon": Hn, "iters": args.iters,
                     "torch": torch.__version__, "cudnn": torch.backends.cudnn.version(),

@@ -539,13 +539,21 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
                            cudaStream_t st) {
     static const char* off = getenv("SCMGAN_WGRAD_V1");
     if (off && atoi(off)) return 1;
-    if (!ws || W % 16 != 0 || W > 256 || n > 128 || n % 16 != 0) return 1;
+    if (!ws || W > 240 || n > 128 || n % 16 != 0) return 1;
     const int Hp = H + 2, Wp = W + 2;
-    const int BH = std::max(1, std::min(128 / W, H));
-    const int KP = W * BH;
+    // The K dimension runs over the pixels of an image row in steps of 16.  For W % 16 != 0 (MiniPacMan: 19) the row is
+    // padded to Wk pixels INSIDE the TMA boxes: dY comes through the interior view, so pixels W..Wk-1 are out of bounds
+    // and arrive as zeros (they contribute nothing, whatever X holds there); the kernel only ever sees Wk.
+    const int Wk = (W + 15) & ~15;
+    {
+        static const char* v1_ragged = getenv("SCMGAN_WGRAD_V1_RAGGED");  // A/B switch: previous kernel for W % 16 != 0
+        if (Wk != W && v1_ragged && atoi(v1_ragged)) return 1;
+    }
+    const int BH = std::max(1, std::min(128 / Wk, H));
+    const int KP = Wk * BH;
     const int q_aw = (n % 64 == 0) ? 64 : (n % 32 == 0 ? 32 : 16);
     const int q_atoms = n / q_aw;
-    const int wq = (Wp + 7) & ~7;
+    const int wq = (std::max(Wp, Wk + 2) + 7) & ~7;
     if (wq > 256) return 1;
     const int q_atom_bytes = (wq * q_aw * 2 + 1023) & ~1023;
     const int stage_bytes = 2 * KP * 128 + BH * q_atoms * q_atom_bytes;
@@ -553,7 +561,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
     if (stages < 2) return 1;
     WgradV2Params P;
     memset(&P, 0, sizeof(P));
-    P.B = B; P.W = W; P.BH = BH;
+    P.B = B; P.W = Wk; P.BH = BH;
     P.nby = (H + BH - 1) / BH;
     P.num_kblocks = B * P.nby;
     int splits = std::max(1, std::min(P.num_kblocks / 4, std::max(1, num_sms() / 3)));
@@ -575,7 +583,7 @@ static int wgrad_launch_v2(int B, int H, int W, const void* pp, int p_cs, int p_
         const __nv_bfloat16* bp = reinterpret_cast<const __nv_bfloat16*>(pp) + (size_t(Wp) + 1) * p_cs;
         uint64_t dims[4] = {uint64_t(p_cs), uint64_t(W), uint64_t(H), uint64_t(B)};
         uint64_t str[3] = {uint64_t(p_cs) * 2, uint64_t(Wp) * p_cs * 2, uint64_t(Hp) * Wp * p_cs * 2};
-        uint32_t box[4] = {64, uint32_t(W), uint32_t(BH), 1};
+        uint32_t box[4] = {64, uint32_t(Wk), uint32_t(BH), 1};
         int rc = encode_tmap_bf16(&tp, bp, 4, dims, str, box, 128);
         if (rc) return rc;
     }

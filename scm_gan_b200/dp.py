@@ -15,8 +15,14 @@ it, and only the last, smallest one (conv1: 27 C x 128 weights, ~14 KB) is expos
 1.3 MB exchange sat between the end of backward and the optimiser (round 1: 0.26 ms of a 10.3 ms iteration at 8 GPUs).
 The optimiser waits for all of them.  Works eagerly and under CUDA-graph capture (fork/join through stream waits).
 """
+import os
+
 import torch
 import torch.distributed as dist
+
+# Diagnostic only (profiles/r02_notes.md, "rank skew"): skip the exchange, so that every rank runs at its own pace and
+# the per-rank step times show how far the GPUs of one box are apart.  Training with it is wrong by construction.
+_NO_EXCHANGE = os.environ.get("SCMGAN_DP_NOSYNC") == "1"
 
 
 class BucketedGradSync:
@@ -74,6 +80,8 @@ class BucketedGradSync:
             self._launch(b)
 
     def _launch(self, b):
+        if _NO_EXCHANGE:
+            return
         if not self.cuda:
             dist.all_reduce(b["flat"], group=self.pg)
             return

@@ -209,7 +209,7 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     # d pre-activation of conv6: dz * p * (1 - p)
     K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
-    K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
+    K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr, side=True)
     with dr.side_section():
         K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
@@ -217,27 +217,27 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
               sample_scale=rs(4), **dg)                                                                     # d pre5
     for s in range(S):
         K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][4], Bs, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9,
-                g_s_ci=9, db=dbs[s][4], defer=dr)
+                g_s_ci=9, db=dbs[s][4], defer=dr, side=True)
     d4 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, sample_scale=rs(3), **dg)  # d pre4
     for s in range(S):
         K.wgrad(seg(d4, s), seg(act3, s), Gs[s][3], Bs, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9,
-                db=dbs[s][3], defer=dr)
+                db=dbs[s][3], defer=dr, side=True)
     K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, sample_scale=rs(2), **dg)        # d pre3
     for s in range(S):
         K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][2], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
-                g_s_ci=9, db=dbs[s][2], defer=dr)
+                g_s_ci=9, db=dbs[s][2], defer=dr, side=True)
     K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, sample_scale=rs(1),
               **dg)                                                                                         # d pre2
     for s in range(S):
         K.wgrad(seg(DB, s), seg(buf6, s), Gs[s][1], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
-                g_s_ci=9, db=dbs[s][1], defer=dr)
+                g_s_ci=9, db=dbs[s][1], defer=dr, side=True)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, sample_scale=rs(0), **dg)  # d pre1
     c1 = L + A
     for s in range(S):
         K.wgrad(seg(d1, s), seg(zin, s), Gs[s][0], Bs, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L,
-                defer=dr)
+                defer=dr, side=True)
         with dr.side_section():
             K.plane_colsum(seg(d1, s), 0, HID, Bs, H, W, S=S1s[s], db=dbs[s][0])
             K.action_wgrad(S1s[s], a[s * Bs:(s + 1) * Bs], L, Gs[s][0])

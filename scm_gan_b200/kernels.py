@@ -19,6 +19,8 @@ LRELU_SLOPE = 0.01  # F.leaky_relu default used by reference models.py:77-99
 import os as _os
 FWD_DTYPE = torch.bfloat16 if _os.environ.get("SCMGAN_FWD_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
 GRAD_DTYPE = torch.bfloat16
+# experiment switch (profiles/r02_notes.md): weight-gradient kernels of the Transition backward on the side stream
+WGRAD_SIDE = _os.environ.get("SCMGAN_WGRAD_SIDE", "0") == "1"
 
 
 def _fmt(t):
@@ -194,7 +196,7 @@ class DeferredReduces:
 
 
 def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
-          co_valid=None, ci_valid=None, scale=1.0, db=None, defer=None):
+          co_valid=None, ci_valid=None, scale=1.0, db=None, defer=None, side=False):
     d = L.WgradDesc()
     d.B, d.H, d.W = B, H, W
     d.dy, d.dy_cs, d.dy_c_off, d.cout = dy_plane.data_ptr(), dy_plane.shape[3], dy_c_off, cout
@@ -210,6 +212,14 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
         d.workspace, d.workspace_bytes = defer.ring.data_ptr(), defer.ring.numel() * 4
         d.defer_jobs, d.defer_cap = defer.jobs, defer.CAP
         d.defer_count, d.workspace_cursor = C.pointer(defer.count), C.pointer(defer.cursor)
+        if side and WGRAD_SIDE:
+            # the whole weight gradient (tensor-core kernel + reduction) leaves the critical path: it only depends on the
+            # gradient plane produced so far and nothing but the optimiser waits for it, so its CTAs fill the SMs that
+            # the data-gradient chain's kernels leave idle in their last wave
+            with defer.side_section():
+                L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
+                defer.kick()
+            return
         L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
         defer.kick()
         return

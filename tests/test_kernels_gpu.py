@@ -270,6 +270,9 @@ WGRAD_CASES = [
     (2, 16, 16, 16, 128, False),
     (2, 12, 32, 256, 128, True),
     (3, 10, 48, 64, 128, True),
+    # ... and so do other widths, padded to the next multiple of 16 inside the TMA boxes (MiniPacMan: 19 -> 32)
+    (2, 9, 37, 128, 128, True),
+    (1, 20, 70, 64, 128, False),
     # 16 output channels at the bench plane size: nine taps folded into N (conv_wgrad_narrow.cuh)
     (2, 64, 64, 256, 16, True),
     (1, 33, 70, 128, 16, False),

@@ -140,7 +140,7 @@ def test_device_replay_feeds_captured_training_graph():
     losses = []
     for i in range(6):
         buf.get_trajectories(B, Hn, out=static)   # device -> device, straight into the graph's inputs
-        losses.append(tr.step(static, 0.5, use_graph=True))
+        losses.append(tr.step(static, 0.5, use_graph=True).clone())   # the graph's output tensor is reused
     vals = [float(v) for v in torch.stack(losses).cpu()]
     assert all(v == v and v > 0 for v in vals) and len(set(round(v, 6) for v in vals)) > 1   # new batch each step
     assert tr.captures == 1
