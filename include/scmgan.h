@@ -118,6 +118,11 @@ typedef struct {
     const float* sample_scale; /* [B] or NULL: y = acc*scale*sample_scale[b] + ...  Samples of several spectral-norm calls
                                   (different sigma: the main rollout step and the counterfactual rollouts of reference
                                   main.py:242-283) then share one GEMM with weights packed for the first call's sigma. */
+    int coord_c1;              /* CoordConv (reference coordconv.py:5-15): 0 = off; otherwise 1 + the index (even, inside the
+                                  input window) of the x-coordinate channel, the y coordinate follows it.  The two channels
+                                  are GENERATED while the producer stages the im2col tile (x = -1 + 2w/W, y = -1 + 2h/H,
+                                  zero in the padding halo); the plane holds zeros there.  Needs cin == 16, W <= 69 and a
+                                  zero-padded plane; wider layers materialise the channels with scmgan_pack_coords. */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
@@ -155,6 +160,13 @@ int scmgan_gru_conv_sweep_bwd(const scmgan_csrn_sweep_desc* desc_host, scmgan_st
  * its own pass (all four outputs of every Philox block used, full-chip parallelism) is ~10x cheaper than inside the
  * conv epilogue.  Replaces torch.rand_like of DifferentiableBernoulliSampler, reference models.py:27-31. */
 int scmgan_philox_uniform(float* out, long long n, unsigned long long* rng_state, scmgan_stream_t stream);
+
+/* Weight gradient of the two coordinate channels of a CoordConv whose coordinates were generated in the tile
+ * (scmgan_conv_desc::coord_c1): g[co*g_s_co + (coord_c + c)*g_s_ci + tap] = sum_{b,h,w} dy[b][co][h][w] * coord_c(h+ky-1,
+ * w+kx-1), zero outside the image.  dy is the fp32 NCHW incoming gradient.  The tensor-core weight-gradient kernels read
+ * the input plane, which holds zeros in those two channels. */
+int scmgan_coord_wgrad(const float* dy, int B, int Co, int H, int W, float* g, long long g_s_co, long long g_s_ci,
+                       int coord_c, scmgan_stream_t stream);
 
 /* Device-side replay buffer sampler: the reference's get_trajectories (envs/minipacman.py:122-164; same contract in
  * envs/betterpong.py, gridworld.py, ...) without leaving the GPU.  Episodes occupy fixed slots in HBM; the first
@@ -326,11 +338,34 @@ int scmgan_eval_stats(const float* sqerr, const float* rpred, const float* rewar
                       long long r_tstride, const float* dones, long long d_bstride, long long d_tstride, int T, int B,
                       int R, float* table, scmgan_stream_t stream);
 
-/* Separate forward / backward entry points of the same fused kernel (the names SURVEY.md section 8b lists). */
-int scmgan_decoder_bce_fwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
-                           long long per, float* loss, scmgan_stream_t stream);
-int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
-                           long long per, float* loss_scratch, float* dx, scmgan_stream_t stream);
+/* Decoder loss head: the decoder's last convolution, the sigmoid, F.binary_cross_entropy, the means over C,H,W and the
+ * masked batch mean (reference models.py:274-287 conv2 + latent-group sum, main.py:188-197, 310-312) as ONE kernel - the
+ * BCE lives in the convolution's epilogue, the logits never reach memory.
+ *   conv     the last decoder layer as a 16-column head (n = 16 >= n_valid colour channels, act = NONE, no gate / add /
+ *            wrap / sample head) over the T*B hidden planes of all rollout steps, t-major (conv.B = T*B);
+ *            conv.out receives d loss_t / d logits as a zero-halo gradient plane (the input of scmgan_conv3x3_dgrad /
+ *            scmgan_conv3x3_wgrad of the decoder backward); conv.out_f32 (optional) still receives the logits
+ *   target   frames; step t of sample b at target + b*target_bstride + t*target_tstride, dense [C][H][W]
+ *   mask     active mask, element (b, t) at mask + b*mask_bstride + t*mask_tstride, or NULL
+ *   loss_t   [T], loss_t[t] += mean_b( mask[b,t] * mean_chw BCE(sigmoid(logits[t,b]), target[b,t]) )  (zeroed by caller)
+ * scmgan_decoder_bce_bwd applies the chain rule in place: rows of step t of the gradient plane are multiplied by g[t]
+ * (= d total / d loss_t, a device vector); steps with g[t] == 1 - the training step's plain sum of terms - are skipped
+ * on the device without touching the plane. */
+typedef struct {
+    scmgan_conv_desc conv;
+    const float* target;
+    long long target_bstride, target_tstride;
+    const float* mask;
+    long long mask_bstride, mask_tstride;
+    int T, B;
+    float* loss_t;
+    float* workspace;          /* scratch, scmgan_decoder_bce_workspace_rows() * T floats: per-warp partial sums, reduced */
+    long long workspace_bytes; /* in a fixed order by a second small kernel (no atomics: bit-reproducible loss) */
+} scmgan_decoder_bce_desc;
+int scmgan_decoder_bce_workspace_rows(void);
+int scmgan_decoder_bce_fwd(const scmgan_decoder_bce_desc* desc_host, scmgan_stream_t stream);
+int scmgan_decoder_bce_bwd(void* dlogits_plane, int cs, int fmt, const float* g, int T, int B, int H, int W,
+                           scmgan_stream_t stream);
 
 /* Counterfactual regularisers (reference main.py:242-283) on fp32 latents za, zb [B][L][H*W]:
  *   mode 0, disentanglement (258-260): loss += lambda * mean_b( mask[b] * mean_l( mean_hw|za-zb| * unswapped[b][l] ) )

@@ -112,6 +112,26 @@ def main():
     case("tr dz 128->16 (f32)", B, 128, 16, x_dt=G16, f32=True, act=K.ACT_NONE, wrap=False, dgrad=True)
     case("dec conv1 16->64 (B*T)", B * T, 16, 64, x_dt=F16, out_dt=F16, out_cs=128, wrap=False)
     case("dec conv2 64->16 (f32 logits, B*T)", B * T, 64, 16, x_dt=F16, x_cs=128, f32=True, act=K.ACT_NONE, wrap=False)
+    if not args.only or args.only in "dec conv2 + BCE head (fused, B*T)":
+        # fused decoder loss head: conv2 + sigmoid + BCE + means in the epilogue, d logits written as a gradient plane
+        b, nb = B * T, 3
+        hid = plane(b, 128, F16, nb)
+        w = (torch.randn(9, 16, 64, device=dev) * 0.03).to(F16)
+        bias = torch.zeros(3, device=dev)
+        frames = (torch.rand(B, T + 2, 3, H, W, device=dev) < 0.2).float()
+        mask = torch.ones(B, T + 2, device=dev)
+        d2 = [torch.empty(b, H + 2, W + 2, 16, dtype=G16, device=dev) for _ in range(nb)]
+        loss_t = torch.zeros(T, device=dev)
+
+        def fn(i):
+            K.decoder_bce_fwd(hid[i % nb], w, T, B, H, W, cin=64, bias=bias, n_valid=3, dlogits_plane=d2[i % nb],
+                              target_bt=frames[:, 1:T + 1], mask_bt=mask[:, 1:T + 1], loss_t=loss_t)
+        us = timeit(fn)
+        alg = b * H * W * (64 * 2 + 16 * 2 + 3 * 4)
+        results.append(dict(layer="dec conv2 + BCE head (fused, B*T)", batch=b, cin=64, n=16, us=round(us, 2),
+                            alg_gbs=round(alg / us / 1e3, 1), hbm_frac=round(alg / us / 1e3 / HBM, 3)))
+        print(f"{'dec conv2 + BCE head (fused, B*T)':46s} B={b:4d} cin= 64 n= 16: {us:7.1f} us  (memset + conv + finalize)  "
+              f"{alg / us / 1e3:7.1f} GB/s algorithmic", flush=True)
     case("dec d1 16->64 (gated dgrad, B*T)", B * T, 16, 64, x_dt=G16, out_dt=G16, out_cs=128, gate_cs=128, act=K.ACT_NONE,
          wrap=False, dgrad=True)
     case("dec dz 64->16 (f32, B*T)", B * T, 64, 16, x_dt=G16, x_cs=128, f32=True, act=K.ACT_NONE, wrap=False, dgrad=True)

@@ -34,7 +34,14 @@ class ConvDesc(C.Structure):
                 ("out_f32", C.c_void_p), ("n_valid", C.c_int),
                 ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p),
                 ("bias_n", C.c_int), ("x_fmt", C.c_int), ("w_fmt", C.c_int), ("out_fmt", C.c_int),
-                ("sample_scale", C.c_void_p)]
+                ("sample_scale", C.c_void_p), ("coord_c1", C.c_int)]
+
+
+class DecoderBceDesc(C.Structure):
+    _fields_ = [("conv", ConvDesc), ("target", C.c_void_p), ("target_bstride", C.c_longlong),
+                ("target_tstride", C.c_longlong), ("mask", C.c_void_p), ("mask_bstride", C.c_longlong),
+                ("mask_tstride", C.c_longlong), ("T", C.c_int), ("B", C.c_int), ("loss_t", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_longlong)]
 
 
 class WgradReduceJob(C.Structure):
@@ -111,6 +118,8 @@ SIGNATURES = {
                                       C.c_void_p]),
     "scmgan_bce_logits": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_coord_wgrad": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong,
+                                     C.c_longlong, C.c_int, C.c_void_p]),
     "scmgan_replay_sample": (C.c_int, [C.POINTER(ReplayDesc), C.c_void_p]),
     "scmgan_eval_sqerr": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_longlong, C.c_int, C.c_int, C.c_longlong,
                                     C.c_void_p, C.c_void_p]),
@@ -120,10 +129,10 @@ SIGNATURES = {
                                          C.c_void_p]),
     "scmgan_reward_head_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                          C.c_void_p]),
-    "scmgan_decoder_bce_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
-                                         C.c_void_p, C.c_void_p]),
-    "scmgan_decoder_bce_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong, C.c_void_p, C.c_int, C.c_longlong,
-                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "scmgan_decoder_bce_fwd": (C.c_int, [C.POINTER(DecoderBceDesc), C.c_void_p]),
+    "scmgan_decoder_bce_workspace_rows": (C.c_int, []),
+    "scmgan_decoder_bce_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p]),
     "scmgan_cf_loss_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p]),
     "scmgan_cf_loss_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int,

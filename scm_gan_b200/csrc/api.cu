@@ -123,6 +123,34 @@ static bool pdl_enabled() {
     static const bool on = [] { const char* e = getenv("SCMGAN_NO_PDL"); return !(e && atoi(e)); }();
     return on;
 }
+// Launch bookkeeping for the pre-wait weight load of conv_igemm_v3.cuh: launches of this library on `st` since the last
+// scmgan_pack_weights on it.  The load is hoisted above griddepcontrol.wait only when at least one library kernel (every
+// one of them starts with griddepcontrol.wait) sits between the pack and the convolution on the same stream.
+// SCMGAN_NO_PREWAIT=1 switches it off.
+static thread_local cudaStream_t t_pack_stream[4] = {nullptr, nullptr, nullptr, nullptr};
+static thread_local int t_pack_since[4] = {1 << 20, 1 << 20, 1 << 20, 1 << 20};
+static thread_local bool t_pack_used[4] = {false, false, false, false};
+static void note_launch(cudaStream_t st, bool is_pack) {
+    int slot = -1;
+    for (int i = 0; i < 4; ++i)
+        if (t_pack_used[i] && t_pack_stream[i] == st) slot = i;
+    if (slot < 0) {
+        if (!is_pack) return;
+        for (int i = 0; i < 4 && slot < 0; ++i)
+            if (!t_pack_used[i]) slot = i;
+        if (slot < 0) slot = 0;  // recycle: the evicted stream becomes "unknown", for which nothing is hoisted
+        t_pack_used[slot] = true; t_pack_stream[slot] = st;
+    }
+    t_pack_since[slot] = is_pack ? 0 : t_pack_since[slot] + 1;
+}
+static bool prewait_weights_ok(cudaStream_t st) {
+    static const bool off = [] { const char* e = getenv("SCMGAN_NO_PREWAIT"); return e && atoi(e); }();
+    if (off) return false;
+    for (int i = 0; i < 4; ++i)
+        if (t_pack_used[i] && t_pack_stream[i] == st) return t_pack_since[i] >= 1;
+    return false;  // unknown stream: be conservative
+}
+
 template <typename... KArgs, typename... Args>
 static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg;
@@ -134,6 +162,7 @@ static void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sme
     cfg.attrs = attr;
     cfg.numAttrs = pdl_enabled() ? 1 : 0;
     (void)cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);  // errors are picked up by cudaGetLastError()
+    note_launch(st, false);
 }
 
 constexpr int kSmemBudget = 200 * 1024;  // tiles; barriers/alignment slack on top (<= 227 KB per CTA)
@@ -161,8 +190,17 @@ constexpr int kSmemMax = 227 * 1024;
 template <int CK, int TPG>
 static int launch_v2_inst(const CUtensorMap& ta, const CUtensorMap& tb, const IgemmParams& P, const IgemmV2Geom& G,
                           int gx, int nsplit, int smem, cudaStream_t st) {
-    SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG>), kSmemMax);
-    launch_k(conv3x3_igemm_v2_kernel<CK, TPG>, dim3(dim3(gx, nsplit)), dim3(v2_threads<CK>()), size_t(smem), st, ta, tb, P, G);
+    // one instantiation per epilogue family (conv_igemm_v2.cuh: HEAD)
+    if (P.bce_ws) {
+        SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG, kHeadBce>), kSmemMax);
+        launch_k(conv3x3_igemm_v2_kernel<CK, TPG, kHeadBce>, dim3(dim3(gx, nsplit)), dim3(v2_threads<CK>()), size_t(smem), st, ta, tb, P, G);
+    } else if (P.out_f32) {
+        SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG, kHeadF32>), kSmemMax);
+        launch_k(conv3x3_igemm_v2_kernel<CK, TPG, kHeadF32>, dim3(dim3(gx, nsplit)), dim3(v2_threads<CK>()), size_t(smem), st, ta, tb, P, G);
+    } else {
+        SCM_OPT_IN_SMEM((conv3x3_igemm_v2_kernel<CK, TPG, kHeadPlane>), kSmemMax);
+        launch_k(conv3x3_igemm_v2_kernel<CK, TPG, kHeadPlane>, dim3(dim3(gx, nsplit)), dim3(v2_threads<CK>()), size_t(smem), st, ta, tb, P, G);
+    }
     SCM_CUDA(cudaGetLastError());
     return SCM_OK;
 }
@@ -206,6 +244,10 @@ static int launch_igemm_v3(const scmgan_conv_desc* d, const IgemmParams& P0, lon
         break;
     }
     if (!tpg) return 1;
+    if (P.coord_c >= 0 && !G.a_soft) {
+        set_error("conv3x3: in-tile coordinate channels need the software-staged producer (cin == 16, W <= 69)");
+        return SCM_EUNSUPPORTED;
+    }
     G.groups = 9 / tpg;
     const int pairs = std::max(1, std::min(P.num_tiles, num_sms() / 2));
     G.tiles_stride = pairs;
@@ -330,7 +372,7 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st);
 static int launch_expand(const scmgan_conv_desc* d, cudaStream_t st) {
     static const char* off = getenv("SCMGAN_NO_EXPAND");
     if (off && atoi(off)) return 1;
-    if (d->cin != 16 || (d->n != 64 && d->n != 128) || !d->out || d->out_f32 || d->add) return 1;
+    if (d->cin != 16 || (d->n != 64 && d->n != 128) || !d->out || d->out_f32 || d->add || d->coord_c1) return 1;
     if (d->W > 128 || d->W < 2 || d->H < 2) return 1;
     ExpandParams P;
     memset(&P, 0, sizeof(P));
@@ -393,6 +435,8 @@ static int launch_expand(const scmgan_conv_desc* d, cudaStream_t st) {
     ++g_launches;
     return SCM_OK;
 }
+
+static thread_local const scmgan_decoder_bce_desc* t_bce = nullptr;  // set by scmgan_decoder_bce_fwd around conv_impl
 
 static int conv_impl(const scmgan_conv_desc* d, cudaStream_t st) {
     const int rc = conv_impl_inner(d, st);
@@ -458,6 +502,19 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
         const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? atoi(dbg) : 0;
     }
+    P.prewait_weights = prewait_weights_ok(st) ? 1 : 0;
+    P.coord_c = d->coord_c1 - 1;
+    if (d->coord_c1) {
+        SCM_REQUIRE(d->coord_c1 > 0 && d->coord_c1 % 2 == 1 && d->coord_c1 + 1 <= d->cin,
+                    "conv3x3: coordinate channels must be an even-aligned pair inside the input window");
+        SCM_REQUIRE(d->cin == 16 && d->W + 2 <= 71 && !d->wrap,
+                    "conv3x3: in-tile coordinate channels need cin == 16, W <= 69 and a zero-padded plane");
+    }
+    if (t_bce) {
+        P.bce_y = t_bce->target; P.bce_ybs = t_bce->target_bstride; P.bce_yts = t_bce->target_tstride;
+        P.bce_mask = t_bce->mask; P.bce_mbs = t_bce->mask_bstride; P.bce_mts = t_bce->mask_tstride;
+        P.bce_B = t_bce->B; P.bce_T = t_bce->T; P.bce_ws = t_bce->workspace;
+    }
 
     {
         static const char* v1env = getenv("SCMGAN_IGEMM_V1");
@@ -473,6 +530,8 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
             if (rc <= 0) return rc;  // launched (0) or failed (<0); 1 = shape does not fit -> first-generation kernel
         }
     }
+    SCM_REQUIRE(!d->coord_c1, "conv3x3: in-tile coordinate channels are not available in the first-generation kernel");
+    SCM_REQUIRE(!t_bce, "decoder_bce_fwd: shape not covered by the weight-stationary kernel (cin=%d)", d->cin);
     CUtensorMap ta, tb;
     {
         uint64_t dims[2] = {uint64_t(d->x_cs), uint64_t(rows)};
@@ -837,6 +896,7 @@ int scmgan_pack_weights(int count, const scmgan_pack_job* jobs, scmgan_stream_t 
         const int threads = 256;
         const int bx = int(std::min<long long>((max_total + threads - 1) / threads, 296));
         launch_k(pack_weights_kernel, dim3(dim3(bx, J.count)), dim3(threads), size_t(0), (cudaStream_t)stream, J);
+        note_launch((cudaStream_t)stream, true);  // operands change: no pre-wait weight load in the very next kernel
         SCM_CUDA(cudaGetLastError());
     ++g_launches;
     }
@@ -1129,6 +1189,15 @@ int scmgan_bce_logits(const float* x, const float* y, long long y_bstride, const
     return scmgan_bce_logits_seq(x, y, y_bstride, 0, mask, 1, 0, 1, B, per, loss, dx, stream);
 }
 
+int scmgan_coord_wgrad(const float* dy, int B, int Co, int H, int W, float* g, long long g_s_co, long long g_s_ci,
+                       int coord_c, scmgan_stream_t stream) {
+    SCM_REQUIRE(dy && g && B > 0 && Co > 0 && H > 0 && W > 0 && coord_c >= 0, "coord_wgrad: bad arguments");
+    launch_k(coord_wgrad_kernel, dim3(Co), dim3(256), size_t(0), (cudaStream_t)stream, dy, B, Co, H, W, g, g_s_co, g_s_ci, coord_c);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
+}
+
 int scmgan_eval_sqerr(const float* x, const float* y, long long y_bstride, long long y_tstride, int T, int B,
                       long long per, float* out, scmgan_stream_t stream) {
     SCM_REQUIRE(x && y && out && T > 0 && B > 0 && per > 0, "eval_sqerr: bad arguments");
@@ -1207,15 +1276,45 @@ int scmgan_transition_tail(const float* x, const float* uniforms, long long n, f
     return SCM_OK;
 }
 
-int scmgan_decoder_bce_fwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
-                           long long per, float* loss, scmgan_stream_t stream) {
-    return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss, nullptr, stream);
+int scmgan_decoder_bce_fwd(const scmgan_decoder_bce_desc* d, scmgan_stream_t stream) {
+    SCM_REQUIRE(d != nullptr, "decoder_bce_fwd: null descriptor");
+    const scmgan_conv_desc& c = d->conv;
+    SCM_REQUIRE(d->target && d->loss_t && d->T > 0 && d->B > 0 && c.B == d->T * d->B,
+                "decoder_bce_fwd: bad arguments (conv.B must be T*B, t-major)");
+    SCM_REQUIRE(c.n == 16 && c.out && c.out_c_off == 0 && c.act == SCMGAN_ACT_NONE && !c.gate && !c.add && !c.wrap &&
+                !c.sample_out, "decoder_bce_fwd: conv2 must be a plain 16-column head writing a zero-halo plane");
+    SCM_REQUIRE(c.n_valid > 0 && c.n_valid <= 16, "decoder_bce_fwd: bad n_valid=%d", c.n_valid);
+    // per-warp partial sums: one row [T] per epilogue warp of every CTA the weight-stationary kernel can launch
+    const int ws_rows = scmgan_decoder_bce_workspace_rows();
+    SCM_REQUIRE(d->workspace && d->workspace_bytes >= (long long)ws_rows * d->T * 4,
+                "decoder_bce_fwd: workspace of %d x T floats required", ws_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    // rows of CTAs / warps that do not exist in this launch must read as zero
+    SCM_CUDA(cudaMemsetAsync(d->workspace, 0, size_t(ws_rows) * d->T * 4, st));
+    t_bce = d;
+    const int rc = conv_impl(&c, st);
+    t_bce = nullptr;
+    if (rc) return rc;
+    launch_k(bce_finalize_kernel, dim3(d->T), dim3(256), size_t(0), st, (const float*)d->workspace, ws_rows, d->T, d->loss_t);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
 }
 
-int scmgan_decoder_bce_bwd(const float* x, const float* y, long long y_bstride, const float* mask, int B,
-                           long long per, float* loss_scratch, float* dx, scmgan_stream_t stream) {
-    SCM_REQUIRE(dx != nullptr && loss_scratch != nullptr, "decoder_bce_bwd: dx and a scratch scalar are required");
-    return scmgan_bce_logits(x, y, y_bstride, mask, B, per, loss_scratch, dx, stream);
+int scmgan_decoder_bce_workspace_rows(void) { return 2 * num_sms() * 16; }
+
+int scmgan_decoder_bce_bwd(void* dlogits_plane, int cs, int fmt, const float* g, int T, int B, int H, int W,
+                           scmgan_stream_t stream) {
+    SCM_REQUIRE(dlogits_plane && g && cs > 0 && cs % 8 == 0 && T > 0 && B > 0 && H > 0 && W > 0 && (fmt | 1) == 1,
+                "decoder_bce_bwd: bad arguments");
+    const long long per_step = (long long)B * (H + 2) * (W + 2) * cs;  // 16-bit elements of one rollout step
+    SCM_REQUIRE(per_step % 8 == 0, "decoder_bce_bwd: plane size");
+    const int bx = int(std::min<long long>((per_step / 8 + 255) / 256, std::max(1, 8 * num_sms() / T)));
+    launch_k(plane_scale_steps_kernel, dim3(dim3(bx, T)), dim3(256), size_t(0), (cudaStream_t)stream,
+             reinterpret_cast<uint4*>(dlogits_plane), per_step / 8, g, fmt);
+    SCM_CUDA(cudaGetLastError());
+    ++g_launches;
+    return SCM_OK;
 }
 
 static int csrn_fill(const scmgan_csrn_sweep_desc* d, CsrnSweepParams& P, bool bwd) {

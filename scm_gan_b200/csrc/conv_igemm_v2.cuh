@@ -47,7 +47,13 @@ template <int CK> struct V2Epi { static constexpr int kWarps = (CK == 16) ? 16 :
 template <int CK> constexpr int v2_threads() { return 64 + 32 * V2Epi<CK>::kWarps; }
 
 // CK: channels per K chunk (64 -> 128B swizzle, 16 -> 32B swizzle).  TPG: filter taps served by one stage.
-template <int CK, int TPG>
+// HEAD selects the epilogue family compiled into the instantiation, so that no variant pays for the registers (spills in
+// the epilogue were measured: conv6 39 -> 69 us) and the instruction-cache footprint of the others:
+//   kHeadPlane  16-bit plane output only (hidden layers, data gradients)
+//   kHeadF32    fp32 NCHW outputs: logits / dz / probabilities + Bernoulli head (optionally with a plane as well)
+//   kHeadBce    fused decoder loss head (scmgan_decoder_bce_fwd)
+constexpr int kHeadPlane = 0, kHeadF32 = 1, kHeadBce = 2;
+template <int CK, int TPG, int HEAD = kHeadPlane>
 __global__ void __launch_bounds__(v2_threads<CK>(), 1)
 conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                         const __grid_constant__ IgemmParams P, const __grid_constant__ IgemmV2Geom G) {
@@ -74,6 +80,7 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     constexpr int kGroups = 9 / TPG;
     constexpr int kEpiWarps = V2Epi<CK>::kWarps;
     constexpr int kShare = kEpiWarps / 4;
+    constexpr bool BCE = HEAD == kHeadBce;
 
     if (warp == 0 && lane == 0) {
         prefetch_tmap(&tmap_a);
@@ -140,14 +147,41 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                         const __nv_bfloat16* src = P.a + (ok ? size_t(row) * P.a_cs + P.a_c_off + (i & 1) * 8 : 0);
                         uint32_t ad = sa + uint32_t(i) * 16u;
                         ad ^= (ad >> 3) & 16u;
-                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ad), "l"(src),
-                                     "r"(ok ? 16u : 0u)
-                                     : "memory");
+                        if (P.coord_c >= 0 && ok && (i & 1) == (P.coord_c >> 3)) {
+                            // CoordConv (reference coordconv.py:10-14): this 16-byte chunk of the pixel holds the two
+                            // coordinate channels.  They exist nowhere in memory - the plane carries zeros there - and
+                            // are generated here, while the im2col super tile is staged: x = -1 + 2w/W, y = -1 + 2h/H on
+                            // interior pixels, 0 in the zero-padding halo (the reference pads AFTER concatenating).
+                            uint4 q4 = __ldg(reinterpret_cast<const uint4*>(src));
+                            const int plane = P.Hp * P.Wp;
+                            const int rem = row % plane;
+                            const int hp = rem / P.Wp, wp = rem - hp * P.Wp;
+                            if (hp >= 1 && hp <= P.H && wp >= 1 && wp <= P.W) {
+                                const uint32_t cw = pack2_fmt(-1.f + 2.f * float(wp - 1) / float(P.W),
+                                                              -1.f + 2.f * float(hp - 1) / float(P.H), P.a_fmt);
+                                const int wi = (P.coord_c & 7) >> 1;
+                                if (wi == 0) q4.x = cw; else if (wi == 1) q4.y = cw; else if (wi == 2) q4.z = cw; else q4.w = cw;
+                            }
+                            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(ad), "r"(q4.x), "r"(q4.y),
+                                         "r"(q4.z), "r"(q4.w)
+                                         : "memory");
+                        } else {
+                            asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(ad), "l"(src),
+                                         "r"(ok ? 16u : 0u)
+                                         : "memory");
+                        }
                     }
                 }
-                // every lane: one (non-incrementing) arrival on the stage's full barrier once its copies have landed
-                asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage]))
-                             : "memory");
+                if (P.coord_c >= 0) {
+                    // mixed cp.async / st.shared staging: wait for the copies, publish both to the async proxy, arrive
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    fence_proxy_async_smem();
+                    mbar_arrive(&full_bar[stage]);
+                } else {
+                    // every lane: one (non-incrementing) arrival on the stage's full barrier once its copies have landed
+                    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[stage]))
+                                 : "memory");
+                }
                 if (++stage == G.num_stages) { stage = 0; phase ^= 1; }
             }
         } else
@@ -232,26 +266,46 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         const int half = ew >> 2;  // which of the kShare warps sharing this lane quarter
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride) {
+        BceCarry bce{nullptr, -1, 0.f};
+        if constexpr (BCE)   // fused decoder loss head: this warp's row of the (zeroed) scratch table
+            bce.row = P.bce_ws + (size_t(blockIdx.y * gridDim.x + blockIdx.x) * kEpiWarps + ew) * P.bce_T;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < P.num_tiles; tile += G.tiles_stride, ++it) {
             const int p = tile * 128 + q * 32 + lane;
             const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(acc * kAccStageCols);
-            if (P.out_f32 && !P.out && G.n_cta == 16)
-                igemm_epilogue_tile<8, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
-                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
-            else if (P.out_f32)
-                igemm_epilogue_tile<16, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
-                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
-            else if ((G.n_cta & 31) == 0 && G.n_cta >= 32 * kShare)  // else 16-column groups keep more warps busy
-                igemm_epilogue_tile<32, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
-                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
-            else
-                igemm_epilogue_tile<16, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
-                                              &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
+            if constexpr (BCE) {
+                // Fused decoder loss head (host side guarantees n = 16, a plane output, no activation).  The single
+                // 16-column group leaves nothing to share between the warps of a lane quarter, and the head's epilogue is
+                // a long dependent chain (target loads, exp / log, stores) - longer than the tile's main loop.  The
+                // kShare warps of a quarter therefore take TURNS: warp `half` owns every kShare-th tile and has kShare
+                // tile periods for it; the others only acknowledge the accumulator (after it is full, so that an
+                // acknowledgement can never land in the previous use of the stage).
+                if (it % kShare == half)
+                    igemm_epilogue_tile<16, true, kShare, true>(P, G.n_total, n0, G.n_cta, p, 0, lane, taddr, s_bias,
+                                                  &acc_full[acc], acc_phase, p + kShare * G.tiles_stride * 128, &bce);
+                else
+                    mbar_wait(&acc_full[acc], acc_phase);
+            } else if constexpr (HEAD == kHeadF32) {
+                if (!P.out && G.n_cta == 16)
+                    igemm_epilogue_tile<8, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                                  &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
+                else
+                    igemm_epilogue_tile<16, true, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                                  &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
+            } else {
+                if ((G.n_cta & 31) == 0 && G.n_cta >= 32 * kShare)  // else 16-column groups keep more warps busy
+                    igemm_epilogue_tile<32, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                                  &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
+                else
+                    igemm_epilogue_tile<16, false, kShare>(P, G.n_total, n0, G.n_cta, p, half, lane, taddr, s_bias,
+                                                  &acc_full[acc], acc_phase, p + G.tiles_stride * 128);
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if constexpr (BCE) bce.flush(lane);
     }
 
     tc_fence_before();

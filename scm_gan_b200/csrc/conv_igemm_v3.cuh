@@ -65,10 +65,13 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_alloc_pair(tmem_slot, 512);
         tmem_relinquish_pair();
     }
-    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < n_full; i += 32 * kV2EpiWarps) s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
-    }
+    // Programmatic dependent launch: everything up to pdl_sync() overlaps the previous kernel's tail.  With
+    // P.prewait_weights the resident weight operand is part of that: it was packed at least two launches ago, and a
+    // kernel can only start once its predecessor's CTAs have passed their own griddepcontrol.wait, i.e. once the
+    // launch before THAT has completed - so the 147 KB weight load of every CTA runs while the chip still drains the
+    // predecessor's last wave instead of in front of the first activation tile.
+    const bool early_b = P.prewait_weights && !G.b_streamed;
+    if (!early_b) pdl_sync();
     tc_fence_before();
     __syncthreads();
     cluster_sync_all();  // barriers of both CTAs initialised before any remote arrive / multicast commit
@@ -76,9 +79,7 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
     const uint32_t tmem_base = *tmem_slot;
     // leader-side barrier addresses as seen from this CTA
     const uint32_t b_full_L = mapa_shared(smem_u32(b_full), 0);
-
     if (warp == 0) {
-        // ------------------------------ TMA producer (both CTAs) ------------------------------
         if (!G.b_streamed && elect_one()) {
             // resident weights: this CTA's N half of every [tap][chunk] tile
             const uint32_t bytes = uint32_t(9 * chunks * G.n_cta * RB);
@@ -89,6 +90,15 @@ conv3x3_igemm_v3_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                      tap * n_full + int(rank) * G.n_cta);
         }
         __syncwarp();
+    }
+    if (early_b) pdl_sync();
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < n_full; i += 32 * kV2EpiWarps) s_bias[i] = (P.bias && i < P.bias_n) ? P.bias[i] : 0.f;
+    }
+    __syncthreads();  // s_bias
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer (both CTAs) ------------------------------
         int stage = 0;
         uint32_t phase = 0;
         const uint32_t tx = uint32_t(G.loads * G.box_rows * RB) + (G.b_streamed ? 9u * uint32_t(G.n_cta * RB) : 0u);

@@ -481,6 +481,88 @@ __global__ void bce_logits_kernel(const float* __restrict__ x, const float* __re
 }
 
 // ----------------------------------------------------------------------------------------------
+// Fused decoder loss head, second half: loss_t[t] += sum over the per-warp partial rows written by the conv epilogue
+// (igemm_epilogue.cuh, BceCarry), in a fixed order.
+// ----------------------------------------------------------------------------------------------
+__global__ void bce_finalize_kernel(const float* __restrict__ ws, int rows, int T, float* __restrict__ loss_t) {
+    pdl_sync();
+    __shared__ float red[33];
+    const int t = blockIdx.x;   // one block per rollout step
+    float acc = 0.f;
+    for (int r = threadIdx.x; r < rows; r += blockDim.x) acc += ws[(long long)r * T + t];
+    acc = block_sum(acc, red);
+    if (threadIdx.x == 0) loss_t[t] += acc;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Backward companion of the fused decoder loss head: the plane holds d loss_t / d logits of every rollout step t
+// (t-major); the chain rule needs g[t] = d total / d loss_t on top.  The training step sums the terms (g = 1), so the
+// kernel reads g[t] first and leaves step t alone when it is exactly 1 - one 4-byte load per block instead of a
+// read-modify-write pass over the plane.
+// ----------------------------------------------------------------------------------------------
+__global__ void plane_scale_steps_kernel(uint4* __restrict__ plane, long long vec_per_step, const float* __restrict__ g,
+                                         int fmt) {
+    pdl_sync();
+    const float k = __ldg(g + blockIdx.y);
+    if (k == 1.f) return;
+    uint4* base = plane + (long long)blockIdx.y * vec_per_step;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < vec_per_step;
+         i += (long long)gridDim.x * blockDim.x) {
+        uint4 q = base[i];
+        uint32_t* w = reinterpret_cast<uint32_t*>(&q);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float lo, hi;
+            if (fmt == FMT_F16) {
+                const __half2 h = *reinterpret_cast<const __half2*>(&w[j]);
+                lo = __low2float(h); hi = __high2float(h);
+            } else {
+                const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&w[j]);
+                lo = __low2float(h); hi = __high2float(h);
+            }
+            w[j] = pack2_fmt(lo * k, hi * k, fmt);
+        }
+        base[i] = q;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Weight gradient of the two CoordConv coordinate channels.  The coordinates are generated inside the convolution's
+// im2col tile and never stored, so the tensor-core weight-gradient kernels (which read the input plane) see zeros there;
+// their gradient is a plain correlation of dy with two known ramps:
+//   g[co][coord_c + c][ky][kx] = sum_{b,h,w} dy[b][co][h][w] * coord_c(h + ky - 1, w + kx - 1)   (0 outside the image)
+// dy: fp32 NCHW (the op's incoming gradient).  One block per output channel, fixed-order reduction (deterministic).
+__global__ void coord_wgrad_kernel(const float* __restrict__ dy, int B, int Co, int H, int W, float* __restrict__ g,
+                                   long long g_s_co, long long g_s_ci, int coord_c) {
+    pdl_sync();
+    __shared__ float red[33];
+    const int co = blockIdx.x;
+    float acc[18];
+#pragma unroll
+    for (int i = 0; i < 18; ++i) acc[i] = 0.f;
+    const long long n = (long long)B * H * W;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+        const int w = int(i % W), h = int((i / W) % H), b = int(i / ((long long)W * H));
+        const float d = __ldg(dy + (((long long)b * Co + co) * H + h) * W + w);
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int hh = h + ky - 1, ww = w + kx - 1;
+                if (hh >= 0 && hh < H && ww >= 0 && ww < W) {
+                    acc[ky * 3 + kx] = fmaf(d, -1.f + 2.f * float(ww) / float(W), acc[ky * 3 + kx]);
+                    acc[9 + ky * 3 + kx] = fmaf(d, -1.f + 2.f * float(hh) / float(H), acc[9 + ky * 3 + kx]);
+                }
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < 18; ++i) {
+        const float s = block_sum(acc[i], red);
+        if (threadIdx.x == 0) g[(long long)co * g_s_co + (long long)(coord_c + i / 9) * g_s_ci + (i % 9)] = s;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // Rollout-MSE evaluation (reference measure_prediction_mse, main.py:784-836).  The decoder / reward predictor are
 // stateless, so all steps of the evaluation rollout are decoded as one batch; these two kernels turn the logits into the
 // four per-step curves without a single host round trip (the reference reads four scalars back per step).

@@ -32,6 +32,27 @@ __device__ __forceinline__ void epi_reg_fence8(float* v) {
     asm volatile("" : "+f"(v[0]), "+f"(v[1]), "+f"(v[2]), "+f"(v[3]), "+f"(v[4]), "+f"(v[5]), "+f"(v[6]), "+f"(v[7]));
 }
 
+// Fused decoder loss head: per-warp running sum of the current rollout step's loss share.  Every epilogue warp owns one
+// row [T] of a scratch table; a step's share is added to it when the warp moves on to another step (tiles of one warp
+// visit the steps in increasing order) and at the end of the kernel, and bce_finalize_kernel sums the rows in a fixed
+// order: no atomics, the same bits on every run.
+struct BceCarry {
+    float* row;  // this warp's scratch row [T]
+    int t;       // step of the running sum (-1: none)
+    float sum;
+    __device__ __forceinline__ void add(int step, float v, int lane) {
+        if (step != t) {
+            flush(lane);
+            t = step;
+        }
+        sum += v;
+    }
+    __device__ __forceinline__ void flush(int lane) {
+        if (t >= 0 && lane == 0) row[t] += sum;
+        sum = 0.f;
+    }
+};
+
 struct EpiRow {
     int p, b, hp, wp;
     bool valid, interior;
@@ -63,10 +84,14 @@ __device__ __forceinline__ EpiRow epi_decode_row(const IgemmParams& P, int p) {
 // gate plane (a saved forward activation, usually in HBM) overlaps the MMAs instead of stalling every column group.
 // SHARE: epilogue warps per TMEM lane quarter (2, or 4 in the narrow-K kernel whose short main loop leaves the
 // epilogue exposed); the warps of a quarter interleave the column groups.
-template <int GROUP, bool F32, int SHARE = 2>
+// BCE: fused decoder loss head (IgemmParams::bce_*; only with GROUP = 16, a plane output and no activation): the group's
+// 16 columns are the (padded) colour channels of one pixel, v becomes d loss / d logit and the warp adds its share of the
+// masked BCE mean of the tile's rollout step to its BceCarry.
+template <int GROUP, bool F32, int SHARE = 2, bool BCE = false>
 __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_total, int n0, int ncols_cta, int p,
                                                     int half, int lane, uint32_t taddr, const float* s_bias,
-                                                    uint64_t* acc_bar, uint32_t acc_phase, int p_next) {
+                                                    uint64_t* acc_bar, uint32_t acc_phase, int p_next,
+                                                    BceCarry* bce = nullptr) {
     static_assert(GROUP == 8 || GROUP == 16 || GROUP == 32, "unsupported column group");
     constexpr int CH = GROUP / 8;       // 16-byte chunks per row segment
     const EpiRow R = epi_decode_row(P, p);
@@ -150,6 +175,27 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             have_upre = true;
         }
     }
+    float bce_acc = 0.f, bce_m = 0.f, bce_inv = 0.f;
+    int bce_t = 0;
+    const float* bce_yp = nullptr;
+    if constexpr (BCE) {
+        if (R.interior) {
+            bce_t = R.b / P.bce_B;
+            const int bb = R.b - bce_t * P.bce_B;
+            bce_m = P.bce_mask ? __ldg(P.bce_mask + (long long)bb * P.bce_mbs + (long long)bce_t * P.bce_mts) : 1.f;
+            bce_inv = 1.f / (float(P.bce_B) * float(P.n_valid) * float(hw));
+            bce_yp = P.bce_y + (long long)bb * P.bce_ybs + (long long)bce_t * P.bce_yts + size_t(R.hp - 1) * P.W + (R.wp - 1);
+        }
+    }
+    // the pixel's target values are fetched before the accumulator wait as well (same reason as the uniforms above)
+    float ypre[BCE ? GROUP : 1];
+    if constexpr (BCE) {
+#pragma unroll
+        for (int i = 0; i < GROUP; ++i) {
+            const int n = n0 + half * GROUP + i;
+            ypre[i] = (R.interior && n < P.n_valid) ? __ldg(bce_yp + size_t(n) * hw) : 0.f;
+        }
+    }
     mbar_wait(acc_bar, acc_phase);
     tc_fence_after();
     const float* sbp = (P.sample_bias && R.valid) ? P.sample_bias + size_t(R.b) * n_total + n0 : nullptr;
@@ -213,6 +259,26 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
         } else if (P.act == ACT_SIGMOID) {
 #pragma unroll
             for (int i = 0; i < GROUP; ++i) v[i] = 1.f / (1.f + __expf(-v[i]));
+        }
+        if constexpr (BCE) {
+            // logits -> d loss / d logits (reference main.py:189-197, 310-312: sigmoid, F.binary_cross_entropy with its log
+            // clamp at -100, mean over C,H,W, mask, mean over the batch); same arithmetic as bce_logits_kernel
+            if (R.interior) {
+                const float k = bce_m * bce_inv;
+#pragma unroll
+                for (int i = 0; i < GROUP; ++i) {
+                    const int n = n0 + c0 + i;
+                    if (n < P.n_valid) {
+                        const float yv = (c0 == half * GROUP) ? ypre[i] : __ldg(bce_yp + size_t(n) * hw);
+                        const float pr = 1.f / (1.f + __expf(-v[i]));
+                        const float lp = fmaxf(__logf(pr), -100.f), lq = fmaxf(__logf(1.f - pr), -100.f);
+                        bce_acc -= yv * lp + (1.f - yv) * lq;
+                        v[i] = (pr - yv) * k;
+                    } else {
+                        v[i] = 0.f;
+                    }
+                }
+            }
         }
         if (R.interior && P.gate) {
             const int bit0 = ((c0 - half * GROUP) / (SHARE * GROUP)) * GROUP;  // this group's first bit in gb
@@ -289,6 +355,22 @@ __device__ __forceinline__ void igemm_epilogue_tile(const IgemmParams& P, int n_
             c0 = c1 + SHARE * GROUP;
             if (c0 < ncols_cta) load(va, c0);
             process(vb, c1);
+        }
+    }
+    if constexpr (BCE) {
+        if (half * GROUP < ncols_cta) {   // warp-uniform: this warp owned a column group
+            // warp-reduce the tile's share step by step (one step per tile, two where a tile straddles a step boundary)
+            float part = R.interior ? bce_acc * bce_m * bce_inv : 0.f;
+            unsigned todo = __ballot_sync(0xFFFFFFFFu, R.interior);
+            while (todo) {
+                const int t0 = __shfl_sync(0xFFFFFFFFu, bce_t, __ffs(todo) - 1);
+                const bool mine = R.interior && bce_t == t0;
+                float sum = mine ? part : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, o);
+                bce->add(t0, sum, lane);
+                todo &= ~__ballot_sync(0xFFFFFFFFu, mine);
+            }
         }
     }
 }

@@ -31,8 +31,10 @@ class CoordConv2d(nn.Module):
 
     def forward(self, x):
         if self._native_ok(x):
-            # 3x3 / stride 1 / pad 1: hand-written path - coordinates synthesised into the bf16 input plane, tcgen05
-            # implicit-GEMM conv (bf16 operands, fp32 accumulation), dgrad/wgrad kernels behind autograd
+            # 3x3 / stride 1 / pad 1: hand-written path - tcgen05 implicit-GEMM conv (16-bit operands, fp32
+            # accumulation), dgrad/wgrad kernels behind autograd.  Up to 14 data channels the two coordinate channels
+            # are generated inside the conv's im2col tile and never stored (scm_gan_b200/engine.py: coords_in_tile);
+            # wider inputs get them written into the 16-bit input plane
             return torch.ops.scmgan.coordconv3x3(x, self.conv.weight, self.conv.bias)[0]
         batch_size, _, height, width = x.shape
         cx, cy = self.coordinates(height, width, x.device, x.dtype)

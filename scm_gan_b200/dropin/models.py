@@ -204,6 +204,16 @@ class Decoder(nn.Module):
         return torch.ops.scmgan.decoder_fwd(z_map, self.conv1.weight, self.conv1.bias, w2f, b2f)[0]
 
 
+    def pixel_loss_seq(self, z_map, target_bt, mask_bt):
+        """Not part of the reference interface (used by scm_gan_b200.train_step): decode the latents of all T rollout
+        steps (z_map [T*B, L, H, W], t-major) and return the T reconstruction terms of main.py:188-197,
+        mean_b(mask[b,t] * mean_chw BCE(sigmoid(decoder(z)), target[b,t])), with sigmoid + BCE + the means evaluated in
+        the epilogue of the last convolution (scmgan_decoder_bce_fwd).  target_bt [B, T, C, H, W], mask_bt [B, T]."""
+        w2f, b2f = self._folded_last_layer()
+        return torch.ops.scmgan.decoder_bce_seq(z_map, self.conv1.weight, self.conv1.bias, w2f, b2f, target_bt,
+                                                mask_bt)[0]
+
+
 class RewardPredictor(nn.Module):
     # Each reward is a per-pixel 3-way classification (+1 / 0 / -1) summed over the map (reference models.py:226-250)
     def __init__(self, latent_dim, num_rewards):

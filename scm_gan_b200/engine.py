@@ -209,7 +209,7 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     # d pre-activation of conv6: dz * p * (1 - p)
     K.pack_nchw(dz_next, DB, c_off=HID, c_pad=LS, wrap=True, sig=p)
     cin6 = 2 * HID
-    K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr, side=True)
+    K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
     with dr.side_section():
         K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
     dg = dict(wrap=True, dgrad=True)
@@ -217,27 +217,27 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
               sample_scale=rs(4), **dg)                                                                     # d pre5
     for s in range(S):
         K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][4], Bs, H, W, cout=HID, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9,
-                g_s_ci=9, db=dbs[s][4], defer=dr, side=True)
+                g_s_ci=9, db=dbs[s][4], defer=dr)
     d4 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DA, wd[4], B, H, W, cin=HID, x_c_off=HID, out=d4, gate=buf5, gate_c_off=0, sample_scale=rs(3), **dg)  # d pre4
     for s in range(S):
         K.wgrad(seg(d4, s), seg(act3, s), Gs[s][3], Bs, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9,
-                db=dbs[s][3], defer=dr, side=True)
+                db=dbs[s][3], defer=dr)
     K.conv3x3(d4, wd[3], B, H, W, cin=HID, out=DA, out_c_off=0, gate=act3, sample_scale=rs(2), **dg)        # d pre3
     for s in range(S):
         K.wgrad(seg(DA, s), seg(buf5, s), Gs[s][2], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
-                g_s_ci=9, db=dbs[s][2], defer=dr, side=True)
+                g_s_ci=9, db=dbs[s][2], defer=dr)
     K.conv3x3(DA, wd[2], B, H, W, cin=2 * HID, out=DB, out_c_off=0, gate=buf5, gate_c_off=HID, sample_scale=rs(1),
               **dg)                                                                                         # d pre2
     for s in range(S):
         K.wgrad(seg(DB, s), seg(buf6, s), Gs[s][1], Bs, H, W, cout=HID, cin=HID, x_c_off=HID, g_s_co=HID * 9,
-                g_s_ci=9, db=dbs[s][1], defer=dr, side=True)
+                g_s_ci=9, db=dbs[s][1], defer=dr)
     d1 = K.new_plane(B, H, W, HID, dev)
     K.conv3x3(DB, wd[1], B, H, W, cin=HID + LS, out=d1, gate=buf6, gate_c_off=HID, sample_scale=rs(0), **dg)  # d pre1
     c1 = L + A
     for s in range(S):
         K.wgrad(seg(d1, s), seg(zin, s), Gs[s][0], Bs, H, W, cout=HID, cin=Lp, g_s_co=c1 * 9, g_s_ci=9, ci_valid=L,
-                defer=dr, side=True)
+                defer=dr)
         with dr.side_section():
             K.plane_colsum(seg(d1, s), 0, HID, Bs, H, W, S=S1s[s], db=dbs[s][0])
             K.action_wgrad(S1s[s], a[s * Bs:(s + 1) * Bs], L, Gs[s][0])
@@ -401,11 +401,54 @@ def decoder_forward(z, w1, b1, w2, b2):
     return logits, [zin, hidp, wd1, wd2]
 
 
-def decoder_backward(dlogits, saved, w1, w2, sink=None):
-    """sink = [gW1, gb1, gW2, gb2] (entries may be None): see transition_backward."""
+def decoder_bce_forward(z, w1, b1, w2, b2, target_bt, mask_bt):
+    """Decoder + pixel loss of all T rollout steps (reference main.py:188-197 once per step): z [T*B, L, H, W] t-major,
+    w2 already folded over the latent groups (Co = colour channels <= 16), target_bt [B, T, C, H, W], mask_bt [B, T].
+    The last conv's epilogue evaluates sigmoid + BCE + the masked means (scmgan_decoder_bce_fwd): no logits tensor, no
+    separate loss kernel, and d loss_t / d logits arrives as the gradient plane the backward convolutions read.
+    Returns (loss_t [T], saved = [zin, hidp, wd1, wd2, d2])."""
+    dev = z.device
+    TB, L, H, W = z.shape
+    B, T = target_bt.shape[0], target_bt.shape[1]
+    assert TB == T * B
+    Lp = _r16(L)
+    hid = w1.shape[1]
+    co = w2.shape[1]
+    cop = _r16(co)
+    assert hid % 64 == 0 and hid <= HID and cop == 16 and target_bt.shape[2] == co
+    wf1 = K.packed_weight(hid, Lp, dev)
+    wf2 = K.packed_weight(cop, hid, dev)
+    wd1 = K.packed_weight(Lp, hid, dev, K.GRAD_DTYPE)
+    wd2 = K.packed_weight(hid, cop, dev, K.GRAD_DTYPE)
+    K.pack_weights([_convT_fwd_job(w1, wf1), _convT_fwd_job(w2, wf2), _convT_dgrad_job(w1, wd1),
+                    _convT_dgrad_job(w2, wd2)])
+    zin = K.fwd_plane(TB, H, W, Lp, dev)
+    K.pack_nchw(z, zin, wrap=False)
+    hidp = K.fwd_plane(TB, H, W, HID, dev)
+    K.conv3x3(zin, wf1, TB, H, W, cin=Lp, bias=b1, act=ACT_LRELU, out=hidp)
+    loss_t = torch.zeros(T, dtype=torch.float32, device=dev)
+    d2 = K.new_plane(TB, H, W, cop, dev)
+    K.decoder_bce_fwd(hidp, wf2, T, B, H, W, cin=hid, bias=b2, n_valid=co, dlogits_plane=d2, target_bt=target_bt,
+                      mask_bt=mask_bt, loss_t=loss_t)
+    return loss_t, [zin, hidp, wd1, wd2, d2]
+
+
+def decoder_bce_backward(g, saved, w1, w2, T, sink=None):
+    """Backward of decoder_bce_forward.  g [T] = d total / d loss_t (the gradient plane is rescaled in place only where
+    g[t] != 1).  Returns like decoder_backward."""
+    zin, hidp, wd1, wd2, d2 = saved
+    TB, Hp, Wp, _ = d2.shape
+    K.decoder_bce_bwd(d2, g, T, TB // T, Hp - 2, Wp - 2)
+    return decoder_backward(None, [zin, hidp, wd1, wd2], w1, w2, sink, d2=d2)
+
+
+def decoder_backward(dlogits, saved, w1, w2, sink=None, d2=None):
+    """sink = [gW1, gb1, gW2, gb2] (entries may be None): see transition_backward.
+    d2 (optional): d loss / d logits already as a gradient plane (fused loss head); dlogits is then ignored."""
     zin, hidp, wd1, wd2 = saved
-    dev = dlogits.device
-    B, co, H, W = dlogits.shape
+    dev = zin.device
+    co = w2.shape[1]
+    B, H, W = zin.shape[0], zin.shape[1] - 2, zin.shape[2] - 2
     cop = _r16(co)
     L, hid = w1.shape[0], w1.shape[1]
     Lp = zin.shape[3]
@@ -424,8 +467,9 @@ def decoder_backward(dlogits, saved, w1, w2, sink=None):
     if sink[3] is not None and cop == co:
         db2 = sink[3]
     dr = K.DeferredReduces(dev)
-    d2 = K.new_plane(B, H, W, cop, dev)
-    K.pack_nchw(dlogits, d2, wrap=False)
+    if d2 is None:
+        d2 = K.new_plane(B, H, W, cop, dev)
+        K.pack_nchw(dlogits, d2, wrap=False)
     # ConvTranspose weight layout [Cin][Cout][3][3], taps flipped relative to the equivalent correlation
     K.wgrad(d2, hidp, g2, B, H, W, cout=cop, cin=HID, g_s_co=9, g_s_ci=co * 9, flip=True, co_valid=co, ci_valid=hid, defer=dr)
     with dr.side_section():
@@ -537,10 +581,21 @@ def coordconv_forward(x, w, b):
     K.pack_weights([_conv2d_fwd_job(w, wf), _conv2d_dgrad_job(w, wd, None, 0, Cc)])
     xin = K.fwd_plane(B, H, W, Cp, dev)
     K.pack_nchw(x, xin, c_pad=Cp, wrap=False)
-    K.pack_coords(xin, Cc)
     y = torch.empty((B, co, H, W), dtype=torch.float32, device=dev)
-    K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=b, act=ACT_NONE, out_f32=y, n_valid=co)
+    if coords_in_tile(Cp, W):
+        # the coordinate channels are generated by the conv's producer while it stages the im2col tile; the plane
+        # holds zeros in their place (scmgan_conv_desc::coord_c1)
+        K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=b, act=ACT_NONE, out_f32=y, n_valid=co, coord_c=Cc)
+    else:
+        K.pack_coords(xin, Cc)   # wide layers (TMA-fed tiles): coordinates materialised in the 16-bit input plane
+        K.conv3x3(xin, wf, B, H, W, cin=Cp, bias=b, act=ACT_NONE, out_f32=y, n_valid=co)
     return y, [xin, wd]
+
+
+def coords_in_tile(Cp, W):
+    """In-tile coordinate generation is available where the conv's producer stages the tile in software: 16 input
+    channels (data + 2 coordinates) and W <= 69."""
+    return Cp == 16 and W + 2 <= 71
 
 
 def coordconv_backward(dy, saved, w):
@@ -558,7 +613,13 @@ def coordconv_backward(dy, saved, w):
     K.pack_nchw(dy, dyp, c_pad=Gp, wrap=False)
     g = torch.zeros_like(w)
     db = torch.zeros(Gp, dtype=torch.float32, device=dev)
-    K.wgrad(dyp, xin, g, B, H, W, cout=Gp, cin=Cp, g_s_co=cin * 9, g_s_ci=9, co_valid=co, ci_valid=cin, db=db)
+    if coords_in_tile(Cp, W):
+        # data channels from the plane (its coordinate channels are zero); the coordinate channels' gradient is the
+        # correlation of dy with the two ramps (scmgan_coord_wgrad)
+        K.wgrad(dyp, xin, g, B, H, W, cout=Gp, cin=Cp, g_s_co=cin * 9, g_s_ci=9, co_valid=co, ci_valid=Cc, db=db)
+        K.coord_wgrad(dy.contiguous(), g, Cc)
+    else:
+        K.wgrad(dyp, xin, g, B, H, W, cout=Gp, cin=Cp, g_s_co=cin * 9, g_s_ci=9, co_valid=co, ci_valid=cin, db=db)
     dx = torch.empty((B, Cc, H, W), dtype=torch.float32, device=dev)
     K.conv3x3(dyp, wd, B, H, W, cin=Gp, out_f32=dx, n_valid=Cc, dgrad=True)
     return dx, g, db[:co].clone()

@@ -19,8 +19,6 @@ LRELU_SLOPE = 0.01  # F.leaky_relu default used by reference models.py:77-99
 import os as _os
 FWD_DTYPE = torch.bfloat16 if _os.environ.get("SCMGAN_FWD_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
 GRAD_DTYPE = torch.bfloat16
-# experiment switch (profiles/r02_notes.md): weight-gradient kernels of the Transition backward on the side stream
-WGRAD_SIDE = _os.environ.get("SCMGAN_WGRAD_SIDE", "0") == "1"
 
 
 def _fmt(t):
@@ -71,6 +69,14 @@ def pack_coords(dst_plane, c_off):
             "scmgan_pack_coords")
 
 
+def coord_wgrad(dy, g, coord_c):
+    """Weight gradient of the in-tile coordinate channels coord_c, coord_c + 1: dy [B, Co, H, W] fp32, g [Co, Cin, 3, 3]."""
+    B, Co, H, W = dy.shape
+    assert dy.is_contiguous() and g.is_contiguous() and g.shape[0] == Co and g.shape[1] >= coord_c + 2
+    L.check(L.lib().scmgan_coord_wgrad(dy.data_ptr(), B, Co, H, W, g.data_ptr(), g.stride(0), g.stride(1), coord_c,
+                                       _stream()), "scmgan_coord_wgrad")
+
+
 def pack_weights(jobs):
     """jobs: list of dicts(w, out, sigma, n_pad, k_pad, n_valid, k_valid, s_n, s_k, k_src_off, flip); `out` may be a
     K window (a [:, :, a:b] view) of a wider packed operand."""
@@ -92,7 +98,18 @@ def packed_weight(n_pad, k_pad, device, dtype=None):
 def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, sample_scale=None,
             act=ACT_NONE,
             out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
-            n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False):
+            n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False, coord_c=None):
+    d = _conv_desc(x_plane, w_packed, B, H, W, cin=cin, x_c_off=x_c_off, scale=scale, bias=bias,
+                   sample_bias=sample_bias, sample_scale=sample_scale, act=act, out=out, out_c_off=out_c_off, wrap=wrap,
+                   add=add, add_c_off=add_c_off, gate=gate, gate_c_off=gate_c_off, out_f32=out_f32, n_valid=n_valid,
+                   sample_out=sample_out, uniforms=uniforms, rng_state=rng_state, coord_c=coord_c)
+    fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
+    L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
+
+
+def _conv_desc(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, sample_scale=None,
+               act=ACT_NONE, out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0,
+               out_f32=None, n_valid=0, sample_out=None, uniforms=None, rng_state=None, coord_c=None):
     n = w_packed.shape[1]
     assert w_packed.shape[2] == cin
     d = L.ConvDesc()
@@ -118,8 +135,34 @@ def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None,
     d.rng_state = L.ptr(rng_state)  # int64 [2] = {seed, offset}; advanced by the library after the launch
     d.x_fmt, d.w_fmt = _fmt(x_plane), _fmt(w_packed)
     d.out_fmt = _fmt(out) if out is not None else L.FMT_BF16
-    fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
-    L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
+    d.coord_c1 = 0 if coord_c is None else coord_c + 1   # CoordConv: coordinate channels generated in the tile
+    return d
+
+
+def decoder_bce_fwd(hid_plane, w_packed, T, B, H, W, *, cin, bias, n_valid, dlogits_plane, target_bt, mask_bt, loss_t,
+                    logits=None):
+    """The decoder's last conv + sigmoid + BCE + masked means in one launch (include/scmgan.h: scmgan_decoder_bce_fwd).
+    hid_plane: hidden planes of the T*B decoded latents (t-major); target_bt [B, T, C, H, W] / mask_bt [B, T]: views of
+    the batch tensors; loss_t [T] zero-initialised; dlogits_plane: zero-halo gradient plane [T*B, H+2, W+2, 16]."""
+    assert target_bt[0, 0].is_contiguous() and target_bt.dtype == torch.float32 and loss_t.numel() == T
+    d = L.DecoderBceDesc()
+    d.conv = _conv_desc(hid_plane, w_packed, T * B, H, W, cin=cin, bias=bias, act=ACT_NONE, out=dlogits_plane,
+                        out_f32=logits, n_valid=n_valid)
+    d.target, d.target_bstride, d.target_tstride = target_bt.data_ptr(), target_bt.stride(0), target_bt.stride(1)
+    d.mask = L.ptr(mask_bt)
+    d.mask_bstride, d.mask_tstride = (mask_bt.stride(0), mask_bt.stride(1)) if mask_bt is not None else (0, 0)
+    d.T, d.B = T, B
+    d.loss_t = loss_t.data_ptr()
+    ws = torch.empty(L.lib().scmgan_decoder_bce_workspace_rows() * T, dtype=torch.float32, device=loss_t.device)
+    d.workspace, d.workspace_bytes = ws.data_ptr(), ws.numel() * 4
+    L.check(L.lib().scmgan_decoder_bce_fwd(C.byref(d), _stream()), "scmgan_decoder_bce_fwd")
+
+
+def decoder_bce_bwd(dlogits_plane, g, T, B, H, W):
+    """In place: rows of rollout step t of the gradient plane *= g[t] (skipped on the device where g[t] == 1)."""
+    assert dlogits_plane.is_contiguous() and g.dtype == torch.float32 and g.numel() == T and g.is_contiguous()
+    L.check(L.lib().scmgan_decoder_bce_bwd(dlogits_plane.data_ptr(), dlogits_plane.shape[3], _fmt(dlogits_plane),
+                                           g.data_ptr(), T, B, H, W, _stream()), "scmgan_decoder_bce_bwd")
 
 
 _WGRAD_WS = {}
@@ -196,7 +239,7 @@ class DeferredReduces:
 
 
 def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_s_co, g_s_ci, g_s_tap=1, flip=False,
-          co_valid=None, ci_valid=None, scale=1.0, db=None, defer=None, side=False):
+          co_valid=None, ci_valid=None, scale=1.0, db=None, defer=None):
     d = L.WgradDesc()
     d.B, d.H, d.W = B, H, W
     d.dy, d.dy_cs, d.dy_c_off, d.cout = dy_plane.data_ptr(), dy_plane.shape[3], dy_c_off, cout
@@ -212,14 +255,6 @@ def wgrad(dy_plane, x_plane, g, B, H, W, *, cout, cin, dy_c_off=0, x_c_off=0, g_
         d.workspace, d.workspace_bytes = defer.ring.data_ptr(), defer.ring.numel() * 4
         d.defer_jobs, d.defer_cap = defer.jobs, defer.CAP
         d.defer_count, d.workspace_cursor = C.pointer(defer.count), C.pointer(defer.cursor)
-        if side and WGRAD_SIDE:
-            # the whole weight gradient (tensor-core kernel + reduction) leaves the critical path: it only depends on the
-            # gradient plane produced so far and nothing but the optimiser waits for it, so its CTAs fill the SMs that
-            # the data-gradient chain's kernels leave idle in their last wave
-            with defer.side_section():
-                L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
-                defer.kick()
-            return
         L.check(L.lib().scmgan_conv3x3_wgrad(C.byref(d), _stream()), "scmgan_conv3x3_wgrad")
         defer.kick()
         return

@@ -264,6 +264,55 @@ decoder_fwd.register_autograd(_decoder_backward, setup_context=_decoder_setup)
 
 
 # ------------------------------------------------------------------------------------------------------------
+# Decoder + pixel loss of all rollout steps with the loss head in the last convolution's epilogue
+# (scmgan_decoder_bce_fwd; used by scm_gan_b200.train_step - main.py keeps decoder() + its own torch loss ops)
+# ------------------------------------------------------------------------------------------------------------
+@torch.library.custom_op("scmgan::decoder_bce_seq", mutates_args=())
+def decoder_bce_seq(z: Tensor, w1: Tensor, b1: Tensor, w2: Tensor, b2: Tensor, target_bt: Tensor,
+                    mask_bt: Tensor) -> List[Tensor]:
+    """z [T*B, L, H, W] (t-major); w2 / b2 folded over the latent groups; target_bt [B, T, C, H, W], mask_bt [B, T].
+    -> [per-step loss terms [T]] + saved planes."""
+    _require_cuda(z, w1, target_bt)
+    if not (target_bt.dtype == torch.float32 and target_bt[0, 0].is_contiguous()):
+        target_bt = target_bt.contiguous().float()
+    if mask_bt.dtype != torch.float32:
+        mask_bt = mask_bt.float()
+    loss_t, saved = E.decoder_bce_forward(z.contiguous().float(), w1, b1, w2.contiguous(), b2.contiguous(), target_bt,
+                                          mask_bt)
+    return [loss_t] + saved
+
+
+@torch.library.custom_op("scmgan::decoder_bce_seq_bwd", mutates_args=("sinks", "saved"))
+def decoder_bce_seq_bwd(g: Tensor, saved: Sequence[Tensor], w1: Tensor, w2: Tensor, sinks: Sequence[Tensor],
+                        sink_mask: int) -> List[Tensor]:
+    _require_cuda(g)
+    out = E.decoder_bce_backward(g.contiguous().float(), list(saved), w1, w2.contiguous(), g.numel(),
+                                 _expand_sinks(sinks, sink_mask, 4))
+    return [t for t in out if t is not None]
+
+
+def _decoder_bce_setup(ctx, inputs, output):
+    ctx.set_materialize_grads(False)
+    z, w1, b1, w2, b2, _, _ = inputs
+    ctx.w1, ctx.w2 = w1, w2
+    ctx.params = [w1, b1, w2, b2]
+    ctx.save_for_backward(*output[1:])
+
+
+def _decoder_bce_backward(ctx, grads):
+    if grads[0] is None:
+        return (None,) * 7
+    sinks, mask = _sinks_of(ctx.params)
+    out = torch.ops.scmgan.decoder_bce_seq_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2, sinks, mask)
+    g = _merge(out[1:], mask, 4)
+    _notify(ctx.params, mask)
+    return (out[0], *g, None, None)
+
+
+decoder_bce_seq.register_autograd(_decoder_bce_backward, setup_context=_decoder_bce_setup)
+
+
+# ------------------------------------------------------------------------------------------------------------
 # Fused sigmoid + BCE + masked mean (used by scm_gan_b200.train_step; main.py keeps its own torch ops)
 # ------------------------------------------------------------------------------------------------------------
 @torch.library.custom_op("scmgan::bce_logits", mutates_args=())

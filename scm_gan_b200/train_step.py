@@ -23,6 +23,8 @@ CF_REGULARIZATION_LAMBDA = 0.01  # reference main.py:55
 # once per iteration on the batch of all steps (A/B measurements; the results are the same)
 SEQUENTIAL_HEADS = os.environ.get("SCMGAN_SEQUENTIAL_HEADS", "0") == "1"
 CLIP_VALUE = 0.1                 # reference main.py:288-290
+# SCMGAN_NO_FUSED_BCE=1: decoder logits to memory + the stand-alone loss kernel (A/B measurements; same results)
+FUSED_DECODER_LOSS = os.environ.get("SCMGAN_NO_FUSED_BCE", "0") != "1"
 
 
 def import_dropin_models():
@@ -144,7 +146,11 @@ def rollout_loss(nets, states, rewards, dones, actions, *, theta, reward_coef=1e
         zcat = torch.cat(zs, dim=0)                                # [T*B, L, H, W], t-major
         mask_bt = masks[:, :T]
         rd = torch.ops.scmgan.masked_mse_seq(rew(zcat), rewards[:, 1:Hn - 1], mask_bt, reward_coef, theta)
-        rec = torch.ops.scmgan.bce_logits_seq(dec(zcat), states[:, 1:Hn - 1], mask_bt)[0]
+        if FUSED_DECODER_LOSS and dec.color_channels <= 16:
+            # decoder + sigmoid + BCE + means: the loss head sits in the epilogue of the decoder's last convolution
+            rec = dec.pixel_loss_seq(zcat, states[:, 1:Hn - 1], mask_bt)
+        else:
+            rec = torch.ops.scmgan.bce_logits_seq(dec(zcat), states[:, 1:Hn - 1], mask_bt)[0]
         terms += [rd[0], rec]
         if collect is not None:
             for t in range(1, Hn - 1):

@@ -634,9 +634,11 @@ def test_csrn_native_sweeps_vs_oracle(shape):
 
 @pytest.mark.parametrize("shape", [(2, 6, 12, 12, 16), (3, 14, 16, 16, 32), (2, 30, 10, 13, 24)])
 def test_coordconv_native_vs_torch(shape):
-    """CoordConv2d 3x3/s1/p1 on the hand-written path (scmgan_pack_coords + tcgen05 conv, dgrad, wgrad) against the
-    same layer evaluated by torch in fp32 (coordinates concatenated as in reference coordconv.py:10-15).  bf16
-    operands: 1e-2 relative."""
+    """CoordConv2d 3x3/s1/p1 on the hand-written path against the same layer evaluated by torch in fp32 (coordinates
+    concatenated as in reference coordconv.py:10-15); 16-bit operands: 1e-2 relative.  The first two shapes (<= 14 data
+    channels) take the in-tile path - coordinates generated by the conv's producer while it stages the im2col tile
+    (scmgan_conv_desc::coord_c1), their weight gradient from scmgan_coord_wgrad; the third (30 data channels, TMA-fed
+    tiles) materialises them with scmgan_pack_coords."""
     _setup()
     import sys
     from scm_gan_b200.train_step import import_dropin_models
@@ -647,6 +649,8 @@ def test_coordconv_native_vs_torch(shape):
     net = CoordConv2d(C + 2, Co, 3, padding=1).to(DEV)
     x = torch.randn(B, C, H, W, device=DEV, requires_grad=True)
     assert net._native_ok(x)
+    from scm_gan_b200 import engine
+    assert engine.coords_in_tile((C + 2 + 15) // 16 * 16, W) == (C + 2 <= 16)
     y = net(x)
     gy = torch.randn_like(y)
     y.backward(gy)

@@ -603,3 +603,48 @@ def test_input_pipeline_feeds_batches_in_order():
     # a few reductions use fp32 atomics (loss sums, per-sample column sums), so later iterations agree to rounding only
     assert all(abs(x - y) <= 1e-3 * abs(y) for x, y in zip(a, b)) and len(set(a)) == 3
     assert abs(a[0] - a[1]) > 1e-2  # different batches really were consumed
+
+
+@pytest.mark.parametrize("name", ["minipacman", "pong64", "sc2"])
+def test_fused_decoder_loss_head(name):
+    """Decoder.pixel_loss_seq (last conv + sigmoid + BCE + masked means in one epilogue, scmgan_decoder_bce_fwd/bwd)
+    against the two-kernel path decoder() -> scmgan::bce_logits_seq and against the oracle's torch expression
+    (main.py:188-197, 310-312): loss terms, dz and all decoder parameter gradients; plain sum (g = 1: the in-place
+    rescale is skipped on the device) and a weighted sum (g != 1)."""
+    _setup()
+    from oracle import restated as R
+    cfg = load(name)["config"]
+    nets = build(cfg)
+    dec = nets["decoder"]
+    T, B = 3, 4
+    torch.manual_seed(3)
+    z0 = (torch.rand(T * B, 16, cfg["H"], cfg["W"], device=DEV) < 0.5).float()
+    frames = (torch.rand(B, T + 2, cfg["C"], cfg["H"], cfg["W"], device=DEV) < 0.2).float()
+    mask = torch.tensor([[1.0] * T, [1.0, 1.0, 0.0], [1.0, 0.0, 0.0], [1.0] * T], device=DEV)[:B]
+    tgt = frames[:, 1:T + 1]
+    params = [dec.conv1.weight, dec.conv1.bias, dec.conv2.weight, dec.conv2.bias]
+
+    def run(fused, wts):
+        for p in params:
+            p.grad = None
+        z = z0.clone().requires_grad_(True)
+        if fused:
+            terms = dec.pixel_loss_seq(z, tgt, mask)
+        else:
+            terms = torch.ops.scmgan.bce_logits_seq(dec(z), tgt, mask)[0]
+        (terms * wts).sum().backward()
+        return terms.detach().clone(), z.grad.clone(), [p.grad.clone() for p in params]
+
+    # oracle terms on the same weights (fp32 torch)
+    sd = {k: v.detach().clone() for k, v in dec.state_dict().items()}
+    with torch.no_grad():
+        pred = torch.sigmoid(R.decoder_forward(sd, z0)).view(T, B, cfg["C"], cfg["H"], cfg["W"])
+        oterms = torch.stack([(R.decoder_pixel_loss(tgt[:, t], pred[t]) * mask[:, t]).mean() for t in range(T)])
+    for wts in (torch.ones(T, device=DEV), torch.tensor([0.5, 2.0, 1.0], device=DEV)):
+        lt_f, dz_f, g_f = run(True, wts)
+        lt_u, dz_u, g_u = run(False, wts)
+        assert report(f"{name} fused loss terms vs two-kernel path", lt_f, lt_u, 1e-5)
+        assert report(f"{name} fused loss terms vs oracle", lt_f, oterms, 1e-3)
+        assert report(f"{name} fused dz", dz_f, dz_u, 4e-3)
+        for n_, a, b in zip(("w1", "b1", "w2", "b2"), g_f, g_u):
+            assert report(f"{name} fused d{n_}", a, b, 4e-3)
