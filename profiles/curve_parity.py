@@ -30,7 +30,9 @@ def smooth(x, w):
     return (c[w:] - c[:-w]) / w
 
 
-def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_seed=None):
+def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_seed=None, schedule=False):
+    """schedule: the reference's horizon schedule (main.py:143-147: horizon = 3 + int((hmax - 3) * theta), hmax =
+    `horizon`) instead of a fixed horizon - one CUDA graph per (horizon, cf) pair, theta exact (a device scalar)."""
     from oracle import restated as R
     from scm_gan_b200.synthetic import MovingDots
     from scm_gan_b200.train_step import Trainer, build_nets
@@ -60,23 +62,26 @@ def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_se
     t_ours = t_oracle = 0.0
     for it in range(1, steps + 1):
         theta = it / steps
+        hn = (3 + int((horizon - 3) * theta)) if schedule else horizon
         cf_now = (it % 5 == 0)
         cf_idx = torch.randint(16, (batch, 2), generator=g)
         cf_perm = torch.randperm(batch, generator=g)
         # ---- ours
-        st, rw, dn, ac = src_a.get_trajectories(batch, horizon)
+        st, rw, dn, ac = src_a.get_trajectories(batch, hn)
         b = {"states": torch.from_numpy(st).to(dev), "rewards": torch.from_numpy(rw).to(dev),
              "dones": torch.from_numpy(dn.astype(np.float32)).to(dev), "actions": torch.from_numpy(ac).to(dev),
              "cf_indices": cf_idx.to(dev), "cf_perm": cf_perm.to(dev)}
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        # theta enters the graph key; quantise it so a handful of graphs cover the schedule
-        th_q = round(theta * 20) / 20 if use_graph else theta
-        loss = trainer.step(b, th_q, cf_now=cf_now, use_graph=use_graph)
-        ours.append(loss.item())
+        # theta = train_iter / train_iters exactly (main.py:143): a device scalar, not part of the graph key
+        th_q = theta
+        trainer.step(b, th_q, cf_now=cf_now, use_graph=use_graph)
+        if it % 10 == 0 or it == steps:   # ONE device->host copy per 10 iterations (main.py:297 ts.print_every(10))
+            n_new = it - len(ours)
+            ours.extend(row["loss"] for row in trainer.read_log(n_new))
         t_ours += time.perf_counter() - t0
         # ---- oracle (same data stream, same theta, same CF draws)
-        st2, rw2, dn2, ac2 = src_b.get_trajectories(batch, horizon)
+        st2, rw2, dn2, ac2 = src_b.get_trajectories(batch, hn)
         assert np.array_equal(st, st2)
         t0 = time.perf_counter()
         opt.zero_grad()
@@ -88,7 +93,8 @@ def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_se
         oracle.append(ol.item())
         t_oracle += time.perf_counter() - t0
         if it % 100 == 0:
-            log(f"iter {it}: ours {np.mean(ours[-50:]):.4f}  oracle {np.mean(oracle[-50:]):.4f}")
+            log(f"iter {it}: ours {np.mean(ours[-50:]):.4f}  oracle {np.mean(oracle[-50:]):.4f}  "
+                f"graph captures so far {trainer.captures}")
     # ---- held-out rollout MSE of both learned weight sets, evaluated by the oracle
     ev = MovingDots(C, H, W, A, Rw, seed=99)
     st, rw, dn, ac = ev.get_trajectories(100, 20)
@@ -98,7 +104,9 @@ def run(steps, batch, horizon, seed=0, cf_h=2, use_graph=True, log=print, rng_se
     sd_orac = {k: {n: v.detach().clone() for n, v in sd.items()} for k, sd in onets.items()}
     mse_ours = R.measure_prediction_mse(sd_ours, st, rw, dn, ac, num_actions=A)[0]
     mse_orac = R.measure_prediction_mse(sd_orac, st, rw, dn, ac, num_actions=A)[0]
-    return {"steps": steps, "batch": batch, "horizon": horizon, "loss_ours": ours, "loss_oracle": oracle,
+    return {"steps": steps, "batch": batch, "horizon": horizon, "schedule": bool(schedule),
+            "theta": "exact (it / steps), device scalar", "graph_captures": trainer.captures,
+            "loss_ours": ours, "loss_oracle": oracle,
             "rollout_mse_ours": mse_ours, "rollout_mse_oracle": mse_orac,
             "seconds_ours": t_ours, "seconds_oracle": t_oracle}
 
@@ -122,9 +130,12 @@ if __name__ == "__main__":
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "curve_parity.json"))
     ap.add_argument("--rng-seed", type=int, default=None, help="seed of the Bernoulli streams only (same init/data)")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--schedule", action="store_true", help="reference horizon schedule 3 .. --horizon (main.py:143-147)")
     args = ap.parse_args()
-    res = run(args.steps, args.batch, args.horizon, rng_seed=args.rng_seed, use_graph=not args.no_graph)
+    res = run(args.steps, args.batch, args.horizon, rng_seed=args.rng_seed, use_graph=not args.no_graph,
+              schedule=args.schedule)
     res["summary"] = summarize(res)
+    res["summary"]["graph_captures"] = res["graph_captures"]
     print(json.dumps(res["summary"], indent=1))
     print(f"time: ours {res['seconds_ours']:.1f}s, oracle (torch fp32 on the same GPU) {res['seconds_oracle']:.1f}s")
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
