@@ -108,6 +108,11 @@ def main():
          x_c_off=128, gate_cs=256, act=K.ACT_NONE, dgrad=True)
     case("tr conv2-4 128->128", B, 128, 128, x_dt=F16, out_dt=F16)
     case("tr conv5 256->128", B, 256, 128, x_dt=F16, out_dt=F16)
+    case("tr d pre4/3 128->128 (gated dgrad)", B, 128, 128, x_dt=G16, out_dt=G16, gate_cs=128, act=K.ACT_NONE, dgrad=True)
+    case("tr d pre2 256->128 (gated dgrad, K-concat)", B, 256, 128, x_dt=G16, out_dt=G16, gate_cs=256, act=K.ACT_NONE,
+         dgrad=True)
+    case("tr d pre1 192->128 (gated dgrad, K-concat)", B, 192, 128, x_dt=G16, out_dt=G16, gate_cs=256, act=K.ACT_NONE,
+         dgrad=True)
     case("tr conv6 256->16 (sigmoid + sample, f32)", B, 256, 16, x_dt=F16, f32=True, sample=True, act=K.ACT_SIGMOID, wrap=False)
     case("tr dz 128->16 (f32)", B, 128, 16, x_dt=G16, f32=True, act=K.ACT_NONE, wrap=False, dgrad=True)
     case("dec conv1 16->64 (B*T)", B * T, 16, 64, x_dt=F16, out_dt=F16, out_cs=128, wrap=False)
@@ -138,6 +143,30 @@ def main():
     case("rew conv1 16->64(32) (B*T)", B * T, 16, 64, x_dt=F16, out_dt=F16, out_cs=128, wrap=False)
     case("rew conv2 32->16 (f32, B*T)", B * T, 32, 16, x_dt=F16, x_cs=128, f32=True, act=K.ACT_NONE, wrap=False)
     case("enc conv1 16->128 (zero pad)", B, 16, 128, x_dt=F16, out_dt=F16, wrap=False)
+    # weight gradients (main kernel + reduction, as launched without the side-stream deferral)
+    def wcase(label, b, cin, cout, x_cs=None, dy_cs=None):
+        if args.only and args.only not in label:
+            return
+        x_cs, dy_cs = x_cs or max(cin, 16), dy_cs or max(cout, 16)
+        nb = nbuf(b * (H + 2) * (W + 2) * max(x_cs, dy_cs) * 2)
+        xs = plane(b, x_cs, F16, nb)
+        dys = plane(b, dy_cs, G16, nb)
+        g = torch.zeros(cout, cin, 3, 3, device=dev)
+        db = torch.zeros(max(cout, 16), device=dev)
+
+        def fn(i):
+            K.wgrad(dys[i % nb], xs[i % nb], g, b, H, W, cout=dy_cs if cout < 16 else cout, cin=x_cs if cin < 16 else cin,
+                    g_s_co=cin * 9, g_s_ci=9, co_valid=cout, ci_valid=cin, db=db)
+        us = timeit(fn)
+        fl = 2.0 * 9 * b * H * W * cin * cout
+        results.append(dict(layer=label, batch=b, cin=cin, n=cout, us=round(us, 2), tflops=round(fl / us / 1e6, 1)))
+        print(f"{label:46s} B={b:4d} cin={cin:3d} n={cout:3d}: {us:7.1f} us  {fl / us / 1e6:7.1f} TFLOP/s  (kernel + reduce)",
+              flush=True)
+
+    wcase("wgrad 128x128 (conv2-4)", B, 128, 128)
+    wcase("wgrad 256->128 (conv5)", B, 256, 128)
+    wcase("wgrad 16->128 (conv1, narrow)", B, 16, 128)
+    wcase("wgrad 256->16 (conv6, narrow)", B, 256, 16)
     if args.json:
         with open(args.json, "w") as f:
             json.dump(results, f, indent=1)

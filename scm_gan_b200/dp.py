@@ -93,5 +93,5 @@ class BucketedGradSync:
         """Join the side stream.  A bucket whose parameters received no gradient this iteration holds zeros on every
         rank and is not exchanged."""
         self._armed = False
-        if self.cuda:
+        if self.cuda and not _NO_EXCHANGE:
             torch.cuda.current_stream().wait_stream(self.side)
