@@ -1,10 +1,10 @@
 #!/bin/bash
-# bench.py at N = 2 / 4 and the rank-skew diagnostic (no gradient exchange) at N = $1 GPUs of one box
+# bench.py at N GPUs of one box, with the gradient exchange and - as a diagnostic - without it (SCMGAN_DP_NOSYNC=1: every
+# rank then runs at its own pace and bench.py's rank_ms_per_step shows the spread the exchange has to wait for).
+#   gpurun --gpus 8 -- bash profiles/final_n248.sh 8
 N=$1
 TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
-if true; then
 $TR --master-port 29521 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err; echo "bench n$N rc=$?"
-fi
 SCMGAN_DP_NOSYNC=1 $TR --master-port 29522 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n${N}_nosync.json 2> gpurun_out/r02_bench_n${N}_nosync.err; echo "nosync rc=$?"
 python -c "
 import json,sys
