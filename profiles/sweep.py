@@ -20,7 +20,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402  (WORKLOADS, algorithmic_flops_per_iter, read_peaks)
 
-CF_RATE, CF_HORIZON = bench.CF_RATE, bench.CF_HORIZON
+CF_RATE = bench.CF_RATE
 
 
 def grids(world):
@@ -36,6 +36,10 @@ def grids(world):
     g["tsweep"] = [("pong64", 32, t + 2, cf, "weak", f"T={t}, CF {'on' if cf else 'off'}")
                    for t in (1, 2, 4, 8, 16, 24, 40) for cf in (False, True)]
     g["tsweep_short"] = [("pong64", 32, t + 2, True, "weak", f"T={t}, CF on") for t in (8, 40)]
+    # BASELINE configs[4]: rollout length x counterfactual batch multiplier (counterfactual_horizon k: k - 1 extra
+    # Transition calls per CF branch, folded into the rollout batch = up to 3 B samples per call on CF iterations)
+    g["tsweep_cf"] = [("pong64", 32, t + 2, True, "weak", f"T={t}, CF on, counterfactual_horizon={k}", k)
+                      for t in (1, 4, 8, 16, 40) for k in (1, 2, 3)]
     return g
 
 
@@ -73,7 +77,9 @@ def main():
     todo = []
     for name in args.grid.split(","):
         todo += grids(world)[name]
-    for workload, B, Hn, cf, scaling, note in todo:
+    for entry in todo:
+        workload, B, Hn, cf, scaling, note = entry[:6]
+        CF_HORIZON = entry[6] if len(entry) > 6 else bench.CF_HORIZON
         C, H, W, A, Rw = bench.WORKLOADS[workload]
         T = Hn - 2
         nets = build_nets(C, A, Rw, seed=0)
