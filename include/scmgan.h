@@ -123,6 +123,10 @@ typedef struct {
                                   are GENERATED while the producer stages the im2col tile (x = -1 + 2w/W, y = -1 + 2h/H,
                                   zero in the padding halo); the plane holds zeros there.  Needs cin == 16, W <= 69 and a
                                   zero-padded plane; wider layers materialise the channels with scmgan_pack_coords. */
+    int weights_stable;        /* 1: the caller guarantees that `w` was last written at least two kernel launches before this
+                                  call in stream order (e.g. data-gradient operands packed during the forward pass): the
+                                  CTA-pair kernel may then load its resident weights before griddepcontrol.wait, i.e. while
+                                  the preceding kernel drains.  0: the library decides from its own launch bookkeeping. */
 } scmgan_conv_desc;
 int scmgan_conv3x3_fwd(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);
 int scmgan_conv3x3_dgrad(const scmgan_conv_desc* desc_host, scmgan_stream_t stream);

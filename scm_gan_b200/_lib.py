@@ -34,7 +34,7 @@ class ConvDesc(C.Structure):
                 ("out_f32", C.c_void_p), ("n_valid", C.c_int),
                 ("sample_out", C.c_void_p), ("uniforms", C.c_void_p), ("rng_state", C.c_void_p),
                 ("bias_n", C.c_int), ("x_fmt", C.c_int), ("w_fmt", C.c_int), ("out_fmt", C.c_int),
-                ("sample_scale", C.c_void_p), ("coord_c1", C.c_int)]
+                ("sample_scale", C.c_void_p), ("coord_c1", C.c_int), ("weights_stable", C.c_int)]
 
 
 class DecoderBceDesc(C.Structure):

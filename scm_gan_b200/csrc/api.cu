@@ -143,9 +143,12 @@ static void note_launch(cudaStream_t st, bool is_pack) {
     }
     t_pack_since[slot] = is_pack ? 0 : t_pack_since[slot] + 1;
 }
-static bool prewait_weights_ok(cudaStream_t st) {
+static bool prewait_enabled() {
     static const bool off = [] { const char* e = getenv("SCMGAN_NO_PREWAIT"); return e && atoi(e); }();
-    if (off) return false;
+    return !off;
+}
+static bool prewait_weights_ok(cudaStream_t st) {
+    if (!prewait_enabled()) return false;
     for (int i = 0; i < 4; ++i)
         if (t_pack_used[i] && t_pack_stream[i] == st) return t_pack_since[i] >= 1;
     return false;  // unknown stream: be conservative
@@ -502,7 +505,7 @@ static int conv_impl_inner(const scmgan_conv_desc* d, cudaStream_t st) {
         const char* dbg = getenv("SCMGAN_DEBUG");
         P.debug = dbg ? atoi(dbg) : 0;
     }
-    P.prewait_weights = prewait_weights_ok(st) ? 1 : 0;
+    P.prewait_weights = (prewait_weights_ok(st) || (d->weights_stable && prewait_enabled())) ? 1 : 0;
     P.coord_c = d->coord_c1 - 1;
     if (d->coord_c1) {
         SCM_REQUIRE(d->coord_c1 > 0 && d->coord_c1 % 2 == 1 && d->coord_c1 + 1 <= d->cin,

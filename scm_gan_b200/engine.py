@@ -212,7 +212,9 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
     K.wgrad(DB, buf6, G6, B, H, W, cout=Lp, cin=cin6, dy_c_off=HID, g_s_co=cin6 * 9, g_s_ci=9, co_valid=L, defer=dr)
     with dr.side_section():
         K.plane_colsum(DB, HID, Lp, B, H, W, db=db6)
-    dg = dict(wrap=True, dgrad=True)
+    # (the dgrad operands wd were packed by this call's forward: stable long before the backward runs, which autograd
+    # drives from its own thread, where the library's launch bookkeeping cannot see the pack)
+    dg = dict(wrap=True, dgrad=True, weights_stable=True)
     K.conv3x3(DB, wd[5], B, H, W, cin=Lp, x_c_off=HID, out=DA, out_c_off=HID, gate=buf6, gate_c_off=0,
               sample_scale=rs(4), **dg)                                                                     # d pre5
     for s in range(S):
@@ -356,11 +358,11 @@ def encoder_backward(dz, z, saved, wbar, sigma, u, v, w4, sink=None):
         gb4 += db4[:L]
     _ready([6, 7])
     K.wgrad(d3, a2, G[2], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[2], defer=dr)
-    K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True)
+    K.conv3x3(d3, wd[1], B, H, W, cin=HID, out=d2, gate=a2, dgrad=True, weights_stable=True)
     dr.join()
     finish_layer(2)
     K.wgrad(d2, a1, G[1], B, H, W, cout=HID, cin=HID, g_s_co=HID * 9, g_s_ci=9, db=db[1], defer=dr)
-    K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True)
+    K.conv3x3(d2, wd[0], B, H, W, cin=HID, out=d1, gate=a1, dgrad=True, weights_stable=True)
     dr.join()
     finish_layer(1)
     K.wgrad(d1, xin, G[0], B, H, W, cout=HID, cin=Cp, g_s_co=cin * 9, g_s_ci=9, ci_valid=cin, db=db[0], defer=dr)

@@ -98,11 +98,15 @@ def packed_weight(n_pad, k_pad, device, dtype=None):
 def conv3x3(x_plane, w_packed, B, H, W, *, cin, x_c_off=0, scale=1.0, bias=None, sample_bias=None, sample_scale=None,
             act=ACT_NONE,
             out=None, out_c_off=0, wrap=False, add=None, add_c_off=0, gate=None, gate_c_off=0, out_f32=None,
-            n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False, coord_c=None):
+            n_valid=0, sample_out=None, uniforms=None, rng_state=None, dgrad=False, coord_c=None,
+            weights_stable=False):
+    """weights_stable: the caller guarantees that w_packed was written at least two launches ago in stream order (see
+    scmgan_conv_desc::weights_stable); the engine sets it for data-gradient operands, which are packed in the forward."""
     d = _conv_desc(x_plane, w_packed, B, H, W, cin=cin, x_c_off=x_c_off, scale=scale, bias=bias,
                    sample_bias=sample_bias, sample_scale=sample_scale, act=act, out=out, out_c_off=out_c_off, wrap=wrap,
                    add=add, add_c_off=add_c_off, gate=gate, gate_c_off=gate_c_off, out_f32=out_f32, n_valid=n_valid,
                    sample_out=sample_out, uniforms=uniforms, rng_state=rng_state, coord_c=coord_c)
+    d.weights_stable = int(bool(weights_stable))
     fn = L.lib().scmgan_conv3x3_dgrad if dgrad else L.lib().scmgan_conv3x3_fwd
     L.check(fn(C.byref(d), _stream()), "scmgan_conv3x3")
 
