@@ -100,19 +100,15 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
-    pdl_sync();  // everything above is CTA-local: it overlaps the previous kernel's tail
-    if (warp >= 2) {
-        for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kEpiWarps) s_bias[i] = (P.bias && n0 + i < P.bias_n) ? P.bias[n0 + i] : 0.f;
-    }
+    // Everything up to pdl_sync() is CTA-local or - with P.prewait_weights (weights packed at least two launches ago, see
+    // conv_igemm_v3.cuh) - the resident weight load: it overlaps the previous kernel's tail.
+    const bool early_b = P.prewait_weights != 0;
+    if (!early_b) pdl_sync();
     tc_fence_before();
-    __syncthreads();
+    __syncthreads();   // barriers initialised, TMEM allocated
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
     if (warp == 0) {
-        // ------------------------------ TMA producer ------------------------------
-        // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one
-        // elected lane issues.
         if (elect_one()) {
             // resident weights: [tap][chunk] tiles of n_cta rows
             mbar_arrive_expect_tx(b_full, uint32_t(9 * chunks * G.n_cta * RB));
@@ -122,6 +118,17 @@ conv3x3_igemm_v2_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid
                                 tap * G.n_total + n0);
         }
         __syncwarp();
+    }
+    if (early_b) pdl_sync();
+    if (warp >= 2) {
+        for (int i = threadIdx.x - 64; i < G.n_cta; i += 32 * kEpiWarps) s_bias[i] = (P.bias && n0 + i < P.bias_n) ? P.bias[n0 + i] : 0.f;
+    }
+    __syncthreads();   // s_bias
+
+    if (warp == 0) {
+        // ------------------------------ TMA producer ------------------------------
+        // The whole warp runs the loop (warp-uniform control flow keeps addresses in uniform registers); one
+        // elected lane issues.
         int stage = 0;
         uint32_t phase = 0;
         if (CK == 16 && G.a_soft) {

@@ -244,7 +244,7 @@ def transition_backward(dz_next, p, a, saved, wbar, sigma, u, v, w6, sink=None):
             K.plane_colsum(seg(d1, s), 0, HID, Bs, H, W, S=S1s[s], db=dbs[s][0])
             K.action_wgrad(S1s[s], a[s * Bs:(s + 1) * Bs], L, Gs[s][0])
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
-    K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True)
+    K.conv3x3(d1, wd[0], B, H, W, cin=HID, out_f32=dz, n_valid=L, dgrad=True, weights_stable=True)
     # spectral norm backward with the u, v currently held by the module (= last forward call)
     dr.join()
     dwbar = [torch.empty_like(w) if gw[i] is None else None for i, w in enumerate(wbar)]
@@ -481,7 +481,7 @@ def decoder_backward(dlogits, saved, w1, w2, sink=None, d2=None):
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=9, g_s_ci=hid * 9, flip=True, co_valid=hid, ci_valid=L,
             db=db1, defer=dr)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
-    K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True)
+    K.conv3x3(d1, wd1, B, H, W, cin=hid, out_f32=dz, n_valid=L, dgrad=True, weights_stable=True)
     dr.join()
     if sink[1] is not None and db1 is not sink[1]:
         sink[1].add_(db1[:hid])
@@ -559,7 +559,7 @@ def reward_backward(dr, saved, w1, w2, sink=None):
     K.conv3x3(d2, wd2, B, H, W, cin=16, out=d1, gate=hidp, dgrad=True)
     K.wgrad(d1, zin, g1, B, H, W, cout=HID, cin=Lp, g_s_co=L * 9, g_s_ci=9, co_valid=RHID, ci_valid=L, db=db1, defer=red)
     dz = torch.empty((B, L, H, W), dtype=torch.float32, device=dev)
-    K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True)
+    K.conv3x3(d1, wd1, B, H, W, cin=RHID, out_f32=dz, n_valid=L, dgrad=True, weights_stable=True)
     red.join()
     if sink[3] is not None:
         sink[3].add_(db2[:co])
