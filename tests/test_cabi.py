@@ -68,10 +68,14 @@ def test_struct_layouts_match_header_sizes(lib, tmp_path):
         pytest.skip("gcc not available")
     pairs = {"PackJob": "scmgan_pack_job", "ConvDesc": "scmgan_conv_desc", "WgradReduceJob": "scmgan_wgrad_reduce_job",
              "WgradDesc": "scmgan_wgrad_desc", "SnLayer": "scmgan_sn_layer", "SnBwdLayer": "scmgan_sn_bwd_layer",
-             "CsrnSweepDesc": "scmgan_csrn_sweep_desc", "AdamChunk": "scmgan_adam_chunk"}
+             "CsrnSweepDesc": "scmgan_csrn_sweep_desc", "AdamChunk": "scmgan_adam_chunk",
+             "ReplayDesc": "scmgan_replay_desc", "DecoderBceDesc": "scmgan_decoder_bce_desc"}
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     body = "".join(f'  printf("{py} %zu %zu\\n", sizeof({c}), offsetof({c}, {getattr(lib, py)._fields_[-1][0]}));\n'
                    for py, c in pairs.items())
+    # ... and every single field offset (a reordered or mistyped field in the middle keeps size and last offset)
+    body += "".join(f'  printf("{py}.{f[0]} %zu 0\\n", offsetof({c}, {f[0]}));\n'
+                    for py, c in pairs.items() for f in getattr(lib, py)._fields_)
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "scmgan.h"\nint main(void) {\n' + body +
                    "  return 0; }\n")
@@ -83,6 +87,8 @@ def test_struct_layouts_match_header_sizes(lib, tmp_path):
         st = getattr(lib, py)
         last = getattr(st, st._fields_[-1][0])
         assert got[py] == (C.sizeof(st), last.offset), (py, got[py], C.sizeof(st), last.offset)
+        for f in st._fields_:
+            assert got[f"{py}.{f[0]}"][0] == getattr(st, f[0]).offset, (py, f[0])
 
 
 def test_header_is_plain_c(tmp_path):
