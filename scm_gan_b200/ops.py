@@ -302,6 +302,12 @@ def _decoder_bce_setup(ctx, inputs, output):
 def _decoder_bce_backward(ctx, grads):
     if grads[0] is None:
         return (None,) * 7
+    if getattr(ctx, "bce_consumed", False):
+        # the saved gradient plane is rescaled IN PLACE by the upstream gradient (scmgan_decoder_bce_bwd): a second
+        # backward through the same forward (retain_graph=True) would apply it twice
+        raise RuntimeError("scmgan::decoder_bce_seq supports one backward pass per forward (retain_graph is not "
+                           "supported by the fused loss head; use decoder() + scmgan::bce_logits_seq instead)")
+    ctx.bce_consumed = True
     sinks, mask = _sinks_of(ctx.params)
     out = torch.ops.scmgan.decoder_bce_seq_bwd(grads[0], list(ctx.saved_tensors), ctx.w1, ctx.w2, sinks, mask)
     g = _merge(out[1:], mask, 4)

@@ -648,3 +648,9 @@ def test_fused_decoder_loss_head(name):
         assert report(f"{name} fused dz", dz_f, dz_u, 4e-3)
         for n_, a, b in zip(("w1", "b1", "w2", "b2"), g_f, g_u):
             assert report(f"{name} fused d{n_}", a, b, 4e-3)
+    # the head rescales its saved gradient plane in place: a second backward through one forward is refused, not wrong
+    z = z0.clone().requires_grad_(True)
+    total = dec.pixel_loss_seq(z, tgt, mask).sum()
+    total.backward(retain_graph=True)
+    with pytest.raises(RuntimeError, match="one backward pass"):
+        total.backward()
